@@ -1,0 +1,843 @@
+"""CPU oracle: a numpy restatement of fenris's global operator assembly path.
+
+THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  The product (``fenris_b200``) never does and
+fails loudly when its CUDA library is missing.
+
+Every function restates one piece of the reference (InteractiveComputerGraphics/
+fenris @ 7181b15, v0.0.33) and cites the ``file:line`` it follows.  Paths are
+relative to the reference checkout.  The restatement is deliberately literal
+(same loop order, same accumulation order, same upper-triangle-then-mirror
+rule) so that it is the arbiter for parity; ``assemble_fast`` is a vectorised
+variant used only to reach larger meshes and is itself checked against the
+literal path in ``tests/test_oracle.py``.
+
+Parity pinning: the reference cannot be compiled here (no Rust toolchain), so
+the oracle is pinned against the reference's own golden vectors (pattern KATs,
+BCC tet mesh insta snapshots, Hex8->Hex27 single element test, Lame
+conversion, linear-elastic energy densities, reference Quad4 Laplace matrix)
+held in ``tests/golden/`` - see ``tests/golden/make_golden.py``.
+
+Third-party arithmetic that is NOT in the reference tree: nalgebra 0.32.1
+(``Cargo.toml:90``) ``determinant()`` / ``try_inverse()`` for 2x2 and 3x3
+matrices.  Its published closed forms (nalgebra ``src/linalg/determinant.rs``,
+``src/linalg/inverse.rs``) are restated in ``det_small`` / ``try_inverse_small``.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# Element type ids (shared with include/fenris_b200.h)
+# --------------------------------------------------------------------------
+QUAD4 = 1
+TET4 = 2
+HEX8 = 3
+HEX27 = 4
+TET10 = 5
+HEX20 = 6
+
+LAPLACE = 1
+LINEAR_ELASTIC = 2
+
+_ELEMENT_INFO = {
+    # type: (nodes, geometry nodes, dim)
+    QUAD4: (4, 4, 2),
+    TET4: (4, 4, 3),
+    HEX8: (8, 8, 3),
+    HEX27: (27, 8, 3),
+    TET10: (10, 4, 3),
+    HEX20: (20, 8, 3),
+}
+
+
+def element_info(elem_type: int) -> Tuple[int, int, int]:
+    return _ELEMENT_INFO[elem_type]
+
+
+# --------------------------------------------------------------------------
+# Quadrature  (fenris-quadrature)
+# --------------------------------------------------------------------------
+def _legendre(n: int, x: float) -> Tuple[float, float]:
+    """p_n(x), p_{n-1}(x) by the three-term recurrence.
+
+    fenris-quadrature/src/univariate.rs:22-36 (LegendreRecurrence::evaluate).
+    """
+    p1, p2 = 1.0, 0.0
+    for m in range(1, n + 1):
+        mf = float(m)
+        p3 = p2
+        p2 = p1
+        p1 = ((2.0 * mf - 1.0) * x * p2 - (mf - 1.0) * p3) / mf
+    return p1, p2
+
+
+def gauss(n: int) -> Tuple[List[float], List[float]]:
+    """Gauss rule on [-1, 1]: (weights, points), positive roots first.
+
+    fenris-quadrature/src/univariate.rs:66-117.
+    """
+    assert n > 0
+    m = (n + 1) // 2
+    points: List[float] = []
+    weights: List[float] = []
+    for i in range(m):
+        x = math.cos(math.pi * (i + 0.75) / (n + 0.5))
+        p1, p2 = _legendre(n, x)
+        dp = n * (x * p1 - p2) / (x * x - 1.0)
+        p = p1
+        while True:
+            dx = -p / dp
+            x += dx
+            p1, p2 = _legendre(n, x)
+            p = p1
+            dp = n * (x * p1 - p2) / (x * x - 1.0)
+            if abs(dx) <= 1e-15:
+                break
+        w = 2.0 / ((1.0 - x * x) * dp * dp)
+        points.append(x)
+        weights.append(w)
+    for i in range(m, n):
+        mirror = n - i - 1
+        points.append(-points[mirror])
+        weights.append(weights[mirror])
+    return weights, points
+
+
+def quadrilateral_gauss(n: int) -> Tuple[np.ndarray, np.ndarray]:
+    """fenris-quadrature/src/tensor.rs:13-32 (x outer, y inner)."""
+    w1, p1 = gauss(n)
+    w, p = [], []
+    for wx, x in zip(w1, p1):
+        for wy, y in zip(w1, p1):
+            w.append(wx * wy)
+            p.append([x, y])
+    return np.array(w), np.array(p)
+
+
+def hexahedron_gauss(n: int) -> Tuple[np.ndarray, np.ndarray]:
+    """fenris-quadrature/src/tensor.rs:36-58 (x outer, z inner, w = wx*wy*wz)."""
+    w1, p1 = gauss(n)
+    w, p = [], []
+    for wx, x in zip(w1, p1):
+        for wy, y in zip(w1, p1):
+            for wz, z in zip(w1, p1):
+                w.append(wx * wy * wz)
+                p.append([x, y, z])
+    return np.array(w), np.array(p)
+
+
+def tetrahedron_rule(strength: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Smallest polyquad tet rule with at least the given strength (only 1, 2).
+
+    fenris-quadrature/src/polyquad.rs:54-56 + build.rs:172-197, data
+    fenris-quadrature/rules/polyquad/expanded/tet/{1-1,2-4}.txt (38-digit
+    decimals rounded to f64 here exactly as Rust's f64 literal parser does).
+    """
+    if strength <= 1:
+        return np.array([1.3333333333333333333333333333333333333]), np.array([[-0.5, -0.5, -0.5]])
+    if strength == 2:
+        a = -0.72360679774997896964091736687312762354
+        b = 0.17082039324993690892275210061938287063
+        w = 0.33333333333333333333333333333333333333
+        return np.array([w, w, w, w]), np.array([[a, a, b], [a, b, a], [b, a, a], [a, a, a]])
+    raise NotImplementedError("only tet strengths 1 and 2 are on the hot path")
+
+
+def canonical_stiffness_rule(elem_type: int) -> Tuple[np.ndarray, np.ndarray]:
+    """src/quadrature/canonical.rs:95,102-104,110-112."""
+    if elem_type == QUAD4:
+        return quadrilateral_gauss(2)
+    if elem_type == HEX8:
+        return hexahedron_gauss(2)
+    if elem_type in (HEX27, HEX20):
+        return hexahedron_gauss(3)
+    if elem_type == TET4:
+        return tetrahedron_rule(1)
+    if elem_type == TET10:
+        return tetrahedron_rule(2)
+    raise ValueError(elem_type)
+
+
+# --------------------------------------------------------------------------
+# Reference elements (src/element*.rs)
+# --------------------------------------------------------------------------
+def _phi_lin(alpha: float, x: float) -> float:  # src/element.rs:246-253
+    return (1.0 + alpha * x) / 2.0
+
+
+def _dphi_lin(alpha: float) -> float:  # src/element.rs:258-263
+    return alpha / 2.0
+
+
+def _phi_quad(alpha: float, x: float) -> float:  # src/element.rs:272-281
+    a2 = alpha * alpha
+    return (3.0 / 2.0 * a2 - 1.0) * (x * x) + 0.5 * alpha * x + 1.0 - a2
+
+
+def _dphi_quad(alpha: float, x: float) -> float:  # src/element.rs:289-298
+    a2 = alpha * alpha
+    return 2.0 * (3.0 / 2.0 * a2 - 1.0) * x + 0.5 * alpha
+
+
+# node sign tables
+_QUAD4_NODES = [(-1.0, -1.0), (1.0, -1.0), (1.0, 1.0), (-1.0, 1.0)]  # quadrilateral.rs:84-89
+_HEX8_NODES = [  # hexahedron.rs:50-59
+    (-1.0, -1.0, -1.0), (1.0, -1.0, -1.0), (1.0, 1.0, -1.0), (-1.0, 1.0, -1.0),
+    (-1.0, -1.0, 1.0), (1.0, -1.0, 1.0), (1.0, 1.0, 1.0), (-1.0, 1.0, 1.0),
+]
+_HEX27_NODES = _HEX8_NODES + [  # hexahedron.rs:176-212 / :236-268
+    (0.0, -1.0, -1.0), (-1.0, 0.0, -1.0), (-1.0, -1.0, 0.0), (1.0, 0.0, -1.0),
+    (1.0, -1.0, 0.0), (0.0, 1.0, -1.0), (1.0, 1.0, 0.0), (-1.0, 1.0, 0.0),
+    (0.0, -1.0, 1.0), (-1.0, 0.0, 1.0), (1.0, 0.0, 1.0), (0.0, 1.0, 1.0),
+    (0.0, 0.0, -1.0), (0.0, -1.0, 0.0), (-1.0, 0.0, 0.0), (1.0, 0.0, 0.0),
+    (0.0, 1.0, 0.0), (0.0, 0.0, 1.0),
+    (0.0, 0.0, 0.0),
+]
+_TET4_GRADS = np.array([[-0.5, -0.5, -0.5], [0.5, 0.0, 0.0], [0.0, 0.5, 0.0], [0.0, 0.0, 0.5]]).T  # tetrahedron.rs:561-568
+_TET10_EDGES = [(0, 1), (1, 2), (0, 2), (0, 3), (2, 3), (1, 3)]  # tetrahedron.rs:236-241
+
+
+def tet4_basis(xi: Sequence[float]) -> np.ndarray:
+    """src/element/tetrahedron.rs:551-558."""
+    x, y, z = xi
+    return np.array([-0.5 * x - 0.5 * y - 0.5 * z - 0.5, 0.5 * x + 0.5, 0.5 * y + 0.5, 0.5 * z + 0.5])
+
+
+def hex8_basis(xi: Sequence[float]) -> np.ndarray:
+    """src/element/hexahedron.rs:43-60."""
+    return np.array([_phi_lin(a, xi[0]) * _phi_lin(b, xi[1]) * _phi_lin(c, xi[2]) for a, b, c in _HEX8_NODES])
+
+
+def reference_gradients(elem_type: int, xi: Sequence[float]) -> np.ndarray:
+    """Reference-basis gradients G_ref(xi), shape (d, n), column = node.
+
+    Quad4 src/element/quadrilateral.rs:94-107; Tet4 tetrahedron.rs:561-568;
+    Tet10 tetrahedron.rs:198-223; Hex8 hexahedron.rs:63-83; Hex27
+    hexahedron.rs:269-315.
+    """
+    if elem_type == QUAD4:
+        g = np.empty((2, 4))
+        for k, (a, b) in enumerate(_QUAD4_NODES):
+            g[0, k] = a * (1.0 + b * xi[1]) / 4.0
+            g[1, k] = b * (1.0 + a * xi[0]) / 4.0
+        return g
+    if elem_type == TET4:
+        return _TET4_GRADS.copy()
+    if elem_type == TET10:
+        psi = tet4_basis(xi)
+        g4 = _TET4_GRADS
+        cols = [g4[:, i] * (4.0 * psi[i] - 1.0) for i in range(4)]
+        cols += [g4[:, i] * (4.0 * psi[j]) + g4[:, j] * (4.0 * psi[i]) for i, j in _TET10_EDGES]
+        return np.stack(cols, axis=1)
+    if elem_type == HEX8:
+        g = np.empty((3, 8))
+        for k, (a, b, c) in enumerate(_HEX8_NODES):
+            g[0, k] = _dphi_lin(a) * _phi_lin(b, xi[1]) * _phi_lin(c, xi[2])
+            g[1, k] = _phi_lin(a, xi[0]) * _dphi_lin(b) * _phi_lin(c, xi[2])
+            g[2, k] = _phi_lin(a, xi[0]) * _phi_lin(b, xi[1]) * _dphi_lin(c)
+        return g
+    if elem_type == HEX27:
+        g = np.empty((3, 27))
+        for k, (a, b, c) in enumerate(_HEX27_NODES):
+            g[0, k] = _dphi_quad(a, xi[0]) * _phi_quad(b, xi[1]) * _phi_quad(c, xi[2])
+            g[1, k] = _phi_quad(a, xi[0]) * _dphi_quad(b, xi[1]) * _phi_quad(c, xi[2])
+            g[2, k] = _phi_quad(a, xi[0]) * _phi_quad(b, xi[1]) * _dphi_quad(c, xi[2])
+        return g
+    raise NotImplementedError(elem_type)
+
+
+def geometry_gradients(elem_type: int, xi: Sequence[float]) -> np.ndarray:
+    """Gradients of the GEOMETRY basis: Hex27/Hex20 use the embedded Hex8
+    (hexahedron.rs:318-335,546-563), Tet10 the embedded Tet4
+    (tetrahedron.rs:226-246); the others are isoparametric."""
+    if elem_type in (HEX27, HEX20):
+        return reference_gradients(HEX8, xi)
+    if elem_type == TET10:
+        return reference_gradients(TET4, xi)
+    return reference_gradients(elem_type, xi)
+
+
+def reference_jacobian(elem_type: int, X: np.ndarray, xi: Sequence[float]) -> np.ndarray:
+    """J = X * G^T with X (d x n_geom) holding the geometry vertices as columns.
+
+    hexahedron.rs:101-107, tetrahedron.rs:584-590, quadrilateral.rs:125-132.
+    The products are accumulated in node order, like nalgebra's small gemm.
+    """
+    G = geometry_gradients(elem_type, xi)
+    d, ng = G.shape
+    J = np.zeros((d, d))
+    for i in range(d):
+        for j in range(d):
+            acc = 0.0
+            for a in range(ng):
+                acc += X[i, a] * G[j, a]
+            J[i, j] = acc
+    return J
+
+
+# --------------------------------------------------------------------------
+# nalgebra 0.32.1 closed forms (third party; see module docstring)
+# --------------------------------------------------------------------------
+def det_small(m: np.ndarray) -> float:
+    """nalgebra src/linalg/determinant.rs (2x2, 3x3 closed forms)."""
+    if m.shape == (2, 2):
+        return m[0, 0] * m[1, 1] - m[1, 0] * m[0, 1]
+    if m.shape == (3, 3):
+        m11, m12, m13 = m[0]
+        m21, m22, m23 = m[1]
+        m31, m32, m33 = m[2]
+        minor_m12_m23 = m22 * m33 - m32 * m23
+        minor_m11_m23 = m21 * m33 - m31 * m23
+        minor_m11_m22 = m21 * m32 - m31 * m22
+        return m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22
+    raise ValueError(m.shape)
+
+
+def try_inverse_small(m: np.ndarray) -> Optional[np.ndarray]:
+    """nalgebra src/linalg/inverse.rs (2x2, 3x3 closed forms); None if det == 0."""
+    det = det_small(m)
+    if det == 0.0:
+        return None
+    if m.shape == (2, 2):
+        return np.array([[m[1, 1] / det, -m[0, 1] / det], [-m[1, 0] / det, m[0, 0] / det]])
+    m11, m12, m13 = m[0]
+    m21, m22, m23 = m[1]
+    m31, m32, m33 = m[2]
+    inv = np.empty((3, 3))
+    inv[0, 0] = (m22 * m33 - m32 * m23) / det
+    inv[0, 1] = (m13 * m32 - m33 * m12) / det
+    inv[0, 2] = (m12 * m23 - m22 * m13) / det
+    inv[1, 0] = -(m21 * m33 - m31 * m23) / det
+    inv[1, 1] = (m11 * m33 - m31 * m13) / det
+    inv[1, 2] = (m13 * m21 - m23 * m11) / det
+    inv[2, 0] = (m21 * m32 - m31 * m22) / det
+    inv[2, 1] = (m12 * m31 - m32 * m11) / det
+    inv[2, 2] = (m11 * m22 - m21 * m12) / det
+    return inv
+
+
+# --------------------------------------------------------------------------
+# Operators
+# --------------------------------------------------------------------------
+def lame_from_young_poisson(young: float, poisson: float) -> Tuple[float, float]:
+    """(mu, lambda). fenris-solid/src/materials.rs:31-43."""
+    mu = 0.5 * young / (1.0 + poisson)
+    lam = 2.0 * mu * poisson / (1.0 - 2.0 * poisson)
+    return mu, lam
+
+
+def linear_elastic_energy_density(F: np.ndarray, mu: float, lam: float) -> float:
+    """fenris-solid/src/materials.rs:80-84 (eps = sym(F) - I)."""
+    eps = 0.5 * (F + F.T) - np.eye(F.shape[0])
+    return mu * float(np.sum(eps * eps)) + 0.5 * lam * float(np.trace(eps)) ** 2
+
+
+def linear_elastic_stress(F: np.ndarray, mu: float, lam: float) -> np.ndarray:
+    """fenris-solid/src/materials.rs:86-95."""
+    d = F.shape[0]
+    eps = 0.5 * (F + F.T) - np.eye(d)
+    return eps * 2.0 * mu + np.eye(d) * (lam * np.trace(eps))
+
+
+def contract(op: int, a: np.ndarray, b: np.ndarray, params: Tuple[float, ...]) -> np.ndarray:
+    """The s x s contraction C(a, b) of one pair of physical basis gradients.
+
+    Laplace: a . b (1x1), src/assembly/operators/laplace.rs:60-68.
+    Linear elasticity: (I (a.b) + b a^T) mu + a b^T lambda,
+    fenris-solid/src/materials.rs:108-122 (F is ignored).
+    """
+    if op == LAPLACE:
+        return np.array([[float(np.dot(a, b))]])
+    if op == LINEAR_ELASTIC:
+        mu, lam = params
+        d = a.shape[0]
+        return (np.eye(d) * float(np.dot(a, b)) + np.outer(b, a)) * mu + np.outer(a, b) * lam
+    raise ValueError(op)
+
+
+def solution_dim(op: int, d: int) -> int:
+    return 1 if op == LAPLACE else d
+
+
+# --------------------------------------------------------------------------
+# Element matrix  (src/assembly/local/elliptic.rs:361-439)
+# --------------------------------------------------------------------------
+class SingularJacobian(Exception):
+    """`Err("Singular element Jacobian encountered")`, elliptic.rs:401-404."""
+
+
+def element_matrix(
+    elem_type: int,
+    X_elem: np.ndarray,
+    op: int,
+    weights: np.ndarray,
+    points: np.ndarray,
+    params_per_point: Sequence[Tuple[float, ...]],
+) -> np.ndarray:
+    """K_e, shape (s n, s n), local dof = s*I + i.
+
+    X_elem: (n, d) coordinates of ALL element nodes in local order (the
+    geometry uses the first n_geom of them).  Literal restatement of
+    assemble_element_elliptic_matrix (elliptic.rs:361-439) with the default
+    symmetric block loop (operators.rs:176-188 / fenris-solid lib.rs:381-391)
+    and the element-level mirror (util.rs:38-50).
+    """
+    n, ng, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    X = np.asarray(X_elem, dtype=np.float64)[:ng].T  # d x n_geom
+    K = np.zeros((s * n, s * n))
+    for w, xi, par in zip(weights, points, params_per_point):
+        J = reference_jacobian(elem_type, X, xi)
+        j_det = det_small(J)
+        j_inv = try_inverse_small(J)
+        if j_inv is None:
+            raise SingularJacobian("Singular element Jacobian encountered")
+        j_inv_t = j_inv.T
+        G = reference_gradients(elem_type, xi)
+        G = j_inv_t @ G  # elliptic.rs:415-418, column by column
+        scale = w * abs(j_det)  # elliptic.rs:422
+        for Jn in range(n):
+            for In in range(min(Jn + 1, n)):
+                c = contract(op, G[:, In], G[:, Jn], par)
+                K[s * In:s * In + s, s * Jn:s * Jn + s] += c * scale
+    # clone_upper_to_lower, util.rs:38-50
+    for j in range(s * n):
+        for i in range(j + 1, s * n):
+            K[i, j] = K[j, i]
+    return K
+
+
+# --------------------------------------------------------------------------
+# Pattern + serial scatter  (src/assembly/global.rs)
+# --------------------------------------------------------------------------
+def assemble_pattern(sdim: int, num_nodes: int, elements: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    """(row_offsets, col_indices) exactly as CsrAssembler::assemble_pattern.
+
+    src/assembly/global.rs:65-120.  `elements` may be ragged, may contain
+    empty elements and repeated nodes (KAT tests/unit_tests/assembly/global.rs:100-138).
+    """
+    node_sets: List[set] = [set() for _ in range(num_nodes)]
+    for nodes in elements:
+        for ni in nodes:
+            for nj in nodes:
+                node_sets[ni].add(nj)
+    offsets = [0]
+    cur = 0
+    for ns in node_sets:
+        for _ in range(sdim):
+            cur += sdim * len(ns)
+            offsets.append(cur)
+    cols: List[int] = []
+    for ns in node_sets:
+        buf = sorted(ns)
+        for _ in range(sdim):
+            for nj in buf:
+                for j in range(sdim):
+                    cols.append(sdim * nj + j)
+    assert offsets[-1] == len(cols)
+    return np.array(offsets, dtype=np.uint64), np.array(cols, dtype=np.uint64)
+
+
+def add_element_row_to_csr_row(row_values, row_cols, nodes, perm, dim, local_row) -> None:
+    """src/assembly/global.rs:504-537: cursor walk through the sorted CSR row."""
+    cursor = 0
+    ncols = len(row_cols)
+    for node_local in perm:
+        node_global = nodes[node_local]
+        for i in range(dim):
+            local_col = dim * node_local + i
+            global_col = dim * node_global + i
+            while cursor < ncols and row_cols[cursor] != global_col:
+                cursor += 1
+            if cursor >= ncols:
+                raise IndexError("Could not find column index associated with node in CSR row")
+            row_values[cursor] += local_row[local_col]
+            cursor += 1
+
+
+def scatter_element(values, row_offsets, col_indices, sdim, nodes, K) -> None:
+    """Per-element body of assemble_into_csr, src/assembly/global.rs:155-178."""
+    perm = sorted(range(len(nodes)), key=lambda i: nodes[i])
+    for local_node, global_node in enumerate(nodes):
+        for i in range(sdim):
+            lrow = sdim * local_node + i
+            grow = sdim * global_node + i
+            b, e = int(row_offsets[grow]), int(row_offsets[grow + 1])
+            add_element_row_to_csr_row(values[b:e], col_indices[b:e], nodes, perm, sdim, K[lrow, :])
+
+
+class Problem:
+    """The four borrowed ingredients of ElementEllipticAssembler (elliptic.rs:153-158):
+    space (mesh), operator, uniform quadrature table (+ per-point data); u = 0."""
+
+    def __init__(self, elem_type, vertices, connectivity, op, weights=None, points=None, params=None):
+        self.elem_type = elem_type
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.connectivity = np.ascontiguousarray(connectivity, dtype=np.int64)
+        self.op = op
+        if weights is None:
+            weights, points = canonical_stiffness_rule(elem_type)
+        self.weights = np.asarray(weights, dtype=np.float64)
+        self.points = np.asarray(points, dtype=np.float64)
+        n, ng, d = element_info(elem_type)
+        self.n, self.ng, self.d = n, ng, d
+        self.sdim = solution_dim(op, d)
+        if params is None:
+            params = ()
+        params = tuple(params)
+        # UniformQuadratureTable::with_uniform_data: same data at every point
+        # (quadrature_table.rs:264-266).  A list of per-point tuples is also accepted.
+        if len(params) > 0 and isinstance(params[0], (tuple, list)):
+            self.params_per_point = [tuple(p) for p in params]
+        else:
+            self.params_per_point = [params] * len(self.weights)
+
+    @property
+    def num_nodes(self):
+        return self.vertices.shape[0]
+
+    @property
+    def num_elements(self):
+        return self.connectivity.shape[0]
+
+    def element_matrix(self, e: int) -> np.ndarray:
+        nodes = self.connectivity[e]
+        return element_matrix(self.elem_type, self.vertices[nodes], self.op, self.weights, self.points,
+                              self.params_per_point)
+
+
+def assemble_serial(problem: Problem, pattern=None, values=None):
+    """CsrAssembler::assemble / assemble_into_csr (global.rs:124-182), literal."""
+    if pattern is None:
+        pattern = assemble_pattern(problem.sdim, problem.num_nodes, problem.connectivity.tolist())
+    row_offsets, col_indices = pattern
+    if values is None:
+        values = np.zeros(len(col_indices))
+    for e in range(problem.num_elements):
+        K = problem.element_matrix(e)
+        scatter_element(values, row_offsets, col_indices, problem.sdim, problem.connectivity[e].tolist(), K)
+    return row_offsets, col_indices, values
+
+
+def assemble_colored(problem: Problem, colors, pattern=None, values=None):
+    """CsrParAssembler::assemble_into_csr (global.rs:314-376): colours in order,
+    elements of a colour in label order (any order gives the same sums because
+    a colour's elements touch disjoint rows)."""
+    if pattern is None:
+        pattern = assemble_pattern(problem.sdim, problem.num_nodes, problem.connectivity.tolist())
+    row_offsets, col_indices = pattern
+    if values is None:
+        values = np.zeros(len(col_indices))
+    for color in colors:
+        for e in color:
+            K = problem.element_matrix(e)
+            scatter_element(values, row_offsets, col_indices, problem.sdim, problem.connectivity[e].tolist(), K)
+    return row_offsets, col_indices, values
+
+
+# --------------------------------------------------------------------------
+# Vectorised variant (same math, batched over elements) for larger meshes.
+# --------------------------------------------------------------------------
+def element_matrices_fast(problem: Problem) -> np.ndarray:
+    """All K_e at once, shape (E, s n, s n).  Same formula and the same
+    upper-triangle-then-mirror rule; only the summation order over nodes inside
+    J = X G^T and over quadrature points may differ in rounding."""
+    et, n, ng, d, s = problem.elem_type, problem.n, problem.ng, problem.d, problem.sdim
+    conn = problem.connectivity
+    E = conn.shape[0]
+    X = problem.vertices[conn[:, :ng]]  # E, ng, d
+    K = np.zeros((E, s * n, s * n))
+    for w, xi, par in zip(problem.weights, problem.points, problem.params_per_point):
+        Gg = geometry_gradients(et, xi)  # d, ng
+        J = np.einsum("eai,ja->eij", X, Gg)  # J[i,j] = sum_a X[a,i] G[j,a]
+        if d == 2:
+            det = J[:, 0, 0] * J[:, 1, 1] - J[:, 1, 0] * J[:, 0, 1]
+        else:
+            det = (J[:, 0, 0] * (J[:, 1, 1] * J[:, 2, 2] - J[:, 2, 1] * J[:, 1, 2])
+                   - J[:, 0, 1] * (J[:, 1, 0] * J[:, 2, 2] - J[:, 2, 0] * J[:, 1, 2])
+                   + J[:, 0, 2] * (J[:, 1, 0] * J[:, 2, 1] - J[:, 2, 0] * J[:, 1, 1]))
+        if np.any(det == 0.0):
+            raise SingularJacobian("Singular element Jacobian encountered")
+        Jinv = np.linalg.inv(J)
+        Gr = reference_gradients(et, xi)  # d, n
+        G = np.einsum("eji,jn->ein", Jinv, Gr)  # J^{-T} G_ref
+        scale = w * np.abs(det)
+        dots = np.einsum("eia,eib->eab", G, G)
+        if problem.op == LAPLACE:
+            K += scale[:, None, None] * dots
+        else:
+            mu, lam = par
+            # block (a,b) entry (i,j): mu (g_a.g_b delta_ij + g_b^i g_a^j) + lam g_a^i g_b^j
+            outer = np.einsum("eia,ejb->eaibj", G, G)  # g_a^i g_b^j
+            Kq = lam * outer + mu * np.transpose(outer, (0, 1, 4, 3, 2))
+            eye = np.eye(d)
+            Kq = Kq + mu * dots[:, :, None, :, None] * eye[None, None, :, None, :]
+            K += scale[:, None, None] * Kq.reshape(E, s * n, s * n)
+    iu = np.triu_indices(s * n, 1)
+    # block-upper-triangle rule: take everything on/above the scalar diagonal, mirror it
+    Ku = np.triu(K)
+    K = Ku + np.transpose(np.triu(K, 1), (0, 2, 1))
+    del iu
+    return K
+
+
+def assemble_fast(problem: Problem, pattern=None):
+    """Vectorised global assembly on the exact reference pattern."""
+    import scipy.sparse as sp
+
+    if pattern is None:
+        pattern = assemble_pattern_fast(problem.sdim, problem.num_nodes, problem.connectivity)
+    row_offsets, col_indices = pattern
+    s, n = problem.sdim, problem.n
+    K = element_matrices_fast(problem)
+    dofs = (problem.connectivity[:, :, None] * s + np.arange(s)[None, None, :]).reshape(-1, s * n)
+    rows = np.repeat(dofs, s * n, axis=1).ravel()
+    cols = np.tile(dofs, (1, s * n)).ravel()
+    nrows = s * problem.num_nodes
+    A = sp.coo_matrix((K.ravel(), (rows, cols)), shape=(nrows, nrows)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    # put onto the reference pattern (which may contain entries A lacks only if K has exact zeros dropped - it does not drop)
+    P = sp.csr_matrix((np.zeros(len(col_indices)), col_indices.astype(np.int64), row_offsets.astype(np.int64)),
+                      shape=(nrows, nrows))
+    assert np.array_equal(A.indptr, P.indptr) and np.array_equal(A.indices, P.indices), "pattern mismatch"
+    return row_offsets, col_indices, A.data.copy()
+
+
+def assemble_pattern_fast(sdim: int, num_nodes: int, connectivity: np.ndarray):
+    """Same output as assemble_pattern for uniform connectivity, via sort-unique."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    n = conn.shape[1]
+    I = np.repeat(conn, n, axis=1).ravel()
+    J = np.tile(conn, (1, n)).ravel()
+    key = np.unique(I * np.int64(num_nodes) + J)
+    bi = key // num_nodes
+    bj = key % num_nodes
+    counts = np.bincount(bi, minlength=num_nodes)
+    row_len = np.repeat(counts * sdim, sdim)
+    row_offsets = np.concatenate([[0], np.cumsum(row_len)]).astype(np.uint64)
+    # per node: block cols, expanded by sdim, repeated sdim times
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    cols = np.empty(int(row_offsets[-1]), dtype=np.uint64)
+    exp = (bj[:, None] * sdim + np.arange(sdim)[None, :]).ravel()  # per block sdim entries, node-major
+    pos = 0
+    estarts = starts * sdim
+    for node in range(num_nodes):
+        seg = exp[estarts[node]:estarts[node + 1]]
+        L = len(seg)
+        for _ in range(sdim):
+            cols[pos:pos + L] = seg
+            pos += L
+    return row_offsets, cols
+
+
+# --------------------------------------------------------------------------
+# Greedy colouring  (fenris-paradis/src/coloring.rs:6-70)
+# --------------------------------------------------------------------------
+def sequential_greedy_coloring(elements: Sequence[Sequence[int]]) -> List[List[int]]:
+    """Returns, per colour, the element labels in the order the reference stores them."""
+    colors: List[List[int]] = []
+    current = list(range(len(elements)))
+    last_visited = {}
+    c = 0
+    while current:
+        postponed: List[int] = []
+        members: List[int] = []
+        for e in current:
+            nodes = elements[e]
+            blocked = any(last_visited.get(nd, -1) == c for nd in nodes)
+            if blocked:
+                postponed.append(e)
+            else:
+                for nd in nodes:
+                    last_visited[nd] = c
+                members.append(e)
+        colors.append(members)
+        current = postponed
+        c += 1
+    return colors
+
+
+# --------------------------------------------------------------------------
+# Procedural meshes  (src/mesh/procedural.rs, src/mesh_convert.rs)
+# --------------------------------------------------------------------------
+def create_unit_square_uniform_quad_mesh_2d(cells_per_dim: int):
+    """src/mesh/procedural.rs:15-20,46-93 (top_left = (0, 1), rows go down)."""
+    if cells_per_dim == 0:
+        return np.zeros((0, 2)), np.zeros((0, 4), dtype=np.int64)
+    cell_size = 1.0 / cells_per_dim
+    nx = ny = cells_per_dim
+    verts = []
+    for j in range(ny + 1):
+        for i in range(nx + 1):
+            verts.append([0.0 + float(i) * cell_size, 1.0 + (-float(j)) * cell_size])
+    idx = lambda i, j: (nx + 1) * j + i
+    cells = []
+    for j in range(ny):
+        for i in range(nx):
+            cells.append([idx(i, j + 1), idx(i + 1, j + 1), idx(i + 1, j), idx(i, j)])
+    return np.array(verts), np.array(cells, dtype=np.int64)
+
+
+def create_rectangular_uniform_hex_mesh(unit_length: float, ux: int, uy: int, uz: int, cells_per_unit: int):
+    """src/mesh/procedural.rs:216-277."""
+    if cells_per_unit == 0 or ux == 0 or uy == 0:
+        return np.zeros((0, 3)), np.zeros((0, 8), dtype=np.int64)
+    h = unit_length / cells_per_unit
+    cx, cy, cz = ux * cells_per_unit, uy * cells_per_unit, uz * cells_per_unit
+    vx, vy, vz = cx + 1, cy + 1, cz + 1
+    k, j, i = np.meshgrid(np.arange(vz), np.arange(vy), np.arange(vx), indexing="ij")
+    verts = np.stack([i.ravel() * h, j.ravel() * h, k.ravel() * h], axis=1).astype(np.float64)
+    idx = lambda i, j, k: (vx * vy) * k + vx * j + i
+    k, j, i = np.meshgrid(np.arange(cz), np.arange(cy), np.arange(cx), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    cells = np.stack([idx(i, j, k), idx(i + 1, j, k), idx(i + 1, j + 1, k), idx(i, j + 1, k),
+                      idx(i, j, k + 1), idx(i + 1, j, k + 1), idx(i + 1, j + 1, k + 1), idx(i, j + 1, k + 1)],
+                     axis=1).astype(np.int64)
+    return verts, cells
+
+
+def create_unit_box_uniform_hex_mesh_3d(cells_per_dim: int):
+    """src/mesh/procedural.rs:30-35."""
+    return create_rectangular_uniform_hex_mesh(1.0, 1, 1, 1, cells_per_dim)
+
+
+_POS_FACE_DELTAS = [  # src/mesh/procedural.rs:331-335
+    [[1, 0, 1], [1, 1, 1], [1, 1, 0], [1, 0, 0]],
+    [[0, 1, 0], [1, 1, 0], [1, 1, 1], [0, 1, 1]],
+    [[0, 1, 1], [1, 1, 1], [1, 0, 1], [0, 0, 1]],
+]
+
+
+def create_rectangular_uniform_tet_mesh(unit_length: float, ux: int, uy: int, uz: int, cells_per_unit: int):
+    """BCC tet mesh, 12 tets per cell.  src/mesh/procedural.rs:286-403."""
+    if ux == 0 or uy == 0 or uz == 0 or cells_per_unit == 0:
+        return np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int64)
+    h = unit_length / float(cells_per_unit)
+    cx, cy, cz = ux * cells_per_unit, uy * cells_per_unit, uz * cells_per_unit
+    vx, vy, vz = cx + 1, cy + 1, cz + 1
+    verts = []
+    for k in range(vz):
+        for j in range(vy):
+            for i in range(vx):
+                verts.append([h * float(i), h * float(j), h * float(k)])
+    center_offset = len(verts)
+    for k in range(cz):
+        for j in range(cy):
+            for i in range(cx):
+                verts.append([h * (0.5 + float(i)), h * (0.5 + float(j)), h * (0.5 + float(k))])
+    vidx = lambda v: (vx * vy) * v[2] + vx * v[1] + v[0]
+    cidx = lambda c: (cx * cy) * c[2] + cx * c[1] + c[0] + center_offset
+    conn = []
+    ncells = [cx, cy, cz]
+    for k in range(cz):
+        for j in range(cy):
+            for i in range(cx):
+                cell = [i, j, k]
+                for axis in (0, 1, 2):
+                    if cell[axis] + 1 < ncells[axis]:
+                        # connect_centers_with_tets, :337-357
+                        face = [vidx([cell[0] + d[0], cell[1] + d[1], cell[2] + d[2]])
+                                for d in _POS_FACE_DELTAS[axis]]
+                        c1 = cidx(cell)
+                        nb = list(cell)
+                        nb[axis] += 1
+                        c2 = cidx(nb)
+                        cyc = face + [face[0]]
+                        for v1, v2 in zip(cyc[:-1], cyc[1:]):
+                            conn.append([c1, c2, v2, v1])
+                    for positive in (False, True):
+                        if (not positive and cell[axis] == 0) or (positive and cell[axis] + 1 == ncells[axis]):
+                            # make_pyramid, :359-384
+                            fv = [[cell[0] + d[0], cell[1] + d[1], cell[2] + d[2]] for d in _POS_FACE_DELTAS[axis]]
+                            if not positive:
+                                fv.reverse()
+                                for c in fv:
+                                    c[axis] -= 1
+                            a, b, c, dd = [vidx(v) for v in fv]
+                            center = cidx(cell)
+                            if (i + j + k) % 2 == 0:
+                                conn.append([a, b, c, center])
+                                conn.append([a, c, dd, center])
+                            else:
+                                conn.append([a, b, dd, center])
+                                conn.append([b, c, dd, center])
+    return np.array(verts, dtype=np.float64), np.array(conn, dtype=np.int64)
+
+
+def create_unit_box_uniform_tet_mesh_3d(cells_per_dim: int):
+    """src/mesh/procedural.rs:37-42."""
+    return create_rectangular_uniform_tet_mesh(1.0, 1, 1, 1, cells_per_dim)
+
+
+_HEX_EDGES = [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (4, 7), (5, 6), (6, 7)]  # mesh_convert.rs:118-129
+_HEX_FACES = [((0, 1, 2, 3), (0.0, 0.0, -1.0)), ((0, 1, 4, 5), (0.0, -1.0, 0.0)), ((0, 3, 4, 7), (-1.0, 0.0, 0.0)),
+              ((1, 2, 5, 6), (1.0, 0.0, 0.0)), ((2, 3, 6, 7), (0.0, 1.0, 0.0)), ((4, 5, 6, 7), (0.0, 0.0, 1.0))]  # :145-150
+_TET_EDGES = [(0, 1), (1, 2), (0, 2), (0, 3), (2, 3), (1, 3)]  # mesh_convert.rs:74-79
+
+
+def _relabel(local_children, vertices_out):
+    """Global labelling in first-seen order keyed by the sorted parent set.
+    src/mesh_convert.rs:227-330 (child index is always 0 for these refinements)."""
+    label = {}
+    final_vertices = []
+    conn = []
+    for elem in local_children:
+        row = []
+        for parents, coord in elem:
+            key = tuple(sorted(parents))
+            if key not in label:
+                label[key] = len(final_vertices)
+                final_vertices.append(coord)
+            row.append(label[key])
+        conn.append(row)
+    return np.array(final_vertices, dtype=np.float64), np.array(conn, dtype=np.int64)
+
+
+def hex27_mesh_from_hex8(vertices: np.ndarray, hex8: np.ndarray):
+    """Hex27Mesh::from(&hex8_mesh).  src/mesh_convert.rs:85-166 + :227-330."""
+    out = []
+    for nodes in hex8.tolist():
+        Xe = vertices[nodes]  # 8 x 3
+        elem = [((g,), Xe[l].copy()) for l, g in enumerate(nodes)]
+        for a, b in _HEX_EDGES:
+            # lerp(t=0.5): nalgebra axpy -> 0.5*b + 0.5*a
+            elem.append(((nodes[a], nodes[b]), 0.5 * Xe[b] + 0.5 * Xe[a]))
+        for face, ref in _HEX_FACES:
+            N = hex8_basis(ref)
+            elem.append((tuple(nodes[f] for f in face), Xe.T @ N))
+        elem.append((tuple(nodes), Xe.T @ hex8_basis((0.0, 0.0, 0.0))))
+        out.append(elem)
+    return _relabel(out, None)
+
+
+def tet10_mesh_from_tet4(vertices: np.ndarray, tet4: np.ndarray):
+    """Tet10Mesh::from(&tet4_mesh).  src/mesh_convert.rs:42-83 + :227-330."""
+    out = []
+    for nodes in tet4.tolist():
+        Xe = vertices[nodes]
+        elem = [((g,), Xe[l].copy()) for l, g in enumerate(nodes)]
+        for a, b in _TET_EDGES:
+            elem.append(((nodes[a], nodes[b]), 0.5 * Xe[b] + 0.5 * Xe[a]))
+        out.append(elem)
+    return _relabel(out, None)
+
+
+# --------------------------------------------------------------------------
+# Helpers used by tests / bench
+# --------------------------------------------------------------------------
+def rel_frobenius(a: np.ndarray, b: np.ndarray) -> float:
+    """||a - b||_F / ||b||_F on identical patterns (SURVEY 8d parity metric)."""
+    nb = float(np.linalg.norm(b))
+    return float(np.linalg.norm(a - b)) / (nb if nb > 0 else 1.0)
+
+
+def jitter_vertices(vertices: np.ndarray, h: float, seed: int = 12345, amp: float = 0.2) -> np.ndarray:
+    """Robustness input of SURVEY 8d: every vertex moved by U(-amp h, amp h) (PCG64)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return vertices + rng.uniform(-amp * h, amp * h, size=vertices.shape)
