@@ -1,0 +1,436 @@
+"""Host-side mirror of the reference's operator/assembler interface for the assembly hot path.
+
+Same names, argument meaning and error behaviour as the Rust reference so that the parity tests read like the
+reference's own tests (file:line = InteractiveComputerGraphics/fenris @ 7181b15):
+
+    Mesh / procedural generators            src/mesh.rs:23-40, src/mesh/procedural.rs
+    UniformQuadratureTable                  src/assembly/local/quadrature_table.rs:213-298
+    LaplaceOperator                         src/assembly/operators/laplace.rs:14
+    LameParameters / YoungPoisson           fenris-solid/src/materials.rs:9-43
+    MaterialEllipticOperator(LinearElasticMaterial)   fenris-solid/src/lib.rs:412-508
+    ElementEllipticAssemblerBuilder         src/assembly/local/elliptic.rs:63-150
+    ElementConnectivityAssembler            src/assembly/local.rs:18-47
+    color_nodes                             src/assembly/global.rs:540-551
+    CsrAssembler / CsrParAssembler          src/assembly/global.rs:27-182 / 186-376
+
+Everything numerical happens in libfenris_b200.so on the GPU; this module only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as nat
+from ._native import Fb200Error, SingularJacobianError  # noqa: F401
+from .context import Context
+
+_NODES = {nat.QUAD4: 4, nat.TET4: 4, nat.HEX8: 8, nat.HEX27: 27, nat.TET10: 10}
+_DIM = {nat.QUAD4: 2, nat.TET4: 3, nat.HEX8: 3, nat.HEX27: 3, nat.TET10: 3}
+
+
+# ----------------------------------------------------------------------------- meshes
+class Mesh:
+    """Mesh<f64, D, C>: `vertices` (N x D, AoS) and `connectivity` (E x n usize)."""
+
+    def __init__(self, vertices: np.ndarray, connectivity: np.ndarray, element_type: int):
+        self.vertices_ = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.connectivity_ = np.ascontiguousarray(connectivity, dtype=np.uint64)
+        self.element_type = element_type
+        assert self.connectivity_.ndim == 2 and self.connectivity_.shape[1] == _NODES[element_type]
+        assert self.vertices_.ndim == 2 and self.vertices_.shape[1] == _DIM[element_type]
+
+    @staticmethod
+    def from_vertices_and_connectivity(vertices, connectivity, element_type):
+        return Mesh(vertices, connectivity, element_type)
+
+    def vertices(self):
+        return self.vertices_
+
+    def connectivity(self):
+        return self.connectivity_
+
+    # ElementConnectivityAssembler for Mesh (local.rs:49-75): solution_dim = 1
+    def solution_dim(self):
+        return 1
+
+    def num_elements(self):
+        return self.connectivity_.shape[0]
+
+    def num_nodes(self):
+        return self.vertices_.shape[0]
+
+    def element_node_count(self, i):
+        return self.connectivity_.shape[1]
+
+    def populate_element_nodes(self, output, i):
+        output[:] = self.connectivity_[i]
+
+
+def _gen(fn, dims, h, n_per_elem, dim, element_type):
+    L = nat.lib()
+    nv, ne = C.c_uint64(0), C.c_uint64(0)
+    st = fn(*dims, C.c_double(h), C.byref(nv), C.byref(ne), None, None)
+    if st != nat.OK:
+        raise Fb200Error(st, "mesh generator failed")
+    v = np.zeros((nv.value, dim))
+    c = np.zeros((ne.value, n_per_elem), dtype=np.uint64)
+    if nv.value and ne.value:
+        st = fn(*dims, C.c_double(h), C.byref(nv), C.byref(ne), nat.ptr(v), nat.ptr(c))
+        if st != nat.OK:
+            raise Fb200Error(st, "mesh generator failed")
+    del L
+    return Mesh(v, c, element_type)
+
+
+def create_rectangular_uniform_hex_mesh(unit_length: float, units_x: int, units_y: int, units_z: int, cells_per_unit: int) -> Mesh:
+    """src/mesh/procedural.rs:216-277"""
+    if cells_per_unit == 0:
+        return Mesh(np.zeros((0, 3)), np.zeros((0, 8), dtype=np.uint64), nat.HEX8)
+    h = unit_length / cells_per_unit
+    return _gen(nat.lib().fb200_gen_hex_mesh, (units_x * cells_per_unit, units_y * cells_per_unit, units_z * cells_per_unit), h, 8, 3, nat.HEX8)
+
+
+def create_unit_box_uniform_hex_mesh_3d(cells_per_dim: int) -> Mesh:
+    """src/mesh/procedural.rs:30-35"""
+    return create_rectangular_uniform_hex_mesh(1.0, 1, 1, 1, cells_per_dim)
+
+
+def create_rectangular_uniform_tet_mesh(unit_length: float, units_x: int, units_y: int, units_z: int, cells_per_unit: int) -> Mesh:
+    """src/mesh/procedural.rs:286-403"""
+    if cells_per_unit == 0:
+        return Mesh(np.zeros((0, 3)), np.zeros((0, 4), dtype=np.uint64), nat.TET4)
+    h = unit_length / float(cells_per_unit)
+    return _gen(nat.lib().fb200_gen_tet_mesh, (units_x * cells_per_unit, units_y * cells_per_unit, units_z * cells_per_unit), h, 4, 3, nat.TET4)
+
+
+def create_unit_box_uniform_tet_mesh_3d(cells_per_dim: int) -> Mesh:
+    """src/mesh/procedural.rs:37-42"""
+    return create_rectangular_uniform_tet_mesh(1.0, 1, 1, 1, cells_per_dim)
+
+
+def create_unit_square_uniform_quad_mesh_2d(cells_per_dim: int) -> Mesh:
+    """src/mesh/procedural.rs:15-20"""
+    if cells_per_dim == 0:
+        return Mesh(np.zeros((0, 2)), np.zeros((0, 4), dtype=np.uint64), nat.QUAD4)
+    return _gen(nat.lib().fb200_gen_quad_mesh, (cells_per_dim, cells_per_dim), 1.0 / cells_per_dim, 4, 2, nat.QUAD4)
+
+
+def hex27_mesh_from(hex8_mesh: Mesh) -> Mesh:
+    """Hex27Mesh::from(&hex8_mesh), src/mesh_convert.rs:85-166,227-330"""
+    assert hex8_mesh.element_type == nat.HEX8
+    L = nat.lib()
+    v, c = hex8_mesh.vertices_, hex8_mesh.connectivity_
+    n27 = C.c_uint64(0)
+    st = L.fb200_hex27_from_hex8(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n27), None, None)
+    if st != nat.OK:
+        raise Fb200Error(st, "hex27 conversion failed")
+    v27 = np.zeros((n27.value, 3))
+    c27 = np.zeros((len(c), 27), dtype=np.uint64)
+    st = L.fb200_hex27_from_hex8(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n27), nat.ptr(v27), nat.ptr(c27))
+    if st != nat.OK:
+        raise Fb200Error(st, "hex27 conversion failed")
+    return Mesh(v27, c27, nat.HEX27)
+
+
+# ----------------------------------------------------------------------------- quadrature tables / operators
+def canonical_stiffness_quadrature(element_type: int):
+    """(weights, points) of the element's CanonicalStiffnessQuadrature, src/quadrature/canonical.rs:95-112"""
+    L = nat.lib()
+    n = C.c_int32(0)
+    st = L.fb200_canonical_quadrature(element_type, C.byref(n), None, None)
+    if st != nat.OK:
+        raise Fb200Error(st, "no canonical quadrature for this element type")
+    w = np.zeros(n.value)
+    p = np.zeros((n.value, _DIM[element_type]))
+    L.fb200_canonical_quadrature(element_type, C.byref(n), nat.ptr(w), nat.ptr(p))
+    return w, p
+
+
+@dataclass
+class LameParameters:
+    mu: float = 0.0
+    lambda_: float = 0.0
+
+    @staticmethod
+    def from_young_poisson(yp: "YoungPoisson") -> "LameParameters":
+        mu, lam = C.c_double(0), C.c_double(0)
+        nat.lib().fb200_lame_from_young_poisson(yp.young, yp.poisson, C.byref(mu), C.byref(lam))
+        return LameParameters(mu.value, lam.value)
+
+
+@dataclass
+class YoungPoisson:
+    young: float
+    poisson: float
+
+
+class UniformQuadratureTable:
+    def __init__(self, points, weights, data=None):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.weights = np.ascontiguousarray(weights, dtype=np.float64)
+        assert len(self.points) == len(self.weights), "points and weights must have the same length"
+        self.data = data  # None (= ()) or list of LameParameters per point
+
+    @staticmethod
+    def from_points_and_weights(points, weights):
+        return UniformQuadratureTable(points, weights, None)
+
+    @staticmethod
+    def from_quadrature(rule):
+        w, p = rule
+        return UniformQuadratureTable(p, w, None)
+
+    @staticmethod
+    def from_points_weights_and_data(points, weights, data):
+        assert len(data) == len(weights)
+        return UniformQuadratureTable(points, weights, list(data))
+
+    def with_uniform_data(self, data):
+        return UniformQuadratureTable(self.points, self.weights, [data] * len(self.weights))
+
+
+class LaplaceOperator:
+    kind = nat.LAPLACE
+
+    def solution_dim(self, geometry_dim):
+        return 1
+
+
+class LinearElasticMaterial:
+    pass
+
+
+class MaterialEllipticOperator:
+    """Wraps a hyperelastic material as an elliptic operator (fenris-solid/src/lib.rs:412-508).
+    Only LinearElasticMaterial has a device specialisation; anything else raises (no CPU fallback)."""
+
+    def __init__(self, material):
+        if not isinstance(material, LinearElasticMaterial) and material is not LinearElasticMaterial:
+            raise Fb200Error(nat.ERR_UNSUPPORTED, "only LinearElasticMaterial is specialised on the device (no CPU fallback)")
+        self.kind = nat.LINEAR_ELASTIC
+
+    def solution_dim(self, geometry_dim):
+        return geometry_dim
+
+
+class ElementConnectivityAssembler:
+    """A bare connectivity view (like the reference tests' MockElementAssembler)."""
+
+    def __init__(self, solution_dim: int, num_nodes: int, element_connectivities: Sequence[Sequence[int]]):
+        self._sdim, self._n, self._conn = solution_dim, num_nodes, [list(e) for e in element_connectivities]
+
+    def solution_dim(self):
+        return self._sdim
+
+    def num_elements(self):
+        return len(self._conn)
+
+    def num_nodes(self):
+        return self._n
+
+    def element_node_count(self, i):
+        return len(self._conn[i])
+
+    def populate_element_nodes(self, output, i):
+        output[:] = self._conn[i]
+
+
+class ElementEllipticAssembler:
+    def __init__(self, space: Mesh, op, qtable: UniformQuadratureTable, u):
+        self.space, self.op, self.qtable, self.u = space, op, qtable, u
+
+    # ElementConnectivityAssembler (elliptic.rs:160-187)
+    def solution_dim(self):
+        return self.op.solution_dim(_DIM[self.space.element_type])
+
+    def num_elements(self):
+        return self.space.num_elements()
+
+    def num_nodes(self):
+        return self.space.num_nodes()
+
+    def element_node_count(self, i):
+        return self.space.element_node_count(i)
+
+    def populate_element_nodes(self, output, i):
+        self.space.populate_element_nodes(output, i)
+
+    def _data(self):
+        if self.op.kind == nat.LAPLACE:
+            return None
+        if self.qtable.data is None:
+            raise Fb200Error(nat.ERR_SHAPE, "quadrature table carries no LameParameters")
+        return np.array([[d.mu, d.lambda_] for d in self.qtable.data], dtype=np.float64)
+
+    # ElementMatrixAssembler::assemble_element_matrix (local.rs:77-103)
+    def assemble_element_matrix(self, element_index: int, ctx: Optional[Context] = None) -> np.ndarray:
+        own = ctx is None
+        ctx = ctx or Context()
+        try:
+            ctx.space_upload(self.space.element_type, self.space.vertices_, self.space.connectivity_)
+            dofs = self.solution_dim() * _NODES[self.space.element_type]
+            return ctx.element_matrices(self.op.kind, self.qtable.weights, self.qtable.points, self._data(), element_index, 1, dofs)[0]
+        finally:
+            if own:
+                ctx.close()
+
+
+class ElementEllipticAssemblerBuilder:
+    """src/assembly/local/elliptic.rs:63-150"""
+
+    def __init__(self):
+        self._space = self._op = self._qt = self._u = None
+
+    def with_finite_element_space(self, space):
+        self._space = space
+        return self
+
+    def with_operator(self, op):
+        self._op = op
+        return self
+
+    def with_quadrature_table(self, qt):
+        self._qt = qt
+        return self
+
+    def with_u(self, u):
+        self._u = u
+        return self
+
+    def build(self) -> ElementEllipticAssembler:
+        assert self._space is not None and self._op is not None and self._qt is not None
+        if self._u is not None:
+            expected = self._op.solution_dim(_DIM[self._space.element_type]) * self._space.num_nodes()
+            assert len(self._u) == expected, "u has the wrong length"  # elliptic.rs:378-383
+        return ElementEllipticAssembler(self._space, self._op, self._qt, self._u)
+
+
+# ----------------------------------------------------------------------------- CSR containers / colours
+class SparsityPattern:
+    def __init__(self, major_offsets, minor_indices, nrows):
+        self.major_offsets, self.minor_indices, self.nrows = major_offsets, minor_indices, nrows
+
+    def nnz(self):
+        return len(self.minor_indices)
+
+
+class CsrMatrix:
+    """nalgebra_sparse::CsrMatrix<f64> as three arrays (usize, usize, f64)."""
+
+    def __init__(self, row_offsets, col_indices, values):
+        self.row_offsets, self.col_indices, self.values = row_offsets, col_indices, values
+
+    @staticmethod
+    def try_from_pattern_and_values(pattern: SparsityPattern, values):
+        assert len(values) == pattern.nnz()
+        return CsrMatrix(pattern.major_offsets, pattern.minor_indices, np.ascontiguousarray(values, dtype=np.float64))
+
+    def nrows(self):
+        return len(self.row_offsets) - 1
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        n = self.nrows()
+        return sp.csr_matrix((self.values, self.col_indices.astype(np.int64), self.row_offsets.astype(np.int64)), shape=(n, n))
+
+
+class DisjointSubsets:
+    """One colour: element labels whose node subsets are pairwise disjoint (fenris-paradis/src/lib.rs:171-181)."""
+
+    def __init__(self, labels):
+        self.labels_ = np.asarray(labels, dtype=np.uint64)
+
+    def labels(self):
+        return self.labels_
+
+
+def _upload(ctx: Context, assembler):
+    if isinstance(assembler, ElementEllipticAssembler):
+        ctx.space_upload(assembler.space.element_type, assembler.space.vertices_, assembler.space.connectivity_)
+    elif isinstance(assembler, Mesh):
+        ctx.space_upload(assembler.element_type, assembler.vertices_, assembler.connectivity_)
+    else:  # any ElementConnectivityAssembler
+        conn = []
+        for i in range(assembler.num_elements()):
+            buf = np.zeros(assembler.element_node_count(i), dtype=np.uint64)
+            assembler.populate_element_nodes(buf, i)
+            conn.append(buf.tolist())
+        ctx.connectivity_upload(assembler.num_nodes(), conn)
+
+
+def color_nodes(connectivity, ctx: Optional[Context] = None) -> List[DisjointSubsets]:
+    """src/assembly/global.rs:540-551 (sequential_greedy_coloring)."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        _upload(ctx, connectivity)
+        ctx.color_nodes()
+        offs, elems = ctx.colors_download(connectivity.num_elements())
+        return [DisjointSubsets(elems[int(offs[c]):int(offs[c + 1])]) for c in range(len(offs) - 1)]
+    finally:
+        if own:
+            ctx.close()
+
+
+class CsrAssembler:
+    """Serial reference semantics (global.rs:27-182); on the device the element loop is parallel with
+    f64 atomics (default) or the row-owner gather (scatter_mode)."""
+
+    def __init__(self, device: int = 0, scatter_mode: int = nat.SCATTER_ATOMIC):
+        self.ctx = Context(device)
+        self.scatter_mode = scatter_mode
+
+    def assemble_pattern(self, element_assembler) -> SparsityPattern:
+        _upload(self.ctx, element_assembler)
+        nrows, _ = self.ctx.assemble_pattern(element_assembler.solution_dim())
+        ro, ci = self.ctx.pattern_download()
+        return SparsityPattern(ro, ci, nrows)
+
+    def assemble(self, element_assembler: ElementEllipticAssembler) -> CsrMatrix:
+        pattern = self.assemble_pattern(element_assembler)
+        matrix = CsrMatrix.try_from_pattern_and_values(pattern, np.zeros(pattern.nnz()))
+        self._assemble_values(matrix, element_assembler, adopt=False)
+        return matrix
+
+    def assemble_into_csr(self, csr: CsrMatrix, element_assembler: ElementEllipticAssembler):
+        _upload(self.ctx, element_assembler)
+        self.ctx.pattern_adopt(element_assembler.solution_dim(), csr.row_offsets, csr.col_indices)
+        self._assemble_values(csr, element_assembler, adopt=True)
+
+    def _colors(self):
+        return None
+
+    def _assemble_values(self, csr: CsrMatrix, ea: ElementEllipticAssembler, adopt: bool):
+        mode = self.scatter_mode
+        colors = self._colors()
+        if colors is not None:
+            offs = np.zeros(len(colors) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(c.labels()) for c in colors])
+            elems = np.concatenate([c.labels() for c in colors]) if len(colors) else np.zeros(0, dtype=np.uint64)
+            self.ctx.colors_adopt(offs, elems)
+            mode = nat.SCATTER_COLORED
+        if len(csr.values) == 0:
+            return
+        self.ctx.assemble_into_csr(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), csr.values, scatter_mode=mode, accumulate=True)
+
+
+class CsrParAssembler(CsrAssembler):
+    """Coloured assembly (global.rs:186-376): one kernel launch per colour, plain read-modify-write."""
+
+    def __init__(self, device: int = 0):
+        super().__init__(device, nat.SCATTER_COLORED)
+        self._cols = None
+
+    def _colors(self):
+        return self._cols
+
+    def assemble(self, colors: Sequence[DisjointSubsets], element_assembler) -> CsrMatrix:  # type: ignore[override]
+        self._cols = list(colors)
+        return super().assemble(element_assembler)
+
+    def assemble_into_csr(self, csr: CsrMatrix, colors: Sequence[DisjointSubsets], element_assembler):  # type: ignore[override]
+        self._cols = list(colors)
+        super().assemble_into_csr(csr, element_assembler)

@@ -1,0 +1,205 @@
+"""Thin object wrapper over the C ABI (one fb200_ctx = one GPU + one stream)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from ._native import Fb200Error, SingularJacobianError
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._lib = nat.lib()
+        h = C.c_void_p()
+        st = self._lib.fb200_create(device, C.byref(h))
+        if st != nat.OK:
+            raise Fb200Error(st, "fb200_create failed: no usable CUDA device (fenris_b200 has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self._keep = []  # host arrays referenced by the last quadrature struct
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int):
+        if st == nat.OK:
+            return
+        buf = C.create_string_buffer(512)
+        elem = C.c_int64(-1)
+        self._lib.fb200_last_error(self._h, buf, 512, C.byref(elem))
+        msg = buf.value.decode() or self._lib.fb200_status_string(st).decode()
+        if st == nat.ERR_SINGULAR_JACOBIAN:
+            raise SingularJacobianError(st, msg, elem.value)
+        raise Fb200Error(st, msg, elem.value)
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        self._check(self._lib.fb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.fb200_synchronize(self._h))
+
+    def timer_begin(self):
+        self._check(self._lib.fb200_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._lib.fb200_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.fb200_launch_count(self._h))
+
+    # -- space
+    def space_upload(self, element_type: int, vertices: np.ndarray, connectivity: np.ndarray):
+        v = nat.as_f64(vertices)
+        c = nat.as_u64(connectivity)
+        self._check(self._lib.fb200_space_upload(self._h, element_type, v.shape[0], nat.ptr(v), c.shape[0], nat.ptr(c)))
+
+    def space_update_vertices(self, vertices: np.ndarray):
+        v = nat.as_f64(vertices)
+        self._check(self._lib.fb200_space_update_vertices(self._h, nat.ptr(v)))
+
+    def connectivity_upload(self, num_nodes: int, elements: Sequence[Sequence[int]]):
+        offs = np.zeros(len(elements) + 1, dtype=np.uint64)
+        if len(elements):
+            offs[1:] = np.cumsum([len(e) for e in elements])
+        flat = np.array([x for e in elements for x in e], dtype=np.uint64)
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.uint64)
+        self._check(self._lib.fb200_connectivity_upload(self._h, num_nodes, len(elements), nat.ptr(offs), nat.ptr(flat)))
+
+    def set_num_owned_elements(self, n: int):
+        self._check(self._lib.fb200_set_num_owned_elements(self._h, n))
+
+    # -- pattern
+    def assemble_pattern(self, solution_dim: int) -> Tuple[int, int]:
+        nrows, nnz = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.fb200_assemble_pattern(self._h, solution_dim, C.byref(nrows), C.byref(nnz)))
+        self.nrows, self.nnz = int(nrows.value), int(nnz.value)
+        return self.nrows, self.nnz
+
+    def pattern_download(self) -> Tuple[np.ndarray, np.ndarray]:
+        ro = np.zeros(self.nrows + 1, dtype=np.uint64)
+        ci = np.zeros(max(self.nnz, 1), dtype=np.uint64)
+        self._check(self._lib.fb200_pattern_download(self._h, nat.ptr(ro), nat.ptr(ci)))
+        return ro, ci[: self.nnz]
+
+    def pattern_adopt(self, solution_dim: int, row_offsets: np.ndarray, col_indices: np.ndarray):
+        ro, ci = nat.as_u64(row_offsets), nat.as_u64(col_indices)
+        if ci.size == 0:
+            ci = np.zeros(1, dtype=np.uint64)
+        self._check(self._lib.fb200_pattern_adopt(self._h, solution_dim, len(ro) - 1, nat.ptr(ro), nat.ptr(ci)))
+        self.nrows, self.nnz = len(ro) - 1, int(ro[-1])
+
+    # -- colours
+    def color_nodes(self) -> int:
+        n = C.c_uint64(0)
+        self._check(self._lib.fb200_color_nodes(self._h, C.byref(n)))
+        self.num_colors = int(n.value)
+        return self.num_colors
+
+    def colors_download(self, num_elements: int) -> Tuple[np.ndarray, np.ndarray]:
+        offs = np.zeros(self.num_colors + 1, dtype=np.uint64)
+        self._check(self._lib.fb200_colors_download(self._h, nat.ptr(offs), None))
+        elems = np.zeros(max(int(offs[-1]), 1), dtype=np.uint64)
+        self._check(self._lib.fb200_colors_download(self._h, None, nat.ptr(elems)))
+        return offs, elems[: int(offs[-1])]
+
+    def colors_adopt(self, color_offsets: np.ndarray, element_ids: np.ndarray):
+        o, e = nat.as_u64(color_offsets), nat.as_u64(element_ids)
+        if e.size == 0:
+            e = np.zeros(1, dtype=np.uint64)
+        self._check(self._lib.fb200_colors_adopt(self._h, len(o) - 1, nat.ptr(o), nat.ptr(e)))
+        self.num_colors = len(o) - 1
+
+    # -- assembly
+    def _structs(self, op_kind: int, weights, points, data):
+        w = nat.as_f64(weights)
+        p = nat.as_f64(points).reshape(len(w), -1)
+        d = None
+        if data is not None:
+            d = nat.as_f64(data)
+            if d.ndim == 1:
+                d = np.ascontiguousarray(np.tile(d, (len(w), 1)))
+            assert d.shape == (len(w), 2)
+        self._keep = [w, p, d]
+        q = nat.Quadrature(len(w), p.shape[1], w.ctypes.data_as(C.POINTER(C.c_double)), p.ctypes.data_as(C.POINTER(C.c_double)),
+                           d.ctypes.data_as(C.POINTER(C.c_double)) if d is not None else None)
+        return nat.Operator(op_kind), q
+
+    def assemble_into_csr_device(self, op_kind: int, weights, points, data=None, scatter_mode: int = nat.SCATTER_ATOMIC,
+                                 accumulate: bool = False):
+        op, q = self._structs(op_kind, weights, points, data)
+        self._check(self._lib.fb200_assemble_into_csr_device(self._h, C.byref(op), C.byref(q), None, scatter_mode, int(accumulate)))
+
+    def assemble_into_csr(self, op_kind: int, weights, points, data, values: np.ndarray, scatter_mode: int = nat.SCATTER_ATOMIC,
+                          accumulate: bool = True):
+        assert values.dtype == np.float64 and values.flags["C_CONTIGUOUS"] and values.size >= self.nnz
+        op, q = self._structs(op_kind, weights, points, data)
+        self._check(self._lib.fb200_assemble_into_csr(self._h, C.byref(op), C.byref(q), None, scatter_mode, int(accumulate), nat.ptr(values)))
+        return values
+
+    def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros(max(self.nnz, 1))
+        self._check(self._lib.fb200_values_download(self._h, nat.ptr(out)))
+        return out[: self.nnz]
+
+    def values_upload(self, values: np.ndarray):
+        v = nat.as_f64(values)
+        self._check(self._lib.fb200_values_upload(self._h, nat.ptr(v)))
+
+    def values_device_ptr(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64(0)
+        self._check(self._lib.fb200_values_device(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def element_matrices(self, op_kind: int, weights, points, data, first: int, count: int, dofs: int) -> np.ndarray:
+        op, q = self._structs(op_kind, weights, points, data)
+        out = np.zeros((max(count, 1), dofs, dofs))
+        self._check(self._lib.fb200_element_matrices(self._h, C.byref(op), C.byref(q), first, count, nat.ptr(out)))
+        # column-major per element -> numpy [e][row][col]
+        return np.transpose(out[:count], (0, 2, 1)).copy()
+
+    # -- multi GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = nat.lib().fb200_comm_unique_id(buf)
+        if st != nat.OK:
+            raise Fb200Error(st, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, num_ranks: int):
+        assert len(unique_id) == 128
+        self._check(self._lib.fb200_comm_init(self._h, unique_id, rank, num_ranks))
+
+    def interface_set(self, local_nodes: np.ndarray, packed_offsets: np.ndarray, packed_len: int):
+        n, o = nat.as_u64(local_nodes), nat.as_u64(packed_offsets)
+        cnt = len(n)
+        if cnt == 0:
+            n = np.zeros(1, dtype=np.uint64)
+            o = np.zeros(1, dtype=np.uint64)
+        self._check(self._lib.fb200_interface_set(self._h, cnt, nat.ptr(n), nat.ptr(o), packed_len))
+
+    def interface_allreduce(self):
+        self._check(self._lib.fb200_interface_allreduce(self._h))

@@ -1,0 +1,184 @@
+// Multi-GPU exchange step: the mesh is partitioned by elements (one rank = one GPU = one slab of elements);
+// rows of nodes on a partition interface receive contributions on several ranks and are summed with
+// ncclAllReduce over NVLink/NVSwitch on a packed buffer that holds ONLY those interface rows.
+// (The reference has no distributed path at all - README.md:58; this is the north-star extension.)
+//
+// NCCL is resolved at run time with dlopen so that the library shares whatever libnccl.so.2 the host process
+// (e.g. torch.distributed) already loaded, and so that single-GPU users need no NCCL at all.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include "fb200_internal.h"
+
+namespace fb200 {
+
+struct Id128 {  // ncclUniqueId (passed by value)
+    char bytes[FB200_UNIQUE_ID_BYTES];
+};
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl(std::string* why) {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // prefer the copy the process already has
+        if (h) break;
+    }
+    if (!h)
+        for (const char* n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+    if (!h) {
+        if (why) *why = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return false;
+    }
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+        if (why) *why = "libnccl.so.2 lacks required symbols";
+        return false;
+    }
+    g_nccl.handle = h;
+    return true;
+}
+
+static fb200_status nccl_fail(fb200_ctx* ctx, int code, const char* what) {
+    std::string m = std::string("NCCL error in ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "?");
+    return fail(ctx, FB200_ERR_NCCL, m);
+}
+
+// values of node row blocks <-> packed interface buffer
+template <bool PACK>
+__global__ void iface_copy_kernel(const int32_t* __restrict__ nodes, const int64_t* __restrict__ offsets, uint64_t count,
+                                  const int64_t* __restrict__ blk_off, int ss, double* values, double* packed) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t k = gwarp; k < count; k += nwarps) {
+        const int32_t node = nodes[k];
+        const int64_t b = blk_off[node];
+        const int64_t len = (blk_off[node + 1] - b) * ss;
+        double* v = values + b * ss;
+        double* pk = packed + offsets[k];
+        for (int64_t t = lane; t < len; t += 32) {
+            if (PACK) pk[t] = v[t]; else v[t] = pk[t];
+        }
+    }
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" {
+
+void fb200_comm_destroy_internal(fb200_ctx* ctx) {
+    if (ctx && ctx->nccl_comm && g_nccl.CommDestroy) {
+        g_nccl.CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+}
+
+fb200_status fb200_comm_unique_id(char id[FB200_UNIQUE_ID_BYTES]) {
+    std::string why;
+    if (!load_nccl(&why)) return FB200_ERR_NCCL;
+    Id128 tmp;
+    std::memset(&tmp, 0, sizeof(tmp));
+    const int rc = g_nccl.GetUniqueId(&tmp);
+    if (rc != 0) return FB200_ERR_NCCL;
+    std::memcpy(id, tmp.bytes, FB200_UNIQUE_ID_BYTES);
+    return FB200_OK;
+}
+
+fb200_status fb200_comm_init(fb200_ctx* ctx, const char id[FB200_UNIQUE_ID_BYTES], int32_t rank, int32_t num_ranks) {
+    if (!ctx) return FB200_ERR_STATE;
+    std::string why;
+    if (!load_nccl(&why)) return fail(ctx, FB200_ERR_NCCL, why);
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    fb200_comm_destroy_internal(ctx);
+    Id128 tmp;
+    std::memcpy(tmp.bytes, id, FB200_UNIQUE_ID_BYTES);
+    void* comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, num_ranks, tmp, rank);
+    if (rc != 0) return nccl_fail(ctx, rc, "ncclCommInitRank");
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = num_ranks;
+    return FB200_OK;
+}
+
+fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t* local_nodes, const uint64_t* packed_offsets,
+                                 uint64_t packed_len) {
+    if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_set needs a pattern");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    dev_free(ctx->d_iface_nodes);
+    dev_free(ctx->d_iface_offsets);
+    dev_free(ctx->d_iface_packed);
+    ctx->iface_count = 0;
+    ctx->iface_packed_len = 0;
+    // validate on the host against the block structure
+    std::vector<int64_t> off(ctx->N + 1);
+    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> nodes(count);
+    std::vector<int64_t> offs(count);
+    const uint64_t ss = (uint64_t)ctx->sdim * ctx->sdim;
+    for (uint64_t k = 0; k < count; ++k) {
+        if (local_nodes[k] >= ctx->N) return fail(ctx, FB200_ERR_INDEX_OOB, "interface node out of range");
+        const uint64_t len = (uint64_t)(off[local_nodes[k] + 1] - off[local_nodes[k]]) * ss;
+        if (packed_offsets[k] + len > packed_len) return fail(ctx, FB200_ERR_SHAPE, "interface row block exceeds the packed buffer");
+        nodes[k] = (int32_t)local_nodes[k];
+        offs[k] = (int64_t)packed_offsets[k];
+    }
+    FB200_TRY(dev_alloc(ctx, &ctx->d_iface_nodes, count));
+    FB200_TRY(dev_alloc(ctx, &ctx->d_iface_offsets, count));
+    FB200_TRY(dev_alloc(ctx, &ctx->d_iface_packed, packed_len));
+    if (count) {
+        FB200_CUDA(ctx, cudaMemcpy(ctx->d_iface_nodes, nodes.data(), count * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FB200_CUDA(ctx, cudaMemcpy(ctx->d_iface_offsets, offs.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    ctx->iface_count = count;
+    ctx->iface_packed_len = packed_len;
+    return FB200_OK;
+}
+
+fb200_status fb200_interface_allreduce(fb200_ctx* ctx) {
+    if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_allreduce needs a pattern");
+    if (ctx->nranks > 1 && !ctx->nccl_comm) return fail(ctx, FB200_ERR_STATE, "fb200_comm_init has not been called");
+    if (ctx->iface_packed_len == 0) return FB200_OK;
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int ss = ctx->sdim * ctx->sdim;
+    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(ctx->iface_count * 32, 256), (uint64_t)ctx->sm_count * 8));
+    FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_iface_packed, 0, ctx->iface_packed_len * sizeof(double), ctx->stream));
+    if (ctx->iface_count) {
+        iface_copy_kernel<true><<<blocks, 256, 0, ctx->stream>>>(ctx->d_iface_nodes, ctx->d_iface_offsets, ctx->iface_count, ctx->d_blk_off, ss,
+                                                                ctx->d_values, ctx->d_iface_packed);
+        FB200_TRY(check_launch(ctx, "iface_copy_kernel<pack>"));
+    }
+    if (ctx->nccl_comm) {
+        const int rc = g_nccl.AllReduce(ctx->d_iface_packed, ctx->d_iface_packed, ctx->iface_packed_len, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
+                                        ctx->nccl_comm, ctx->stream);
+        if (rc != 0) return nccl_fail(ctx, rc, "ncclAllReduce");
+    }
+    if (ctx->iface_count) {
+        iface_copy_kernel<false><<<blocks, 256, 0, ctx->stream>>>(ctx->d_iface_nodes, ctx->d_iface_offsets, ctx->iface_count, ctx->d_blk_off, ss,
+                                                                 ctx->d_values, ctx->d_iface_packed);
+        FB200_TRY(check_launch(ctx, "iface_copy_kernel<unpack>"));
+    }
+    return FB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// Internal definitions shared by the translation units of libfenris_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fenris_b200.h"
+
+namespace fb200 {
+
+constexpr int kMaxNodes = 27;
+constexpr int kMaxDim = 3;
+constexpr unsigned long long kNoError = ~0ull;
+
+struct ElementInfo {
+    int n;   // nodes per element
+    int ng;  // geometry nodes (sub-parametric high-order elements use the embedded linear element)
+    int d;   // geometry == reference dimension
+};
+bool element_info(int element_type, ElementInfo* out);
+
+// Host restatement of the reference-element gradient tables (see hostgen.cpp).
+void reference_gradients(int element_type, const double* xi, double* g /* [n*d], node-major */);
+int geometry_type(int element_type);
+
+// Device-side error word: [63:8] smallest offending element index, [7:0] status code. atomicMin keeps the first element.
+struct DeviceTables {
+    // layout (doubles): w[nq] | mu[nq] | lam[nq] | ggeo[nq*ng*d] | gref[nq*n*d]
+    double* d_data = nullptr;
+    std::vector<double> host;  // what is currently resident in d_data
+    size_t capacity = 0;  // doubles
+    int nq = 0;
+    bool uniform_params = true;
+    double mu0 = 0, lam0 = 0;
+};
+
+}  // namespace fb200
+
+struct fb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    std::string err;
+    int64_t err_elem = -1;
+    uint64_t launches = 0;
+
+    // ---- space
+    bool has_space = false;       // vertices + uniform connectivity
+    bool has_connectivity = false;  // any connectivity (uniform or ragged)
+    bool ragged = false;
+    int elem_type = 0;
+    fb200::ElementInfo ei{0, 0, 0};
+    uint64_t N = 0, E = 0, E_owned = 0;
+    double* d_vertices = nullptr;
+    int32_t* d_conn = nullptr;       // uniform: E*n ; ragged: flat node list
+    int64_t* d_elem_off = nullptr;   // ragged only: E+1
+    uint64_t conn_len = 0;           // total incidences
+
+    // ---- adjacency: node -> flat incidence indices k into d_conn (uniform: element = k / n, local node = k % n),
+    //      sorted ascending per node (deterministic)
+    int64_t* d_adj_off = nullptr;    // N+1
+    int32_t* d_adj_inc = nullptr;    // conn_len
+
+    // ---- pattern (node-block form; scalar CSR arrays are derived on download)
+    bool has_pattern = false;
+    bool adopted = false;
+    int sdim = 0;
+    uint64_t P = 0;                  // number of coupled node pairs (block nnz)
+    uint64_t nrows = 0, nnz = 0;
+    int64_t* d_blk_off = nullptr;    // N+1
+    int32_t* d_blk_cols = nullptr;   // P, sorted per node
+    uint16_t* d_blockmap = nullptr;  // uniform: E*n*n, position of node b in the block row of node a
+    int max_row_blocks = 0;
+
+    // ---- colours
+    bool has_colors = false;
+    std::vector<uint64_t> h_color_off;  // num_colors+1
+    std::vector<uint64_t> h_color_elems;
+    int32_t* d_color_elems = nullptr;   // E (owned elements only are launched)
+
+    // ---- values
+    double* d_values = nullptr;
+    uint64_t values_capacity = 0;
+
+    // ---- tables + deferred error word
+    fb200::DeviceTables tab;
+    unsigned long long* d_errword = nullptr;
+    unsigned long long* h_errword = nullptr;  // pinned
+
+    // ---- multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    uint64_t iface_count = 0, iface_packed_len = 0;
+    int32_t* d_iface_nodes = nullptr;
+    int64_t* d_iface_offsets = nullptr;
+    double* d_iface_packed = nullptr;
+};
+
+namespace fb200 {
+
+fb200_status fail(fb200_ctx* ctx, fb200_status s, const std::string& msg, int64_t elem = -1);
+fb200_status cuda_fail(fb200_ctx* ctx, cudaError_t e, const char* what);
+
+#define FB200_CUDA(ctx, call)                                                   \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return fb200::cuda_fail((ctx), _e, #call);       \
+    } while (0)
+
+#define FB200_TRY(call)                         \
+    do {                                        \
+        fb200_status _s = (call);               \
+        if (_s != FB200_OK) return _s;          \
+    } while (0)
+
+template <class T>
+fb200_status dev_alloc(fb200_ctx* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    return FB200_OK;
+}
+template <class T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// after a kernel launch
+fb200_status check_launch(fb200_ctx* ctx, const char* name);
+
+// pattern.cu
+fb200_status build_adjacency(fb200_ctx* ctx);
+void free_pattern(fb200_ctx* ctx);
+void free_space(fb200_ctx* ctx);
+fb200_status exclusive_scan_i64(fb200_ctx* ctx, int64_t* d_data, uint64_t count);  // in place, count elements
+
+// assemble.cu
+fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q);
+fb200_status read_errword(fb200_ctx* ctx);  // sync + translate deferred device errors
+
+inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace fb200

@@ -1,0 +1,191 @@
+/*
+ * fenris_b200.h - C ABI of the B200-native global operator/stiffness assembly path.
+ *
+ * This is the drop-in boundary for ONE hot path of InteractiveComputerGraphics/fenris (reference
+ * @ 7181b15): `CsrAssembler` / `CsrParAssembler` {assemble_pattern, assemble, assemble_into_csr}
+ * (src/assembly/global.rs:65,124,133,206,301,314) fed by an `ElementEllipticAssembler`
+ * (src/assembly/local/elliptic.rs:153-158) = { space: Mesh, operator, UniformQuadratureTable, u }.
+ * The reference has no FFI of its own (it is 100 % Rust); each entry point below names the
+ * reference item a Rust `-sys` shim would bind it to (see INTEGRATION.md for that shim).
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types; every function returns an fb200_status
+ *     (0 = OK) and never throws; details via fb200_last_error().
+ *   - indices at the boundary are uint64_t (Rust `usize`), scalars are double (every reference
+ *     call site instantiates T = f64); the device narrows indices to 32 bit and checks ranges.
+ *   - host pointers are borrowed for the duration of the call only; the context owns all
+ *     device memory.  A context is bound to one CUDA device and one stream and must not be
+ *     used from two host threads at once (CsrAssembler is likewise !Sync, global.rs:30).
+ *   - there is NO CPU fallback: unsupported element/operator combinations return
+ *     FB200_ERR_UNSUPPORTED, a missing GPU returns FB200_ERR_CUDA.
+ */
+#ifndef FENRIS_B200_H
+#define FENRIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_VERSION 1
+
+typedef int32_t fb200_status;
+enum {
+    FB200_OK = 0,
+    FB200_ERR_SINGULAR_JACOBIAN = 1,   /* eyre!("Singular element Jacobian encountered"), elliptic.rs:401-404 */
+    FB200_ERR_SHAPE = 2,               /* assert!s at elliptic.rs:378-391, global.rs:515-517 */
+    FB200_ERR_INDEX_OOB = 3,           /* connectivity index >= num_nodes (space_impl.rs:35,44 panics) */
+    FB200_ERR_COLUMN_NOT_IN_PATTERN = 4, /* "Could not find column index ...", global.rs:533 */
+    FB200_ERR_UNSUPPORTED = 5,         /* no specialisation and no CPU fallback */
+    FB200_ERR_CUDA = 6,
+    FB200_ERR_NCCL = 7,
+    FB200_ERR_STATE = 8,               /* call order violated (e.g. assemble before a pattern exists) */
+    FB200_ERR_COLORING = 9             /* adopted colours are not disjoint (DisjointSubsets::try_from..., fenris-paradis/src/lib.rs:184-220) */
+};
+
+/* Element types = the reference's connectivity newtypes (src/connectivity.rs:182,523,607,667,912). */
+enum {
+    FB200_QUAD4 = 1,  /* Quad4d2Connectivity  */
+    FB200_TET4 = 2,   /* Tet4Connectivity     */
+    FB200_HEX8 = 3,   /* Hex8Connectivity     */
+    FB200_HEX27 = 4,  /* Hex27Connectivity (geometry from the first 8 vertices, hexahedron.rs:318-335) */
+    FB200_TET10 = 5   /* Tet10Connectivity (geometry from the first 4 vertices, tetrahedron.rs:226-246) */
+};
+
+/* Operators = EllipticContraction implementors on the path. */
+enum {
+    FB200_LAPLACE = 1,        /* LaplaceOperator, src/assembly/operators/laplace.rs:14,60-72; Parameters = () */
+    FB200_LINEAR_ELASTIC = 2  /* MaterialEllipticOperator<LinearElasticMaterial>, fenris-solid/src/lib.rs:412-508,
+                                 materials.rs:108-122; Parameters = LameParameters{mu, lambda} */
+};
+
+/* How element contributions reach the CSR values. All three give the same sums up to fp reassociation. */
+enum {
+    FB200_SCATTER_ATOMIC = 0,  /* element-parallel, f64 atomic add (red.global.add.f64) */
+    FB200_SCATTER_COLORED = 1, /* CsrParAssembler semantics: one launch per colour, plain read-modify-write (global.rs:322-373) */
+    FB200_SCATTER_GATHER = 2   /* row-owner: each CSR value is produced by exactly one thread group, no atomics, deterministic */
+};
+
+typedef struct fb200_ctx fb200_ctx;
+
+/* UniformQuadratureTable<T, D, Data> (src/assembly/local/quadrature_table.rs:213-298):
+ * one rule + one data entry per point, shared by every element. */
+typedef struct fb200_quadrature {
+    int32_t num_points;
+    int32_t dim;            /* reference dimension (2 or 3) */
+    const double* weights;  /* [num_points] */
+    const double* points;   /* [num_points * dim], point-major */
+    const double* data;     /* operator Parameters per point: NULL for LAPLACE; [num_points * 2] = (mu, lambda) for LINEAR_ELASTIC
+                               (UniformQuadratureTable::with_uniform_data repeats one value, quadrature_table.rs:264-266) */
+} fb200_quadrature;
+
+typedef struct fb200_operator {
+    int32_t kind; /* FB200_LAPLACE | FB200_LINEAR_ELASTIC */
+} fb200_operator;
+
+/* ---- lifetime / errors ------------------------------------------------------------------ */
+fb200_status fb200_create(int32_t cuda_device, fb200_ctx** out);
+void fb200_destroy(fb200_ctx* ctx);
+const char* fb200_status_string(fb200_status s);
+/* Message of the last failure on ctx (NUL-terminated, truncated to len) and, for SINGULAR_JACOBIAN /
+ * INDEX_OOB / COLUMN_NOT_IN_PATTERN, the smallest offending element index (-1 otherwise). */
+fb200_status fb200_last_error(fb200_ctx* ctx, char* buf, size_t len, int64_t* element_index);
+int32_t fb200_abi_version(void);
+
+/* Adopt an external CUDA stream (e.g. torch's current stream) for all subsequent work; NULL = ctx-owned stream. */
+fb200_status fb200_set_stream(fb200_ctx* ctx, void* cuda_stream);
+fb200_status fb200_synchronize(fb200_ctx* ctx); /* waits, then reports deferred kernel errors (singular Jacobian ...) */
+/* cudaEvent pair on the ctx stream, for callers without a CUDA binding of their own. */
+fb200_status fb200_timer_begin(fb200_ctx* ctx);
+fb200_status fb200_timer_end(fb200_ctx* ctx, float* milliseconds); /* synchronizes */
+/* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
+uint64_t fb200_launch_count(fb200_ctx* ctx);
+
+/* ---- the space: Mesh<f64, D, C>  (src/mesh.rs:23-40) --------------------------------------- */
+/* vertices: num_nodes x d AoS (Vec<OPoint<f64,D>>); connectivity: num_elements x n row-major (Vec<C([usize; n])>).
+ * Implements ElementConnectivityAssembler for the mesh (local.rs:49-75) and the FiniteElementSpace gather. */
+fb200_status fb200_space_upload(fb200_ctx* ctx, int32_t element_type, uint64_t num_nodes, const double* vertices,
+                                uint64_t num_elements, const uint64_t* connectivity);
+/* Replace the vertex coordinates only (same sizes). */
+fb200_status fb200_space_update_vertices(fb200_ctx* ctx, const double* vertices);
+/* A bare ElementConnectivityAssembler (local.rs:18-47) with ragged elements (NestedVec layout:
+ * element_offsets[num_elements+1], element_nodes[]), e.g. the reference's MockElementAssembler
+ * (tests/unit_tests/assembly/global.rs:238-264).  Pattern and colouring only. */
+fb200_status fb200_connectivity_upload(fb200_ctx* ctx, uint64_t num_nodes, uint64_t num_elements,
+                                       const uint64_t* element_offsets, const uint64_t* element_nodes);
+/* Multi-GPU: only elements [0, num_owned) are assembled; the rest are ghosts that complete the
+ * sparsity pattern of interface rows.  Default: all owned. */
+fb200_status fb200_set_num_owned_elements(fb200_ctx* ctx, uint64_t num_owned);
+
+/* ---- CsrAssembler::assemble_pattern (global.rs:65-120 == 206-297) ------------------------- */
+fb200_status fb200_assemble_pattern(fb200_ctx* ctx, int32_t solution_dim, uint64_t* num_rows, uint64_t* nnz);
+/* Exactly the reference's SparsityPattern: offsets[num_rows+1], sorted col indices[nnz]. Either pointer may be NULL. */
+fb200_status fb200_pattern_download(fb200_ctx* ctx, uint64_t* row_offsets, uint64_t* col_indices);
+/* Use the caller's existing CsrMatrix pattern (assemble_into_csr on a matrix built elsewhere).  The pattern must be
+ * node-block structured (what assemble_pattern produces); otherwise FB200_ERR_UNSUPPORTED. Missing couplings are
+ * reported as FB200_ERR_COLUMN_NOT_IN_PATTERN (global.rs:533). */
+fb200_status fb200_pattern_adopt(fb200_ctx* ctx, int32_t solution_dim, uint64_t num_rows, const uint64_t* row_offsets,
+                                 const uint64_t* col_indices);
+
+/* ---- color_nodes (global.rs:540-551 -> fenris-paradis/src/coloring.rs:6-70) ---------------- */
+fb200_status fb200_color_nodes(fb200_ctx* ctx, uint64_t* num_colors);
+/* Vec<DisjointSubsets> flattened: color_offsets[num_colors+1], element labels per colour in reference order. */
+fb200_status fb200_colors_download(fb200_ctx* ctx, uint64_t* color_offsets, uint64_t* element_ids);
+fb200_status fb200_colors_adopt(fb200_ctx* ctx, uint64_t num_colors, const uint64_t* color_offsets, const uint64_t* element_ids);
+
+/* ---- assemble_into_csr (global.rs:133-182, 314-376) ---------------------------------------- */
+/* u: global solution vector (solution_dim * num_nodes) or NULL (= zeros, as every reference call site passes);
+ *    the in-scope operators are linear, so K does not depend on u (laplace.rs:62, materials.rs:110).
+ * accumulate != 0: values += contributions (assemble_into_csr);  == 0: values = contributions (assemble()).
+ * The _device form only enqueues work on the ctx stream (values stay in HBM; call fb200_synchronize to
+ * collect deferred errors).  The host form uploads `values` first when accumulating, waits, and copies
+ * the result back into `values` [nnz]. */
+fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature,
+                                            const double* u, int32_t scatter_mode, int32_t accumulate);
+fb200_status fb200_assemble_into_csr(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature,
+                                     const double* u, int32_t scatter_mode, int32_t accumulate, double* values);
+fb200_status fb200_values_device(fb200_ctx* ctx, double** device_ptr, uint64_t* nnz);
+fb200_status fb200_values_download(fb200_ctx* ctx, double* values);
+fb200_status fb200_values_upload(fb200_ctx* ctx, const double* values);
+/* Element matrices only (ElementMatrixAssembler::assemble_element_matrix, local.rs:77-103): K_e for elements
+ * [first, first+count), each (s n)^2 doubles column-major like nalgebra's DMatrix. Test/debug surface. */
+fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature,
+                                    uint64_t first, uint64_t count, double* out);
+
+/* ---- multi-GPU: element partition + interface-row exchange --------------------------------- */
+#define FB200_UNIQUE_ID_BYTES 128
+fb200_status fb200_comm_unique_id(char id[FB200_UNIQUE_ID_BYTES]);
+fb200_status fb200_comm_init(fb200_ctx* ctx, const char id[FB200_UNIQUE_ID_BYTES], int32_t rank, int32_t num_ranks);
+/* Interface nodes = local nodes whose rows also receive contributions on other ranks.  packed_offsets[i] is the
+ * position (in doubles) of node local_nodes[i]'s value block (solution_dim^2 * coupled-node-count doubles, identical on
+ * every sharing rank because ghosts complete the pattern) inside a packed buffer of packed_len doubles that has the same
+ * layout on every rank. */
+fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t* local_nodes, const uint64_t* packed_offsets,
+                                 uint64_t packed_len);
+/* pack interface rows -> ncclAllReduce(sum, f64) over NVLink -> unpack.  Enqueued on the ctx stream. */
+fb200_status fb200_interface_allreduce(fb200_ctx* ctx);
+
+/* ---- host-side helpers restating the reference's generators (no GPU needed) ----------------- */
+/* src/mesh/procedural.rs:216-277 / 286-403 / 46-93.  Call with vertices == NULL to query sizes. */
+fb200_status fb200_gen_hex_mesh(uint64_t cells_x, uint64_t cells_y, uint64_t cells_z, double cell_size,
+                                uint64_t* num_vertices, uint64_t* num_elements, double* vertices, uint64_t* connectivity);
+fb200_status fb200_gen_tet_mesh(uint64_t cells_x, uint64_t cells_y, uint64_t cells_z, double cell_size,
+                                uint64_t* num_vertices, uint64_t* num_elements, double* vertices, uint64_t* connectivity);
+fb200_status fb200_gen_quad_mesh(uint64_t cells_x, uint64_t cells_y, double cell_size,
+                                 uint64_t* num_vertices, uint64_t* num_elements, double* vertices, uint64_t* connectivity);
+/* Hex27Mesh::from(&hex8_mesh) (src/mesh_convert.rs:85-166,227-330). vertices27 needs capacity for the returned count
+ * (query with vertices27 == NULL). */
+fb200_status fb200_hex27_from_hex8(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* hex8,
+                                   uint64_t* num_vertices27, double* vertices27, uint64_t* hex27);
+/* Canonical stiffness quadrature of an element type (src/quadrature/canonical.rs:95,102-104,110-112):
+ * query num_points with weights == NULL. points are point-major [num_points * dim]. */
+fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_points, double* weights, double* points);
+/* LameParameters::from(YoungPoisson) (fenris-solid/src/materials.rs:31-43). */
+void fb200_lame_from_young_poisson(double young, double poisson, double* mu, double* lambda);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FENRIS_B200_H */
