@@ -390,3 +390,25 @@ def test_full_size_c2_tet_poisson(ctx):
         ctx.assemble_into_csr_device(fo.LAPLACE, w, p, None, scatter_mode=mode)
         ctx.synchronize()
         assert fo.rel_frobenius(ctx.values_download(), ref) < TOL
+
+
+# ------------------------------------------------------------------ the reference's own convergence goldens, end to end on the GPU matrix
+@pytest.mark.parametrize("name", ["quad4", "hex8", "tet4"])
+def test_mms_goldens_with_gpu_matrix(ctx, kats, name):
+    """tests/convergence_tests/poisson_{2d,3d}_mms.rs: assemble (GPU) -> Dirichlet -> solve -> L2/H1 errors within 1 % of the
+    reference's stored values (reference_values/*.json)."""
+    from tests import mms
+    et, producer, qrule, erule, key, resolutions = mms.CASES[name]
+    golden = kats["mms_summaries"][key]
+    for k, res in enumerate(resolutions):
+        v, c = producer(res)
+        w, p = qrule()
+        ctx.space_upload(et, v, c.astype(np.uint64))
+        ctx.assemble_pattern(1)
+        ro, ci = ctx.pattern_download()
+        ctx.assemble_into_csr_device(fo.LAPLACE, w, p, None, scatter_mode=fb.SCATTER_GATHER)
+        ctx.synchronize()
+        vals = ctx.values_download().copy()
+        l2, h1 = mms.solve_poisson(et, v, c, mms.csr_from(ro, ci, vals), qrule(), erule())
+        assert abs(l2 - golden["L2_errors"][k]) / golden["L2_errors"][k] < 0.01, (name, res, l2)
+        assert abs(h1 - golden["H1_seminorm_errors"][k]) / golden["H1_seminorm_errors"][k] < 0.01, (name, res, h1)
