@@ -1,4 +1,5 @@
 // Context lifetime, error plumbing, stream/timer helpers and the space (mesh) upload.
+#include <algorithm>
 #include <cstring>
 
 #include "fb200_internal.h"
@@ -38,8 +39,58 @@ void free_pattern(fb200_ctx* ctx) {
     ctx->sdim = 0;
 }
 
+// Locality-preserving visiting order: elements sorted by the Morton code of their centroid (host preprocessing, like
+// the colouring).  The assembled sums do not depend on the order; it only decides which CSR rows are live in L2 together.
+static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order) {
+    order.resize(E);
+    if (E == 0 || N == 0) return;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint64_t i = 0; i < N; ++i)
+        for (int k = 0; k < d; ++k) {
+            lo[k] = std::min(lo[k], v[i * d + k]);
+            hi[k] = std::max(hi[k], v[i * d + k]);
+        }
+    const int bits = d == 2 ? 15 : 10;
+    const double cells = (double)(1u << bits);
+    double inv[3] = {0, 0, 0};
+    for (int k = 0; k < d; ++k) inv[k] = hi[k] > lo[k] ? cells / (hi[k] - lo[k]) : 0.0;
+    std::vector<uint64_t> keys(E);
+    for (uint64_t e = 0; e < E; ++e) {
+        uint32_t q[3] = {0, 0, 0};
+        for (int k = 0; k < d; ++k) {
+            double c = 0.0;
+            for (int a = 0; a < n; ++a) c += v[conn[e * n + a] * d + k];
+            c = (c / n - lo[k]) * inv[k];
+            q[k] = (uint32_t)std::min(std::max(c, 0.0), cells - 1.0);
+        }
+        uint64_t code = 0;
+        for (int b = bits - 1; b >= 0; --b)
+            for (int k = d - 1; k >= 0; --k) code = (code << 1) | ((q[k] >> b) & 1u);
+        keys[e] = (code << 32) | (uint64_t)e;
+    }
+    std::sort(keys.begin(), keys.end());
+    for (uint64_t e = 0; e < E; ++e) order[e] = (int32_t)(keys[e] & 0xffffffffull);
+}
+
+static fb200_status upload_order(fb200_ctx* ctx) {
+    dev_free(ctx->d_order);
+    ctx->order_count = 0;
+    if (ctx->h_order.empty()) return FB200_OK;
+    std::vector<int32_t> owned;
+    owned.reserve(ctx->E_owned);
+    for (int32_t e : ctx->h_order)
+        if ((uint64_t)e < ctx->E_owned) owned.push_back(e);
+    FB200_TRY(dev_alloc(ctx, &ctx->d_order, owned.size()));
+    if (!owned.empty()) FB200_CUDA(ctx, cudaMemcpy(ctx->d_order, owned.data(), owned.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->order_count = owned.size();
+    return FB200_OK;
+}
+
 void free_space(fb200_ctx* ctx) {
     free_pattern(ctx);
+    dev_free(ctx->d_order);
+    ctx->order_count = 0;
+    ctx->h_order.clear();
     dev_free(ctx->d_vertices);
     dev_free(ctx->d_conn);
     dev_free(ctx->d_elem_off);
@@ -254,7 +305,8 @@ fb200_status fb200_space_upload(fb200_ctx* ctx, int32_t element_type, uint64_t n
     }
     ctx->has_space = ctx->has_connectivity = true;
     ctx->ragged = false;
-    return FB200_OK;
+    morton_order(ei.d, ei.n, num_nodes, vertices, num_elements, connectivity, ctx->h_order);  // indices were validated above
+    return upload_order(ctx);
 }
 
 fb200_status fb200_space_update_vertices(fb200_ctx* ctx, const double* vertices) {
@@ -314,9 +366,9 @@ fb200_status fb200_set_num_owned_elements(fb200_ctx* ctx, uint64_t num_owned) {
     if (!ctx || !ctx->has_connectivity) return fail(ctx, FB200_ERR_STATE, "no connectivity uploaded");
     if (num_owned > ctx->E) return fail(ctx, FB200_ERR_SHAPE, "num_owned exceeds num_elements");
     ctx->E_owned = num_owned;
-    // colours depend on the owned set
+    // colours and the visiting order depend on the owned set
     ctx->has_colors = false;
-    return FB200_OK;
+    return upload_order(ctx);
 }
 
 }  // extern "C"

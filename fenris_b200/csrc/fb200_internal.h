@@ -61,6 +61,11 @@ struct fb200_ctx {
     int64_t* d_elem_off = nullptr;   // ragged only: E+1
     uint64_t conn_len = 0;           // total incidences
 
+    // ---- locality (Morton) visiting order of the owned elements for the atomic scatter
+    int32_t* d_order = nullptr;
+    uint64_t order_count = 0;
+    std::vector<int32_t> h_order;  // over all E elements; filtered to the owned ones on upload
+
     // ---- adjacency: node -> flat incidence indices k into d_conn (uniform: element = k / n, local node = k % n),
     //      sorted ascending per node (deterministic)
     int64_t* d_adj_off = nullptr;    // N+1
