@@ -290,238 +290,8 @@ __global__ void __launch_bounds__(THREADS) assemble_elements_kernel(const Assemb
     }
 }
 
-// ------------------------------------------------------------------------------------------------ Hex8 warp-per-element kernel (v2)
-// Same mathematics as assemble_elements_kernel, re-mapped so that every phase uses all 32 lanes (the FP64 pipe retires a
-// warp instruction in 2 cycles no matter how many lanes are active) and the scatter is sector-coalesced:
-//   load     lanes 0-7 read the node ids (one 32 B sector), every lane reads two uint16 map entries = exactly the two node
-//            blocks it will compute; node ids are broadcast with shuffles for the coordinate gather (lanes 0-23);
-//            the next element's ids/map are prefetched while the current one is processed.
-//   geometry lane = (q, s): 4 lanes share a quadrature point; each accumulates J over 2 of the 8 nodes, a 2-step xor-shuffle
-//            reduction completes J, all four invert it (closed form) and each pushes 2 nodes' gradients forward, scaled by
-//            sqrt(w |det J|), into shared memory (row stride 26 doubles: conflict-free for this lane layout, 16 B aligned).
-//   blocks   lane owns K_{a,b0}, K_{a,b0+1} (a = lane/4, b0 = 2 (lane%4)): per point 3 LDS.64 (broadcast) + 3 LDS.128, 18 DFMA.
-//   stage    K_e row-major in shared memory (row stride S*8+3).
-//   scatter  one instruction per K_e row, lane = column: the 3 doubles of a node block are contiguous in the CSR row, so the
-//            reduction touches ~12 sectors per instruction instead of 32 (L2 RED throughput is per sector).
-// Requires uniform operator parameters (the general per-point case uses assemble_elements_kernel).
-template <int OP, int MODE, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const AssembleParams p) {
-    constexpr int N = 8, D = 3;
-    constexpr int S = OP == FB200_LAPLACE ? 1 : D;
-    constexpr int SN = S * N;
-    constexpr int TS = 26;      // row stride of the gradient tables and of the per-point gradient rows
-    constexpr int KS = SN + 3;  // row stride of the staged K_e
-    constexpr int WARPS = THREADS / 32;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ double smem[];
-    const int nq = p.nq;
-    double* s_w = smem;
-    double* s_ggeo = s_w + nq;
-    double* s_gref = s_ggeo + nq * TS;
-    const int tab_len = (nq * (1 + 2 * TS) + 1) & ~1;
-    for (int i = threadIdx.x; i < nq; i += THREADS) s_w[i] = p.tab[i];
-    for (int i = threadIdx.x; i < nq * N * D; i += THREADS) {
-        const int q = i / (N * D), r = i - q * (N * D);
-        s_ggeo[q * TS + r] = p.tab[3 * nq + i];
-        s_gref[q * TS + r] = p.tab[3 * nq + nq * N * D + i];
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warp_doubles = N * D + nq * TS + SN * KS + 28;  // + 8 int64 + 8 int32 + 32 uint32
-    double* s_X = smem + tab_len + warp * warp_doubles;
-    double* s_g = s_X + N * D;
-    double* s_K = s_g + nq * TS;
-    long long* s_base = reinterpret_cast<long long*>(s_K + SN * KS);
-    int* s_rowlen = reinterpret_cast<int*>(s_base + N);
-    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_rowlen + N);
-    const uint16_t* s_pos16 = reinterpret_cast<const uint16_t*>(s_pos);
-    __syncthreads();
-
-    const int qs = lane >> 2, s4 = lane & 3;      // geometry role
-    const int ba = lane >> 2, b0 = 2 * (lane & 3);  // block role
-    const int col_b = lane / S, col_j = lane - col_b * S;  // scatter role (lane < SN)
-    const double mu = p.mu, lam = p.lam;
-
-    const uint64_t nw = (uint64_t)gridDim.x * WARPS;
-    uint64_t idx = (uint64_t)blockIdx.x * WARPS + warp;
-    bool valid = idx < p.count;
-    uint64_t e = 0;
-    int node = 0;
-    uint32_t mapw = 0;
-    if (valid) {
-        e = p.elem_list ? (uint64_t)p.elem_list[idx] : idx;
-        if (lane < N) node = p.conn[e * N + lane];
-        if (MODE != MODE_DUMP) mapw = reinterpret_cast<const uint32_t*>(p.blockmap + e * (uint64_t)(N * N))[lane];
-    }
-    while (valid) {  // warp-uniform
-        // ---- dependent loads of the current element
-        long long o0 = 0, o1 = 0;
-        if (MODE != MODE_DUMP && lane < N) {
-            o0 = p.blk_off[node];
-            o1 = p.blk_off[node + 1];
-        }
-        const int na = __shfl_sync(FULL, node, lane < N * D ? lane / D : 0);
-        double x = 0.0;
-        if (lane < N * D) x = p.vertices[(uint64_t)na * D + (lane - (lane / D) * D)];
-        // ---- prefetch the next element's ids + map
-        const uint64_t idx_n = idx + nw;
-        const bool valid_n = idx_n < p.count;
-        uint64_t e_n = 0;
-        int node_n = 0;
-        uint32_t mapw_n = 0;
-        if (valid_n) {
-            e_n = p.elem_list ? (uint64_t)p.elem_list[idx_n] : idx_n;
-            if (lane < N) node_n = p.conn[e_n * N + lane];
-            if (MODE != MODE_DUMP) mapw_n = reinterpret_cast<const uint32_t*>(p.blockmap + e_n * (uint64_t)(N * N))[lane];
-        }
-        if (lane < N * D) s_X[lane] = x;
-        if (MODE != MODE_DUMP) {
-            if (lane < N) {
-                s_base[lane] = (long long)(S * S) * o0;
-                s_rowlen[lane] = (int)(o1 - o0) * S;
-            }
-            s_pos[lane] = mapw;
-        }
-        __syncwarp();
-
-        // ---- geometry: 8 quadrature points per pass, 4 lanes each
-        for (int q0 = 0; q0 < nq; q0 += 8) {
-            const int q = q0 + qs;
-            const bool act = q < nq;
-            const int qq = act ? q : 0;
-            double J[D][D];
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j < D; ++j) J[i][j] = 0.0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int a = s4 + 4 * h;
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = 0; j < D; ++j) J[i][j] = fma(s_X[a * D + i], s_ggeo[qq * TS + a * D + j], J[i][j]);
-            }
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    J[i][j] += __shfl_xor_sync(FULL, J[i][j], 1);
-                    J[i][j] += __shfl_xor_sync(FULL, J[i][j], 2);
-                }
-            const double c00 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
-            const double c01 = J[1][0] * J[2][2] - J[2][0] * J[1][2];
-            const double c02 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
-            const double det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
-            double r = 0.0;
-            if (det != 0.0) {
-                r = sqrt(s_w[qq] * fabs(det)) / det;  // (1/det) * sqrt(w |det|): gradients come out pre-scaled
-            } else if (act && s4 == 0) {
-                flag_error(p.errword, e, FB200_ERR_SINGULAR_JACOBIAN);
-            }
-            double Ji[D][D];  // sqrt(alpha) * J^{-1}
-            Ji[0][0] = c00 * r;
-            Ji[0][1] = (J[0][2] * J[2][1] - J[2][2] * J[0][1]) * r;
-            Ji[0][2] = (J[0][1] * J[1][2] - J[1][1] * J[0][2]) * r;
-            Ji[1][0] = -c01 * r;
-            Ji[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * r;
-            Ji[1][2] = (J[0][2] * J[1][0] - J[1][2] * J[0][0]) * r;
-            Ji[2][0] = c02 * r;
-            Ji[2][1] = (J[0][1] * J[2][0] - J[2][1] * J[0][0]) * r;
-            Ji[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * r;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int a = s4 + 4 * h;
-                const double g0 = s_gref[qq * TS + a * D + 0], g1 = s_gref[qq * TS + a * D + 1], g2 = s_gref[qq * TS + a * D + 2];
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    const double v = fma(Ji[2][i], g2, fma(Ji[1][i], g1, Ji[0][i] * g0));  // (J^{-T} g)_i
-                    if (act) s_g[q * TS + a * D + i] = v;
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- two node blocks per lane
-        double K0[S][S], K1[S][S];
-        if constexpr (S == 1) {
-            double t0 = 0.0, t1 = 0.0;
-            for (int q = 0; q < nq; ++q) {
-                const double* ga = s_g + q * TS + ba * D;
-                const double2* gb = reinterpret_cast<const double2*>(s_g + q * TS + b0 * D);
-                const double a0 = ga[0], a1 = ga[1], a2 = ga[2];
-                const double2 v0 = gb[0], v1 = gb[1], v2 = gb[2];
-                t0 = fma(a0, v0.x, fma(a1, v0.y, fma(a2, v1.x, t0)));
-                t1 = fma(a0, v1.y, fma(a1, v2.x, fma(a2, v2.y, t1)));
-            }
-            K0[0][0] = t0;
-            K1[0][0] = t1;
-        } else {
-            double M0[D][D], M1[D][D];
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j < D; ++j) { M0[i][j] = 0.0; M1[i][j] = 0.0; }
-            for (int q = 0; q < nq; ++q) {
-                const double* ga = s_g + q * TS + ba * D;
-                const double2* gb = reinterpret_cast<const double2*>(s_g + q * TS + b0 * D);
-                const double va[3] = {ga[0], ga[1], ga[2]};
-                const double2 v0 = gb[0], v1 = gb[1], v2 = gb[2];
-                const double vb[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        M0[i][j] = fma(va[i], vb[j], M0[i][j]);
-                        M1[i][j] = fma(va[i], vb[3 + j], M1[i][j]);
-                    }
-            }
-            const double tr0 = M0[0][0] + M0[1][1] + M0[2][2], tr1 = M1[0][0] + M1[1][1] + M1[2][2];
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    K0[i][j] = mu * ((i == j ? tr0 : 0.0) + M0[j][i]) + lam * M0[i][j];
-                    K1[i][j] = mu * ((i == j ? tr1 : 0.0) + M1[j][i]) + lam * M1[i][j];
-                }
-        }
-#pragma unroll
-        for (int i = 0; i < S; ++i)
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                s_K[(S * ba + i) * KS + S * b0 + j] = K0[i][j];
-                s_K[(S * ba + i) * KS + S * (b0 + 1) + j] = K1[i][j];
-            }
-        __syncwarp();
-
-        // ---- scatter: one K_e row per instruction, lane = column
-        if (lane < SN) {
-            if (MODE == MODE_DUMP) {
-                double* out = p.dump + idx * (uint64_t)(SN * SN);
-#pragma unroll
-                for (int rrow = 0; rrow < SN; ++rrow) out[(uint64_t)lane * SN + rrow] = s_K[rrow * KS + lane];
-            } else {
-#pragma unroll
-                for (int a = 0; a < N; ++a) {
-                    const long long off = s_base[a] + (long long)(S * (int)s_pos16[a * N + col_b] + col_j);
-                    const int rl = s_rowlen[a];
-#pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        double* dst = p.values + off + (long long)i * rl;
-                        const double v = s_K[(S * a + i) * KS + lane];
-                        if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
-                        else *dst += v;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        idx = idx_n;
-        valid = valid_n;
-        e = e_n;
-        node = node_n;
-        mapw = mapw_n;
-    }
-}
+// ------------------------------------------------------------------------------------------------ Hex8 warp-per-element kernel
+#include "hex8_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ row-owner (gather) kernel
 // One warp per node row-block.  The warp walks the node's incident elements in groups of 32/GE elements, each group of GE
@@ -694,13 +464,14 @@ static fb200_status launch_elements(fb200_ctx* ctx, AssembleParams& p) {
     return check_launch(ctx, "assemble_elements_kernel");
 }
 
-template <int OP, int MODE>
+template <int OP, int MODE, int MINB>
 static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
-    constexpr int THREADS = 128, MINB = 5, WARPS = THREADS / 32;
-    constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8, TS = 26, KS = SN + 3;
+    constexpr int THREADS = 128, WARPS = THREADS / 32;
+    constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8, TS = 33;
+    constexpr int KLEN = S == 1 ? SN * (SN + 1) : SN * SN + 4;
     if (p.count == 0) return FB200_OK;
     const int tab_len = (p.nq * (1 + 2 * TS) + 1) & ~1;
-    const int warp_doubles = 24 + p.nq * TS + SN * KS + 28;
+    const int warp_doubles = 24 + p.nq * TS + KLEN + (KLEN & 1) + 28;
     const size_t smem = sizeof(double) * (size_t)(tab_len + WARPS * warp_doubles);
     auto kernel = assemble_hex8_kernel<OP, MODE, THREADS, MINB>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -718,7 +489,13 @@ template <int N, int NG, int D, int OP, int MODE>
 static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
     if constexpr (N == 8 && NG == 8 && D == 3) {
         static const bool force_v1 = std::getenv("FB200_HEX8_V1") != nullptr;
-        if (p.uniform && !force_v1) return launch_hex8<OP, MODE>(ctx, p);
+        if (p.uniform && !force_v1) {
+            // registers per thread <-> resident warps per SM: 5 CTAs (96 regs), 6 (78 regs) or 8 (64 regs, small spills)
+            static const int minb = std::getenv("FB200_MINB") ? std::atoi(std::getenv("FB200_MINB")) : 6;
+            if (minb <= 5) return launch_hex8<OP, MODE, 5>(ctx, p);
+            if (minb >= 8) return launch_hex8<OP, MODE, 8>(ctx, p);
+            return launch_hex8<OP, MODE, 6>(ctx, p);
+        }
     }
     return launch_elements<N, NG, D, OP, MODE>(ctx, p);
 }

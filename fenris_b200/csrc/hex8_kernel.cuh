@@ -1,0 +1,266 @@
+// Hex8 warp-per-element assembly kernel (included by assemble.cu).
+//
+// Same mathematics as assemble_elements_kernel (see assemble.cu for the reference citations), re-mapped so that every
+// phase uses all 32 lanes - the FP64 pipe retires a warp instruction in 2 cycles no matter how many lanes are active -
+// and so that shared memory and the L2 reduction units see conflict-free / sector-coalesced traffic:
+//   load     lanes 0-7 read the node ids (one 32 B sector), every lane reads two uint16 map entries (exactly the two node
+//            blocks it will compute); ids are broadcast with shuffles for the coordinate gather (lanes 0-23).  The next
+//            element's ids, map, block offsets and coordinates are prefetched into registers while the current element is
+//            processed, so no global-load latency sits on the critical path of the loop.
+//   geometry lane = (q, s): 4 lanes share a quadrature point; each accumulates J over 2 of the 8 nodes, a 2-step
+//            xor-shuffle reduction completes J, all four invert it (closed form) and each pushes 2 nodes' gradients forward,
+//            pre-scaled by sqrt(w |det J|), into shared memory.
+//   layout   per-point rows of 33 doubles, node a at offset 4a + (a >> 2): the (q, s) lanes of a half-warp hit 16 distinct
+//            bank pairs, and the 8 (resp. 4) distinct addresses of the block phase's broadcast loads never share a bank.
+//   blocks   lane owns K_{a,b0}, K_{a,b0+1} (a = lane/4, b0 = 2 (lane%4)): per point 9 broadcast LDS.64 (1 wavefront each;
+//            a 128-bit load would cost 4 wavefronts regardless of broadcast) and 18 DFMA.
+//   stage    K_e row-major in shared memory, row r at 24 r + r/6 (conflict-free for the (a, m) writer layout).
+//   scatter  one instruction per K_e row, lane = column: the 3 doubles of a node block are contiguous in the CSR row, so a
+//            reduction instruction touches ~12 sectors instead of 32 (the L2 RED units work per sector).
+// Requires uniform operator parameters (the per-point case uses assemble_elements_kernel).
+#pragma once
+
+template <int OP, int MODE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const AssembleParams p) {
+    constexpr int N = 8, D = 3;
+    constexpr int S = OP == FB200_LAPLACE ? 1 : D;
+    constexpr int SN = S * N;
+    constexpr int TS = 33;                                  // row stride of the gradient tables / per-point gradient rows
+    constexpr int KLEN = S == 1 ? SN * (SN + 1) : SN * SN + 4;  // staged K_e
+    constexpr int WARPS = THREADS / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double smem[];
+    const int nq = p.nq;
+    double* s_w = smem;
+    double* s_ggeo = s_w + nq;
+    double* s_gref = s_ggeo + nq * TS;
+    const int tab_len = (nq * (1 + 2 * TS) + 1) & ~1;
+    for (int i = threadIdx.x; i < nq; i += THREADS) s_w[i] = p.tab[i];
+    for (int i = threadIdx.x; i < nq * N * D; i += THREADS) {
+        const int q = i / (N * D), r = i - q * (N * D);
+        const int a = r / D, j = r - a * D;
+        s_ggeo[q * TS + 4 * a + (a >> 2) + j] = p.tab[3 * nq + i];
+        s_gref[q * TS + 4 * a + (a >> 2) + j] = p.tab[3 * nq + nq * N * D + i];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_doubles = N * D + nq * TS + KLEN + (KLEN & 1) + 28;  // + 8 int64 + 8 int32 + 32 uint32
+    double* s_X = smem + tab_len + warp * warp_doubles;
+    double* s_g = s_X + N * D;
+    double* s_K = s_g + nq * TS;
+    long long* s_base = reinterpret_cast<long long*>(s_K + KLEN + (KLEN & 1));
+    int* s_rowlen = reinterpret_cast<int*>(s_base + N);
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_rowlen + N);
+    const uint16_t* s_pos16 = reinterpret_cast<const uint16_t*>(s_pos);
+    __syncthreads();
+
+    const int qs = lane >> 2, s4 = lane & 3;                // geometry role
+    const int ga0 = 4 * s4, ga1 = 4 * (s4 + 4) + 1;         // row offsets of this lane's two nodes (s4, s4 + 4)
+    const int ba = lane >> 2, b0 = 2 * (lane & 3);          // block role
+    const int oa = 4 * ba + (ba >> 2);
+    const int ob0 = 4 * b0 + (b0 >> 2), ob1 = 4 * (b0 + 1) + ((b0 + 1) >> 2);
+    const int col_b = lane / S, col_j = lane - col_b * S;   // scatter role (lane < SN)
+    const int xl = lane < N * D ? lane : 0;
+    const int x_node = xl / D, x_comp = xl - x_node * D;
+    const double mu = p.mu, lam = p.lam;
+
+    const uint64_t nw = (uint64_t)gridDim.x * WARPS;
+    uint64_t idx = (uint64_t)blockIdx.x * WARPS + warp;
+    bool valid = idx < p.count;
+    uint64_t e = 0;
+    uint32_t mapw = 0;
+    long long o0 = 0, o1 = 0;
+    double x = 0.0;
+    if (valid) {
+        e = p.elem_list ? (uint64_t)p.elem_list[idx] : idx;
+        int node = 0;
+        if (lane < N) node = p.conn[e * N + lane];
+        if (MODE != MODE_DUMP) {
+            mapw = reinterpret_cast<const uint32_t*>(p.blockmap + e * (uint64_t)(N * N))[lane];
+            if (lane < N) {
+                o0 = p.blk_off[node];
+                o1 = p.blk_off[node + 1];
+            }
+        }
+        const int na = __shfl_sync(FULL, node, x_node);
+        if (lane < N * D) x = p.vertices[(uint64_t)na * D + x_comp];
+    }
+    while (valid) {  // warp-uniform
+        // ---- stage the current element (everything was prefetched into registers)
+        if (lane < N * D) s_X[lane] = x;
+        if (MODE != MODE_DUMP) {
+            if (lane < N) {
+                s_base[lane] = (long long)(S * S) * o0;
+                s_rowlen[lane] = (int)(o1 - o0) * S;
+            }
+            s_pos[lane] = mapw;
+        }
+        // ---- first half of the prefetch of the next element: ids + map
+        const uint64_t idx_n = idx + nw;
+        const bool valid_n = idx_n < p.count;
+        uint64_t e_n = 0;
+        int node_n = 0;
+        uint32_t mapw_n = 0;
+        if (valid_n) {
+            e_n = p.elem_list ? (uint64_t)p.elem_list[idx_n] : idx_n;
+            if (lane < N) node_n = p.conn[e_n * N + lane];
+            if (MODE != MODE_DUMP) mapw_n = reinterpret_cast<const uint32_t*>(p.blockmap + e_n * (uint64_t)(N * N))[lane];
+        }
+        __syncwarp();
+
+        // ---- geometry: 8 quadrature points per pass, 4 lanes each
+        for (int q0 = 0; q0 < nq; q0 += 8) {
+            const int q = q0 + qs;
+            const bool act = q < nq;
+            const int qq = act ? q : 0;
+            const double* tg = s_ggeo + qq * TS;
+            double J[D][D];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) J[i][j] = s_X[s4 * D + i] * tg[ga0 + j];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) J[i][j] = fma(s_X[(s4 + 4) * D + i], tg[ga1 + j], J[i][j]);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    J[i][j] += __shfl_xor_sync(FULL, J[i][j], 1);
+                    J[i][j] += __shfl_xor_sync(FULL, J[i][j], 2);
+                }
+            const double c00 = J[1][1] * J[2][2] - J[2][1] * J[1][2];
+            const double c01 = J[1][0] * J[2][2] - J[2][0] * J[1][2];
+            const double c02 = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+            const double det = J[0][0] * c00 - J[0][1] * c01 + J[0][2] * c02;
+            double r = 0.0;
+            if (det != 0.0) {
+                r = sqrt(s_w[qq] * fabs(det)) / det;  // (1/det) * sqrt(w |det|): gradients come out pre-scaled
+            } else if (act && s4 == 0) {
+                flag_error(p.errword, e, FB200_ERR_SINGULAR_JACOBIAN);
+            }
+            double Ji[D][D];  // sqrt(alpha) * J^{-1}
+            Ji[0][0] = c00 * r;
+            Ji[0][1] = (J[0][2] * J[2][1] - J[2][2] * J[0][1]) * r;
+            Ji[0][2] = (J[0][1] * J[1][2] - J[1][1] * J[0][2]) * r;
+            Ji[1][0] = -c01 * r;
+            Ji[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * r;
+            Ji[1][2] = (J[0][2] * J[1][0] - J[1][2] * J[0][0]) * r;
+            Ji[2][0] = c02 * r;
+            Ji[2][1] = (J[0][1] * J[2][0] - J[2][1] * J[0][0]) * r;
+            Ji[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * r;
+            const double* tr = s_gref + qq * TS;
+            double* go = s_g + qq * TS;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int off = h == 0 ? ga0 : ga1;
+                const double g0 = tr[off], g1 = tr[off + 1], g2 = tr[off + 2];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double v = fma(Ji[2][i], g2, fma(Ji[1][i], g1, Ji[0][i] * g0));  // (J^{-T} g)_i
+                    if (act) go[off + i] = v;
+                }
+            }
+        }
+        // ---- second half of the prefetch: data that depends on the next element's node ids
+        long long o0_n = 0, o1_n = 0;
+        double x_n = 0.0;
+        {
+            if (MODE != MODE_DUMP && valid_n && lane < N) {
+                o0_n = p.blk_off[node_n];
+                o1_n = p.blk_off[node_n + 1];
+            }
+            const int na = __shfl_sync(FULL, node_n, x_node);
+            if (valid_n && lane < N * D) x_n = p.vertices[(uint64_t)na * D + x_comp];
+        }
+        __syncwarp();
+
+        // ---- two node blocks per lane
+        double K0[S][S], K1[S][S];
+        if constexpr (S == 1) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                const double* gq = s_g + q * TS;
+                const double a0 = gq[oa], a1 = gq[oa + 1], a2 = gq[oa + 2];
+                t0 = fma(a0, gq[ob0], fma(a1, gq[ob0 + 1], fma(a2, gq[ob0 + 2], t0)));
+                t1 = fma(a0, gq[ob1], fma(a1, gq[ob1 + 1], fma(a2, gq[ob1 + 2], t1)));
+            }
+            K0[0][0] = t0;
+            K1[0][0] = t1;
+        } else {
+            double M0[D][D], M1[D][D];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) { M0[i][j] = 0.0; M1[i][j] = 0.0; }
+#pragma unroll 2
+            for (int q = 0; q < nq; ++q) {
+                const double* gq = s_g + q * TS;
+                const double va[3] = {gq[oa], gq[oa + 1], gq[oa + 2]};
+                const double vb[6] = {gq[ob0], gq[ob0 + 1], gq[ob0 + 2], gq[ob1], gq[ob1 + 1], gq[ob1 + 2]};
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        M0[i][j] = fma(va[i], vb[j], M0[i][j]);
+                        M1[i][j] = fma(va[i], vb[3 + j], M1[i][j]);
+                    }
+            }
+            const double tr0 = M0[0][0] + M0[1][1] + M0[2][2], tr1 = M1[0][0] + M1[1][1] + M1[2][2];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    K0[i][j] = mu * ((i == j ? tr0 : 0.0) + M0[j][i]) + lam * M0[i][j];
+                    K1[i][j] = mu * ((i == j ? tr1 : 0.0) + M1[j][i]) + lam * M1[i][j];
+                }
+        }
+        // row r of K_e starts at krow(r): 24 r + r/6 (elasticity) or 9 r (Laplace)
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            const int r = S * ba + i;
+            const int kr = S == 1 ? r * (SN + 1) : r * SN + (ba >> 1);
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                s_K[kr + S * b0 + j] = K0[i][j];
+                s_K[kr + S * (b0 + 1) + j] = K1[i][j];
+            }
+        }
+        __syncwarp();
+
+        // ---- scatter: one K_e row per instruction, lane = column
+        if (lane < SN) {
+            if (MODE == MODE_DUMP) {
+                double* out = p.dump + idx * (uint64_t)(SN * SN);
+#pragma unroll
+                for (int r = 0; r < SN; ++r) {
+                    const int kr = S == 1 ? r * (SN + 1) : r * SN + r / 6;
+                    out[(uint64_t)lane * SN + r] = s_K[kr + lane];
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    double* rowp = p.values + (s_base[a] + (long long)(S * (int)s_pos16[a * N + col_b] + col_j));
+                    const int rl = s_rowlen[a];
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        const int r = S * a + i;
+                        const int kr = S == 1 ? r * (SN + 1) : r * SN + (a >> 1);
+                        const double v = s_K[kr + lane];
+                        double* dst = rowp + i * rl;
+                        if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
+                        else *dst += v;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        idx = idx_n;
+        valid = valid_n;
+        e = e_n;
+        mapw = mapw_n;
+        o0 = o0_n;
+        o1 = o1_n;
+        x = x_n;
+    }
+}
