@@ -41,10 +41,16 @@ struct AssembleParams {
     int nq;
     int uniform;                // all quadrature points carry the same operator parameters
     double mu, lam;             // the uniform parameters
-    const int32_t* elem_list;   // optional indirection (colour lists)
+    const int32_t* elem_list;   // optional indirection (colour lists) - generic kernel
+    // Hex8 warp kernel: connectivity / map rows already arranged in processing order (row = position)
+    const int32_t* conn_pos;
+    const uint16_t* map_pos;
+    const int32_t* elem_ids;    // element id of each position (nullptr: first_elem + position); error reports + dump
+    uint64_t first_elem;
     uint64_t count;             // elements to process
     unsigned long long* errword;
     double* dump;               // MODE_DUMP: count * (S N)^2 doubles, column-major per element
+    uint64_t dump_first;        // MODE_DUMP: first element of the contiguous range
     // gather mode
     const int64_t* adj_off;
     const int32_t* adj_inc;
@@ -464,6 +470,43 @@ static fb200_status launch_elements(fb200_ctx* ctx, AssembleParams& p) {
     return check_launch(ctx, "assemble_elements_kernel");
 }
 
+// rows of a per-element array gathered into processing order: dst[pos] = src[ids[pos]]
+__global__ void permute_rows_kernel(const uint32_t* __restrict__ src, const int32_t* __restrict__ ids, uint64_t count, int words_per_row,
+                                    uint32_t* __restrict__ dst) {
+    const uint64_t total = count * (uint64_t)words_per_row;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint64_t pos = t / words_per_row;
+        const int k = (int)(t - pos * words_per_row);
+        dst[t] = src[(uint64_t)ids[pos] * words_per_row + k];
+    }
+}
+
+// Connectivity and scatter map re-laid in a processing order (Morton order, or the concatenated colour lists), so that the
+// element loop reads them with unit stride and without a dependent index load.
+static fb200_status ensure_ordered(fb200_ctx* ctx, OrderedCopy& oc, const int32_t* d_ids, uint64_t count) {
+    if (oc.valid && oc.count == count && oc.ids == d_ids) return FB200_OK;
+    dev_free(oc.conn);
+    dev_free(oc.map);
+    oc.valid = false;
+    const int n = ctx->ei.n;
+    FB200_TRY(dev_alloc(ctx, &oc.conn, count * n));
+    FB200_TRY(dev_alloc(ctx, &oc.map, count * (uint64_t)(n * n)));
+    if (count) {
+        const int blocks = (int)std::min<uint64_t>(div_up(count * n, 256), (uint64_t)ctx->sm_count * 16);
+        permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(ctx->d_conn), d_ids, count, n,
+                                                             reinterpret_cast<uint32_t*>(oc.conn));
+        FB200_TRY(check_launch(ctx, "permute_rows_kernel<conn>"));
+        permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(ctx->d_blockmap), d_ids, count, n * n / 2,
+                                                             reinterpret_cast<uint32_t*>(oc.map));
+        FB200_TRY(check_launch(ctx, "permute_rows_kernel<map>"));
+    }
+    oc.ids = d_ids;
+    oc.count = count;
+    oc.valid = true;
+    return FB200_OK;
+}
+
 template <int OP, int MODE, int MINB>
 static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     constexpr int THREADS = 128, WARPS = THREADS / 32;
@@ -490,6 +533,29 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
     if constexpr (N == 8 && NG == 8 && D == 3) {
         static const bool force_v1 = std::getenv("FB200_HEX8_V1") != nullptr;
         if (p.uniform && !force_v1) {
+            // hand the kernel position-indexed connectivity / map rows (no dependent index load in the element loop)
+            p.first_elem = 0;
+            if (MODE == MODE_DUMP) {
+                p.conn_pos = p.conn + p.dump_first * 8;
+                p.map_pos = nullptr;
+                p.elem_ids = nullptr;
+                p.first_elem = p.dump_first;
+            } else if (p.elem_list == nullptr) {
+                p.conn_pos = p.conn;
+                p.map_pos = p.blockmap;
+                p.elem_ids = nullptr;
+            } else if (MODE == MODE_ATOMIC) {
+                FB200_TRY(ensure_ordered(ctx, ctx->ord_morton, ctx->d_order, ctx->order_count));
+                p.conn_pos = ctx->ord_morton.conn;
+                p.map_pos = ctx->ord_morton.map;
+                p.elem_ids = ctx->d_order;
+            } else {
+                FB200_TRY(ensure_ordered(ctx, ctx->ord_colors, ctx->d_color_elems, ctx->h_color_elems.size()));
+                const uint64_t off = (uint64_t)(p.elem_list - ctx->d_color_elems);
+                p.conn_pos = ctx->ord_colors.conn + off * 8;
+                p.map_pos = ctx->ord_colors.map + off * 64;
+                p.elem_ids = p.elem_list;
+            }
             // registers per thread <-> resident warps per SM: 5 CTAs (96 regs), 6 (78 regs) or 8 (64 regs, small spills)
             static const int minb = std::getenv("FB200_MINB") ? std::atoi(std::getenv("FB200_MINB")) : 6;
             if (minb <= 5) return launch_hex8<OP, MODE, 5>(ctx, p);
@@ -560,6 +626,16 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
         case FB200_HEX27: return dispatch_op<27, 8, 3>(ctx, p, op, mode);
         case FB200_TET10: return dispatch_op<10, 4, 3>(ctx, p, op, mode);
         default: return fail(ctx, FB200_ERR_UNSUPPORTED, "element type has no device specialisation (no CPU fallback)");
+    }
+}
+
+void free_ordered(fb200_ctx* ctx) {
+    for (OrderedCopy* oc : {&ctx->ord_morton, &ctx->ord_colors}) {
+        dev_free(oc->conn);
+        dev_free(oc->map);
+        oc->valid = false;
+        oc->count = 0;
+        oc->ids = nullptr;
     }
 }
 
@@ -668,6 +744,7 @@ fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, co
         p.elem_list = d_list;
         p.count = count;
         p.dump = d_out;
+        p.dump_first = first;
         st = dispatch(ctx, p, op->kind, MODE_DUMP);
     }
     if (st == FB200_OK) {

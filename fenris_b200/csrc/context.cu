@@ -28,6 +28,7 @@ fb200_status check_launch(fb200_ctx* ctx, const char* name) {
 }
 
 void free_pattern(fb200_ctx* ctx) {
+    free_ordered(ctx);
     dev_free(ctx->d_blk_off);
     dev_free(ctx->d_blk_cols);
     dev_free(ctx->d_blockmap);
@@ -73,6 +74,7 @@ static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, 
 }
 
 static fb200_status upload_order(fb200_ctx* ctx) {
+    free_ordered(ctx);
     dev_free(ctx->d_order);
     ctx->order_count = 0;
     if (ctx->h_order.empty()) return FB200_OK;

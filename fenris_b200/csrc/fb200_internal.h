@@ -37,6 +37,15 @@ struct DeviceTables {
     double mu0 = 0, lam0 = 0;
 };
 
+// connectivity + scatter map gathered into a processing order (see assemble.cu::ensure_ordered)
+struct OrderedCopy {
+    int32_t* conn = nullptr;
+    uint16_t* map = nullptr;
+    const int32_t* ids = nullptr;  // the device order array it was built from (not owned)
+    uint64_t count = 0;
+    bool valid = false;
+};
+
 }  // namespace fb200
 
 struct fb200_ctx {
@@ -65,6 +74,8 @@ struct fb200_ctx {
     int32_t* d_order = nullptr;
     uint64_t order_count = 0;
     std::vector<int32_t> h_order;  // over all E elements; filtered to the owned ones on upload
+
+    fb200::OrderedCopy ord_morton, ord_colors;
 
     // ---- adjacency: node -> flat incidence indices k into d_conn (uniform: element = k / n, local node = k % n),
     //      sorted ascending per node (deterministic)
@@ -147,6 +158,7 @@ void free_space(fb200_ctx* ctx);
 fb200_status exclusive_scan_i64(fb200_ctx* ctx, int64_t* d_data, uint64_t count);  // in place, count elements
 
 // assemble.cu
+void free_ordered(fb200_ctx* ctx);
 fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q);
 fb200_status read_errword(fb200_ctx* ctx);  // sync + translate deferred device errors
 

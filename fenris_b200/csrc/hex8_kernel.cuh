@@ -63,29 +63,43 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
     const int x_node = xl / D, x_comp = xl - x_node * D;
     const double mu = p.mu, lam = p.lam;
 
+    // Software pipeline over this warp's positions pos, pos + nw, pos + 2 nw, ...:
+    //   stage A (two elements ahead): node ids + map words          (addresses known in advance)
+    //   stage B (one element ahead) : block offsets + coordinates   (addresses depend on stage A's ids, which arrived an iteration ago)
+    //   stage C (current element)   : everything is in registers.
     const uint64_t nw = (uint64_t)gridDim.x * WARPS;
     uint64_t idx = (uint64_t)blockIdx.x * WARPS + warp;
     bool valid = idx < p.count;
-    uint64_t e = 0;
-    uint32_t mapw = 0;
-    long long o0 = 0, o1 = 0;
-    double x = 0.0;
-    if (valid) {
-        e = p.elem_list ? (uint64_t)p.elem_list[idx] : idx;
-        int node = 0;
-        if (lane < N) node = p.conn[e * N + lane];
-        if (MODE != MODE_DUMP) {
-            mapw = reinterpret_cast<const uint32_t*>(p.blockmap + e * (uint64_t)(N * N))[lane];
-            if (lane < N) {
-                o0 = p.blk_off[node];
-                o1 = p.blk_off[node + 1];
-            }
+    auto load_ids = [&](uint64_t pos, int& node, uint32_t& mapw) {
+        node = 0;
+        mapw = 0;
+        if (pos < p.count) {
+            if (lane < N) node = p.conn_pos[pos * N + lane];
+            if (MODE != MODE_DUMP) mapw = reinterpret_cast<const uint32_t*>(p.map_pos + pos * (uint64_t)(N * N))[lane];
         }
+    };
+    auto load_dep = [&](bool ok, int node, long long& a0, long long& a1, double& xv) {
+        a0 = 0;
+        a1 = 0;
+        xv = 0.0;
         const int na = __shfl_sync(FULL, node, x_node);
-        if (lane < N * D) x = p.vertices[(uint64_t)na * D + x_comp];
-    }
+        if (ok) {
+            if (MODE != MODE_DUMP && lane < N) {
+                a0 = p.blk_off[node];
+                a1 = p.blk_off[node + 1];
+            }
+            if (lane < N * D) xv = p.vertices[(uint64_t)na * D + x_comp];
+        }
+    };
+    int node0, node1;
+    uint32_t mapw, mapw1;
+    long long o0, o1;
+    double x;
+    load_ids(idx, node0, mapw);
+    load_ids(idx + nw, node1, mapw1);
+    load_dep(valid, node0, o0, o1, x);
     while (valid) {  // warp-uniform
-        // ---- stage the current element (everything was prefetched into registers)
+        // ---- stage the current element
         if (lane < N * D) s_X[lane] = x;
         if (MODE != MODE_DUMP) {
             if (lane < N) {
@@ -94,17 +108,15 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
             }
             s_pos[lane] = mapw;
         }
-        // ---- first half of the prefetch of the next element: ids + map
+        // ---- stage A for idx + 2 nw, stage B for idx + nw
         const uint64_t idx_n = idx + nw;
         const bool valid_n = idx_n < p.count;
-        uint64_t e_n = 0;
-        int node_n = 0;
-        uint32_t mapw_n = 0;
-        if (valid_n) {
-            e_n = p.elem_list ? (uint64_t)p.elem_list[idx_n] : idx_n;
-            if (lane < N) node_n = p.conn[e_n * N + lane];
-            if (MODE != MODE_DUMP) mapw_n = reinterpret_cast<const uint32_t*>(p.blockmap + e_n * (uint64_t)(N * N))[lane];
-        }
+        int node2;
+        uint32_t mapw2;
+        load_ids(idx_n + nw, node2, mapw2);
+        long long o0_n, o1_n;
+        double x_n;
+        load_dep(valid_n, node1, o0_n, o1_n, x_n);
         __syncwarp();
 
         // ---- geometry: 8 quadrature points per pass, 4 lanes each
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
             if (det != 0.0) {
                 r = sqrt(s_w[qq] * fabs(det)) / det;  // (1/det) * sqrt(w |det|): gradients come out pre-scaled
             } else if (act && s4 == 0) {
-                flag_error(p.errword, e, FB200_ERR_SINGULAR_JACOBIAN);
+                flag_error(p.errword, p.elem_ids ? (uint64_t)p.elem_ids[idx] : p.first_elem + idx, FB200_ERR_SINGULAR_JACOBIAN);
             }
             double Ji[D][D];  // sqrt(alpha) * J^{-1}
             Ji[0][0] = c00 * r;
@@ -161,17 +173,6 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
                     if (act) go[off + i] = v;
                 }
             }
-        }
-        // ---- second half of the prefetch: data that depends on the next element's node ids
-        long long o0_n = 0, o1_n = 0;
-        double x_n = 0.0;
-        {
-            if (MODE != MODE_DUMP && valid_n && lane < N) {
-                o0_n = p.blk_off[node_n];
-                o1_n = p.blk_off[node_n + 1];
-            }
-            const int na = __shfl_sync(FULL, node_n, x_node);
-            if (valid_n && lane < N * D) x_n = p.vertices[(uint64_t)na * D + x_comp];
         }
         __syncwarp();
 
@@ -257,8 +258,9 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
         __syncwarp();
         idx = idx_n;
         valid = valid_n;
-        e = e_n;
-        mapw = mapw_n;
+        mapw = mapw1;
+        mapw1 = mapw2;
+        node1 = node2;
         o0 = o0_n;
         o1 = o1_n;
         x = x_n;

@@ -440,6 +440,7 @@ static ConnView conn_view(const fb200_ctx* ctx) {
 }
 
 static fb200_status upload_colors(fb200_ctx* ctx) {
+    free_ordered(ctx);
     dev_free(ctx->d_color_elems);
     const uint64_t total = ctx->h_color_elems.size();
     FB200_TRY(dev_alloc(ctx, &ctx->d_color_elems, total));

@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Times the BASELINE.json configs that are NOT the headline bench line (C2 Tet4 Poisson, C4 Hex27 elasticity, a per-GPU share
+of C5 Tet4 elasticity) - they are parity-test cases in tests/, this script only records where their kernels stand.
+One JSON line per (config, scatter mode)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fenris_b200 as fb  # noqa: E402
+
+MODES = {"atomic": 0, "colored": 1, "gather": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2,c4,c5")
+    ap.add_argument("--modes", default="atomic,gather")
+    ap.add_argument("--steps", type=int, default=10)
+    args = ap.parse_args()
+    lame = fb.LameParameters.from_young_poisson(fb.YoungPoisson(1e6, 0.2))
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    for cfg in args.configs.split(","):
+        if cfg == "c2":
+            mesh, op, data, sdim, name = fb.create_unit_box_uniform_tet_mesh_3d(44), fb.LAPLACE, None, 1, "C2 Tet4 Poisson 44^3 cells"
+        elif cfg == "c4":
+            mesh, op, data, sdim, name = fb.hex27_mesh_from(fb.create_unit_box_uniform_hex_mesh_3d(63)), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C4 Hex27 elasticity 63^3 cells"
+        elif cfg == "c5":
+            mesh, op, data, sdim, name = fb.create_unit_box_uniform_tet_mesh_3d(80), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C5 share: Tet4 elasticity 80^3 cells (1/8 of 161^3)"
+        elif cfg == "c3":
+            mesh, op, data, sdim, name = fb.create_unit_box_uniform_hex_mesh_3d(126), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C3 Hex8 elasticity 126^3"
+        else:
+            continue
+        w, p = fb.canonical_stiffness_quadrature(mesh.element_type)
+        n, d = mesh.connectivity().shape[1], mesh.vertices().shape[1]
+        with fb.Context(0) as ctx:
+            ctx.space_upload(mesh.element_type, mesh.vertices(), mesh.connectivity())
+            nrows, nnz = ctx.assemble_pattern(sdim)
+            ctx.color_nodes()
+            E, N = mesh.num_elements(), mesh.num_nodes()
+            b_algo = 4 * n * E + 8 * d * N + 4 * n * n * E + 16 * nnz
+            for mname in args.modes.split(","):
+                m = MODES[mname]
+                try:
+                    for _ in range(3):
+                        ctx.assemble_into_csr_device(op, w, p, data, scatter_mode=m, accumulate=False)
+                    ctx.synchronize()
+                    ctx.timer_begin()
+                    for _ in range(args.steps):
+                        ctx.assemble_into_csr_device(op, w, p, data, scatter_mode=m, accumulate=False)
+                    ms = ctx.timer_end() / args.steps
+                    ctx.synchronize()
+                    print(json.dumps({"config": name, "scatter": mname, "elements": E, "nnz": nnz, "ms_per_step": ms, "elements_per_s": E / (ms * 1e-3),
+                                      "algorithmic_GBps": b_algo / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": b_algo / (ms * 1e-3) / 1e9 / peak}), flush=True)
+                except fb.Fb200Error as exc:
+                    print(json.dumps({"config": name, "scatter": mname, "error": str(exc)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
