@@ -47,6 +47,14 @@ struct AssembleParams {
     const uint16_t* map_pos;
     const int32_t* elem_ids;    // element id of each position (nullptr: first_elem + position); error reports + dump
     uint64_t first_elem;
+    unsigned int* ticket32;      // dynamic position counter of the Hex8 warp kernel
+    // fused zero-fill (values = contributions without a memset pass)
+    int zfuse;
+    const int64_t* zero_off;     // per chunk of CHUNK positions: range in zero_nodes
+    const int32_t* zero_nodes;   // nodes whose first contribution comes from that chunk
+    uint32_t* row_epoch;         // per node: epoch of the last clear
+    uint32_t epoch;
+    uint32_t num_chunks;
     uint64_t count;             // elements to process
     unsigned long long* errword;
     double* dump;               // MODE_DUMP: count * (S N)^2 doubles, column-major per element
@@ -470,6 +478,74 @@ static fb200_status launch_elements(fb200_ctx* ctx, AssembleParams& p) {
     return check_launch(ctx, "assemble_elements_kernel");
 }
 
+constexpr int kHex8Chunk = 8;  // positions per ticket = one 2x2x2 Morton cell
+
+// ---- fused zero-fill bookkeeping: which chunk of the processing order touches a node first
+__global__ void first_pos_kernel(const int32_t* __restrict__ conn_pos, uint64_t count, int n, int* first_pos) {
+    const uint64_t total = count * (uint64_t)n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) atomicMin(&first_pos[conn_pos[t]], (int)(t / n));
+}
+__global__ void zero_count_kernel(const int* __restrict__ first_pos, uint64_t num_nodes, int chunk, unsigned long long* cnt) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_nodes; i += stride) {
+        const int fp = first_pos[i];
+        atomicAdd(&cnt[fp >= 0x7f000000 ? 0 : fp / chunk], 1ull);  // rows no owned element touches are cleared by chunk 0
+    }
+}
+__global__ void zero_fill_kernel(const int* __restrict__ first_pos, uint64_t num_nodes, int chunk, unsigned long long* cursor, int32_t* nodes) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_nodes; i += stride) {
+        const int fp = first_pos[i];
+        nodes[atomicAdd(&cursor[fp >= 0x7f000000 ? 0 : fp / chunk], 1ull)] = (int32_t)i;
+    }
+}
+
+static fb200_status ensure_zero_lists(fb200_ctx* ctx, const OrderedCopy& oc) {
+    if (ctx->zero_valid && ctx->zero_count == oc.count) return FB200_OK;
+    dev_free(ctx->d_zero_off);
+    dev_free(ctx->d_zero_nodes);
+    ctx->zero_valid = false;
+    const uint64_t N = ctx->N, chunks = (oc.count + kHex8Chunk - 1) / kHex8Chunk;
+    int* d_first = nullptr;
+    unsigned long long* d_cursor = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_first, N));
+    fb200_status st = dev_alloc(ctx, &ctx->d_zero_off, chunks + 2);
+    if (st == FB200_OK) st = dev_alloc(ctx, &ctx->d_zero_nodes, N);
+    if (st == FB200_OK) st = dev_alloc(ctx, &d_cursor, chunks + 2);
+    if (st == FB200_OK && !ctx->d_row_epoch) {
+        st = dev_alloc(ctx, &ctx->d_row_epoch, N);
+        if (st == FB200_OK) cudaMemsetAsync(ctx->d_row_epoch, 0, std::max<uint64_t>(N, 1) * sizeof(uint32_t), ctx->stream);
+    }
+    if (st == FB200_OK) {
+        cudaMemsetAsync(d_first, 0x7f, N * sizeof(int), ctx->stream);  // 0x7f7f7f7f > any position; normalised below
+        cudaMemsetAsync(ctx->d_zero_off, 0, (chunks + 2) * sizeof(int64_t), ctx->stream);
+        const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(oc.count * ctx->ei.n, 256), (uint64_t)ctx->sm_count * 16));
+        if (oc.count) {
+            first_pos_kernel<<<blocks, 256, 0, ctx->stream>>>(oc.conn, oc.count, ctx->ei.n, d_first);
+            st = check_launch(ctx, "first_pos_kernel");
+        }
+    }
+    const int nb = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(N, 256), (uint64_t)ctx->sm_count * 16));
+    if (st == FB200_OK && N) {
+        zero_count_kernel<<<nb, 256, 0, ctx->stream>>>(d_first, N, kHex8Chunk, reinterpret_cast<unsigned long long*>(ctx->d_zero_off));
+        st = check_launch(ctx, "zero_count_kernel");
+    }
+    if (st == FB200_OK) st = exclusive_scan_i64(ctx, ctx->d_zero_off, chunks + 1);
+    if (st == FB200_OK && N) {
+        cudaMemcpyAsync(d_cursor, ctx->d_zero_off, (chunks + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        zero_fill_kernel<<<nb, 256, 0, ctx->stream>>>(d_first, N, kHex8Chunk, d_cursor, ctx->d_zero_nodes);
+        st = check_launch(ctx, "zero_fill_kernel");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_first);
+    if (d_cursor) cudaFree(d_cursor);
+    FB200_TRY(st);
+    ctx->zero_valid = true;
+    ctx->zero_count = oc.count;
+    return FB200_OK;
+}
+
 // rows of a per-element array gathered into processing order: dst[pos] = src[ids[pos]]
 __global__ void permute_rows_kernel(const uint32_t* __restrict__ src, const int32_t* __restrict__ ids, uint64_t count, int words_per_row,
                                     uint32_t* __restrict__ dst) {
@@ -507,7 +583,7 @@ static fb200_status ensure_ordered(fb200_ctx* ctx, OrderedCopy& oc, const int32_
     return FB200_OK;
 }
 
-template <int OP, int MODE, int MINB>
+template <int OP, int MODE, int MINB, bool DYN, bool HINT, int CHUNK = 8, bool ZFUSE = false>
 static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     constexpr int THREADS = 128, WARPS = THREADS / 32;
     constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8, TS = 33;
@@ -516,13 +592,20 @@ static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     const int tab_len = (p.nq * (1 + 2 * TS) + 1) & ~1;
     const int warp_doubles = 24 + p.nq * TS + KLEN + (KLEN & 1) + 28;
     const size_t smem = sizeof(double) * (size_t)(tab_len + WARPS * warp_doubles);
-    auto kernel = assemble_hex8_kernel<OP, MODE, THREADS, MINB>;
+    auto kernel = assemble_hex8_kernel<OP, MODE, THREADS, MINB, DYN, HINT, CHUNK, ZFUSE>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
     if (per_sm < 1) return fail(ctx, FB200_ERR_UNSUPPORTED, "quadrature rule too large for shared memory");
     const uint64_t want = (p.count + WARPS - 1) / WARPS;
+    // Resident CTAs per SM.  More warps hide latency better, but every element in flight widens the front of CSR rows that must
+    // stay in L2 between a node's first and last contribution and adds same-address pressure on the L2 reduction units; 3 CTAs
+    // (12 warps) per SM measured best for the atomic scatter (profiles/r01).
+    static const int grid_cap = std::getenv("FB200_GRID_CAP") ? std::atoi(std::getenv("FB200_GRID_CAP")) : 3;
+    if (MODE == MODE_ATOMIC && grid_cap > 0) per_sm = std::min(per_sm, grid_cap);
     const int blocks = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm);
+    p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    if (DYN) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
     kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
     return check_launch(ctx, "assemble_hex8_kernel");
 }
@@ -549,6 +632,14 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
                 p.conn_pos = ctx->ord_morton.conn;
                 p.map_pos = ctx->ord_morton.map;
                 p.elem_ids = ctx->d_order;
+                if (p.zfuse) {
+                    FB200_TRY(ensure_zero_lists(ctx, ctx->ord_morton));
+                    p.zero_off = ctx->d_zero_off;
+                    p.zero_nodes = ctx->d_zero_nodes;
+                    p.row_epoch = ctx->d_row_epoch;
+                    p.epoch = ++ctx->epoch;
+                    p.num_chunks = (uint32_t)((ctx->ord_morton.count + kHex8Chunk - 1) / kHex8Chunk);
+                }
             } else {
                 FB200_TRY(ensure_ordered(ctx, ctx->ord_colors, ctx->d_color_elems, ctx->h_color_elems.size()));
                 const uint64_t off = (uint64_t)(p.elem_list - ctx->d_color_elems);
@@ -556,11 +647,16 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
                 p.map_pos = ctx->ord_colors.map + off * 64;
                 p.elem_ids = p.elem_list;
             }
-            // registers per thread <-> resident warps per SM: 5 CTAs (96 regs), 6 (78 regs) or 8 (64 regs, small spills)
-            static const int minb = std::getenv("FB200_MINB") ? std::atoi(std::getenv("FB200_MINB")) : 6;
-            if (minb <= 5) return launch_hex8<OP, MODE, 5>(ctx, p);
-            if (minb >= 8) return launch_hex8<OP, MODE, 8>(ctx, p);
-            return launch_hex8<OP, MODE, 6>(ctx, p);
+            // tuning knobs (environment, read once); defaults = best measured on B200 (profiles/r01)
+            static const bool dyn = std::getenv("FB200_STATIC_SCHED") == nullptr;
+            static const bool hint = std::getenv("FB200_NO_L2_HINTS") == nullptr;
+            if constexpr (MODE == MODE_ATOMIC) {
+                if (p.zfuse) return launch_hex8<OP, MODE, 6, true, true, kHex8Chunk, true>(ctx, p);
+                if (dyn) return hint ? launch_hex8<OP, MODE, 6, true, true, kHex8Chunk>(ctx, p) : launch_hex8<OP, MODE, 6, true, false, kHex8Chunk>(ctx, p);
+                return hint ? launch_hex8<OP, MODE, 6, false, true>(ctx, p) : launch_hex8<OP, MODE, 6, false, false>(ctx, p);
+            } else {
+                return launch_hex8<OP, MODE, 6, false, false>(ctx, p);
+            }
         }
     }
     return launch_elements<N, NG, D, OP, MODE>(ctx, p);
@@ -630,6 +726,9 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
 }
 
 void free_ordered(fb200_ctx* ctx) {
+    dev_free(ctx->d_zero_off);
+    dev_free(ctx->d_zero_nodes);
+    ctx->zero_valid = false;
     for (OrderedCopy* oc : {&ctx->ord_morton, &ctx->ord_colors}) {
         dev_free(oc->conn);
         dev_free(oc->map);
@@ -681,7 +780,15 @@ fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator
     AssembleParams p;
     fill_params(ctx, p);
     p.accumulate = accumulate ? 1 : 0;
-    if (!accumulate && scatter_mode != FB200_SCATTER_GATHER)
+    // values = contributions: the Hex8 atomic kernel clears rows itself just before their first contribution (fused zero-fill);
+    // every other path starts from an explicit memset
+    static const bool no_zfuse = std::getenv("FB200_NO_ZFUSE") != nullptr || std::getenv("FB200_STATIC_SCHED") != nullptr ||
+                                 std::getenv("FB200_NO_ORDER") != nullptr || std::getenv("FB200_HEX8_V1") != nullptr;
+    p.zfuse = (!accumulate && scatter_mode == FB200_SCATTER_ATOMIC && ctx->elem_type == FB200_HEX8 && p.uniform && !no_zfuse && ctx->d_order &&
+               ctx->order_count == p.count && p.count > 0)
+                  ? 1
+                  : 0;
+    if (!accumulate && scatter_mode != FB200_SCATTER_GATHER && !p.zfuse)
         FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
     return dispatch(ctx, p, op->kind, scatter_mode);
 }

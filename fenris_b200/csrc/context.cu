@@ -93,6 +93,7 @@ void free_space(fb200_ctx* ctx) {
     dev_free(ctx->d_order);
     ctx->order_count = 0;
     ctx->h_order.clear();
+    dev_free(ctx->d_row_epoch);
     dev_free(ctx->d_vertices);
     dev_free(ctx->d_conn);
     dev_free(ctx->d_elem_off);
@@ -192,6 +193,7 @@ fb200_status fb200_create(int32_t device, fb200_ctx** out) {
     cudaEventCreate(&ctx->ev1);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaMalloc((void**)&ctx->d_errword, sizeof(unsigned long long));
+    cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned long long));
     cudaMallocHost((void**)&ctx->h_errword, sizeof(unsigned long long));
     const unsigned long long init = kNoError;
     cudaMemcpy(ctx->d_errword, &init, sizeof(init), cudaMemcpyHostToDevice);
@@ -214,6 +216,7 @@ void fb200_destroy(fb200_ctx* ctx) {
     free_space(ctx);
     dev_free(ctx->tab.d_data);
     dev_free(ctx->d_errword);
+    dev_free(ctx->d_ticket);
     dev_free(ctx->d_iface_nodes);
     dev_free(ctx->d_iface_offsets);
     dev_free(ctx->d_iface_packed);

@@ -76,6 +76,13 @@ struct fb200_ctx {
     std::vector<int32_t> h_order;  // over all E elements; filtered to the owned ones on upload
 
     fb200::OrderedCopy ord_morton, ord_colors;
+    // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
+    int64_t* d_zero_off = nullptr;
+    int32_t* d_zero_nodes = nullptr;
+    uint32_t* d_row_epoch = nullptr;
+    uint32_t epoch = 0;
+    bool zero_valid = false;
+    uint64_t zero_count = 0;
 
     // ---- adjacency: node -> flat incidence indices k into d_conn (uniform: element = k / n, local node = k % n),
     //      sorted ascending per node (deterministic)
@@ -105,6 +112,7 @@ struct fb200_ctx {
 
     // ---- tables + deferred error word
     fb200::DeviceTables tab;
+    unsigned long long* d_ticket = nullptr;   // dynamic work counter of the element kernels
     unsigned long long* d_errword = nullptr;
     unsigned long long* h_errword = nullptr;  // pinned
 

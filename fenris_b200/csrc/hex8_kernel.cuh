@@ -20,7 +20,36 @@
 // Requires uniform operator parameters (the per-point case uses assemble_elements_kernel).
 #pragma once
 
-template <int OP, int MODE, int THREADS, int MINB>
+// L2 eviction-priority hints (PTX createpolicy / .L2::cache_hint): CSR rows under accumulation are kept (evict_last) until all
+// of a node's elements have contributed; the streamed, read-once connectivity / map rows are marked evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void red_add_f64_hint(double* addr, double v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* addr) {
+    uint32_t r;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* addr, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const void* addr, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(addr), "l"(pol));
+    return r;
+}
+
+template <int OP, int MODE, int THREADS, int MINB, bool DYN, bool HINT, int CHUNK = 8, bool ZFUSE = false>
 __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const AssembleParams p) {
     constexpr int N = 8, D = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
@@ -62,26 +91,83 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
     const int xl = lane < N * D ? lane : 0;
     const int x_node = xl / D, x_comp = xl - x_node * D;
     const double mu = p.mu, lam = p.lam;
+    constexpr bool hints = HINT;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
-    // Software pipeline over this warp's positions pos, pos + nw, pos + 2 nw, ...:
+    // Positions (in processing order) are handed out dynamically: a warp takes a ticket = CHUNK consecutive positions from a
+    // global counter, so the set of elements in flight stays a compact front of the Morton order no matter how unevenly the
+    // warps progress (far-die L2 latency, RED back-pressure).  A compact front is what keeps a node's CSR rows resident in L2
+    // from its first to its last contribution.  (Without a ticket counter: static grid-stride assignment.)
+    // Software pipeline per warp over its position sequence:
     //   stage A (two elements ahead): node ids + map words          (addresses known in advance)
     //   stage B (one element ahead) : block offsets + coordinates   (addresses depend on stage A's ids, which arrived an iteration ago)
     //   stage C (current element)   : everything is in registers.
-    const uint64_t nw = (uint64_t)gridDim.x * WARPS;
-    uint64_t idx = (uint64_t)blockIdx.x * WARPS + warp;
-    bool valid = idx < p.count;
-    auto load_ids = [&](uint64_t pos, int& node, uint32_t& mapw) {
-        node = 0;
-        mapw = 0;
-        if (pos < p.count) {
-            if (lane < N) node = p.conn_pos[pos * N + lane];
-            if (MODE != MODE_DUMP) mapw = reinterpret_cast<const uint32_t*>(p.map_pos + pos * (uint64_t)(N * N))[lane];
+    // positions fit 32 bits (the upload rejects meshes with >= 2^31 incidences); saturate instead of wrapping
+    const uint32_t nw = (uint32_t)gridDim.x * WARPS;
+    const uint32_t count = (uint32_t)p.count;
+    constexpr bool dynamic = DYN;
+    uint32_t static_pos = (uint32_t)blockIdx.x * WARPS + warp;
+    uint32_t gen_base = 0;
+    int gen_left = 0;
+    unsigned int tick_next = 0;
+    if (dynamic && lane == 0) tick_next = atomicAdd(p.ticket32, 1u);
+    auto next_pos = [&]() -> uint32_t {
+        if constexpr (!dynamic) {
+            const uint32_t r = static_pos;
+            static_pos = (r >= count) ? r : r + nw;
+            return r;
+        } else {
+            if (gen_left == 0) {
+                const unsigned int t = __shfl_sync(FULL, tick_next, 0);
+                gen_base = t >= 0x3fffffffu ? 0xfffffff0u : t * CHUNK;
+                gen_left = CHUNK;
+                if (lane == 0) tick_next = atomicAdd(p.ticket32, 1u);  // consumed CHUNK iterations from now
+                if constexpr (ZFUSE) {
+                    // Fused zero-fill (values = contributions): the rows whose FIRST contribution comes from this chunk are
+                    // cleared here - two or three iterations before the chunk's elements are scattered - and published with
+                    // a release store of the current epoch.  The lines are created in L2 (no DRAM read) and the reductions
+                    // that follow hit them there, so the separate 3.9 GB memset pass and its DRAM round trip disappear.
+                    if (t < p.num_chunks) {
+                        const long long zb = p.zero_off[t], ze = p.zero_off[t + 1];
+                        for (long long k = zb; k < ze; ++k) {
+                            const int zn = p.zero_nodes[k];
+                            const long long rb = p.blk_off[zn];
+                            const int len = (int)(p.blk_off[zn + 1] - rb) * (S * S);
+                            double* row = p.values + (long long)(S * S) * rb;
+                            for (int w = lane; w < len; w += 32) row[w] = 0.0;
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        for (long long k = zb + lane; k < ze; k += 32) st_release_u32(p.row_epoch + p.zero_nodes[k], p.epoch);
+                    }
+                }
+            }
+            const uint32_t r = gen_base + (uint32_t)(CHUNK - gen_left);
+            --gen_left;
+            return r;
         }
     };
-    auto load_dep = [&](bool ok, int node, long long& a0, long long& a1, double& xv) {
+    auto load_ids = [&](uint32_t pos, int& node, uint32_t& mapw) {
+        node = 0;
+        mapw = 0;
+        if (pos < count) {
+            if constexpr (hints) {
+                if (lane < N) node = (int)ld_u32_hint(p.conn_pos + (uint64_t)pos * N + lane, pol_stream);
+                if (MODE != MODE_DUMP) mapw = ld_u32_hint(reinterpret_cast<const uint32_t*>(p.map_pos + pos * (uint64_t)(N * N)) + lane, pol_stream);
+            } else {
+                if (lane < N) node = p.conn_pos[(uint64_t)pos * N + lane];
+                if (MODE != MODE_DUMP) mapw = reinterpret_cast<const uint32_t*>(p.map_pos + pos * (uint64_t)(N * N))[lane];
+            }
+        }
+    };
+    auto load_dep = [&](bool ok, int node, long long& a0, long long& a1, double& xv, uint32_t& flag) {
         a0 = 0;
         a1 = 0;
         xv = 0.0;
+        flag = p.epoch;
+        if constexpr (ZFUSE) {
+            if (ok && lane < N) flag = ld_acquire_u32(p.row_epoch + node);
+        }
         const int na = __shfl_sync(FULL, node, x_node);
         if (ok) {
             if (MODE != MODE_DUMP && lane < N) {
@@ -95,9 +181,14 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
     uint32_t mapw, mapw1;
     long long o0, o1;
     double x;
+    uint32_t rflag;
+    uint32_t idx = next_pos();
+    uint32_t idx_n = next_pos();
+    uint32_t idx_n2 = next_pos();
+    bool valid = idx < count;
     load_ids(idx, node0, mapw);
-    load_ids(idx + nw, node1, mapw1);
-    load_dep(valid, node0, o0, o1, x);
+    load_ids(idx_n, node1, mapw1);
+    load_dep(valid, node0, o0, o1, x, rflag);
     while (valid) {  // warp-uniform
         // ---- stage the current element
         if (lane < N * D) s_X[lane] = x;
@@ -108,15 +199,16 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
             }
             s_pos[lane] = mapw;
         }
-        // ---- stage A for idx + 2 nw, stage B for idx + nw
-        const uint64_t idx_n = idx + nw;
-        const bool valid_n = idx_n < p.count;
+        // ---- stage A for the element two iterations ahead, stage B for the next one
+        const bool valid_n = idx_n < count;
         int node2;
         uint32_t mapw2;
-        load_ids(idx_n + nw, node2, mapw2);
+        load_ids(idx_n2, node2, mapw2);
+        const uint32_t idx_n3 = next_pos();
         long long o0_n, o1_n;
         double x_n;
-        load_dep(valid_n, node1, o0_n, o1_n, x_n);
+        uint32_t rflag_n;
+        load_dep(valid_n, node1, o0_n, o1_n, x_n, rflag_n);
         __syncwarp();
 
         // ---- geometry: 8 quadrature points per pass, 4 lanes each
@@ -149,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
             if (det != 0.0) {
                 r = sqrt(s_w[qq] * fabs(det)) / det;  // (1/det) * sqrt(w |det|): gradients come out pre-scaled
             } else if (act && s4 == 0) {
-                flag_error(p.errword, p.elem_ids ? (uint64_t)p.elem_ids[idx] : p.first_elem + idx, FB200_ERR_SINGULAR_JACOBIAN);
+                flag_error(p.errword, p.elem_ids ? (uint64_t)p.elem_ids[idx] : p.first_elem + (uint64_t)idx, FB200_ERR_SINGULAR_JACOBIAN);
             }
             double Ji[D][D];  // sqrt(alpha) * J^{-1}
             Ji[0][0] = c00 * r;
@@ -229,10 +321,17 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
         }
         __syncwarp();
 
+        if constexpr (ZFUSE) {
+            // all 8 rows must have been cleared (by whichever chunk touches them first) before we add to them; the flags were
+            // prefetched an iteration ago and are almost always current - otherwise poll
+            while (!__all_sync(FULL, rflag == p.epoch)) {
+                if (rflag != p.epoch) rflag = ld_acquire_u32(p.row_epoch + node0);
+            }
+        }
         // ---- scatter: one K_e row per instruction, lane = column
         if (lane < SN) {
             if (MODE == MODE_DUMP) {
-                double* out = p.dump + idx * (uint64_t)(SN * SN);
+                double* out = p.dump + (uint64_t)idx * (uint64_t)(SN * SN);
 #pragma unroll
                 for (int r = 0; r < SN; ++r) {
                     const int kr = S == 1 ? r * (SN + 1) : r * SN + r / 6;
@@ -249,7 +348,10 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
                         const int kr = S == 1 ? r * (SN + 1) : r * SN + (a >> 1);
                         const double v = s_K[kr + lane];
                         double* dst = rowp + i * rl;
-                        if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
+                        if (MODE == MODE_ATOMIC) {
+                            if constexpr (hints) red_add_f64_hint(dst, v, pol_keep);
+                            else atomicAdd(dst, v);
+                        }
                         else *dst += v;
                     }
                 }
@@ -257,10 +359,14 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
         }
         __syncwarp();
         idx = idx_n;
+        idx_n = idx_n2;
+        idx_n2 = idx_n3;
         valid = valid_n;
         mapw = mapw1;
         mapw1 = mapw2;
+        node0 = node1;
         node1 = node2;
+        rflag = rflag_n;
         o0 = o0_n;
         o1 = o1_n;
         x = x_n;
