@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scatter", default=os.environ.get("FB200_SCATTER", "gather"), choices=list(MODE_NAMES))
+    ap.add_argument("--scatter", default=os.environ.get("FB200_SCATTER", "atomic"), choices=list(MODE_NAMES))
     ap.add_argument("--cells", type=int, default=CELLS, help="cells per edge per GPU (126 = BASELINE config C3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -255,7 +255,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": {"atomic": "assemble_elements_kernel<ATOMIC>", "colored": "assemble_elements_kernel<COLORED> x colours",
-                           "gather": "assemble_gather_kernel"}[args.scatter],
+                           "gather": "assemble_gather_kernel"}[args.scatter].replace("assemble_elements_kernel<ATOMIC>", "assemble_hex8_kernel<LINEAR_ELASTIC, ATOMIC>"),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": b_algo, "bytes_per_element": b_algo / max(E_loc, 1), "peak_source": peak_src}
 
     other = None

@@ -52,6 +52,8 @@ struct AssembleParams {
     int zfuse;
     const int64_t* zero_off;     // per chunk of CHUNK positions: range in zero_nodes
     const int32_t* zero_nodes;   // nodes whose first contribution comes from that chunk
+    const int64_t* zero_base;    // ... index of their first value
+    const int32_t* zero_len;     // ... number of values in their s rows
     uint32_t* row_epoch;         // per node: epoch of the last clear
     uint32_t epoch;
     uint32_t num_chunks;
@@ -493,11 +495,15 @@ __global__ void zero_count_kernel(const int* __restrict__ first_pos, uint64_t nu
         atomicAdd(&cnt[fp >= 0x7f000000 ? 0 : fp / chunk], 1ull);  // rows no owned element touches are cleared by chunk 0
     }
 }
-__global__ void zero_fill_kernel(const int* __restrict__ first_pos, uint64_t num_nodes, int chunk, unsigned long long* cursor, int32_t* nodes) {
+__global__ void zero_fill_kernel(const int* __restrict__ first_pos, uint64_t num_nodes, int chunk, unsigned long long* cursor, int32_t* nodes,
+                                 const int64_t* __restrict__ blk_off, int ss, int64_t* base, int32_t* len) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_nodes; i += stride) {
         const int fp = first_pos[i];
-        nodes[atomicAdd(&cursor[fp >= 0x7f000000 ? 0 : fp / chunk], 1ull)] = (int32_t)i;
+        const unsigned long long slot = atomicAdd(&cursor[fp >= 0x7f000000 ? 0 : fp / chunk], 1ull);
+        nodes[slot] = (int32_t)i;
+        base[slot] = (int64_t)ss * blk_off[i];
+        len[slot] = (int32_t)((blk_off[i + 1] - blk_off[i]) * ss);
     }
 }
 
@@ -505,6 +511,8 @@ static fb200_status ensure_zero_lists(fb200_ctx* ctx, const OrderedCopy& oc) {
     if (ctx->zero_valid && ctx->zero_count == oc.count) return FB200_OK;
     dev_free(ctx->d_zero_off);
     dev_free(ctx->d_zero_nodes);
+    dev_free(ctx->d_zero_base);
+    dev_free(ctx->d_zero_len);
     ctx->zero_valid = false;
     const uint64_t N = ctx->N, chunks = (oc.count + kHex8Chunk - 1) / kHex8Chunk;
     int* d_first = nullptr;
@@ -512,6 +520,8 @@ static fb200_status ensure_zero_lists(fb200_ctx* ctx, const OrderedCopy& oc) {
     FB200_TRY(dev_alloc(ctx, &d_first, N));
     fb200_status st = dev_alloc(ctx, &ctx->d_zero_off, chunks + 2);
     if (st == FB200_OK) st = dev_alloc(ctx, &ctx->d_zero_nodes, N);
+    if (st == FB200_OK) st = dev_alloc(ctx, &ctx->d_zero_base, N);
+    if (st == FB200_OK) st = dev_alloc(ctx, &ctx->d_zero_len, N);
     if (st == FB200_OK) st = dev_alloc(ctx, &d_cursor, chunks + 2);
     if (st == FB200_OK && !ctx->d_row_epoch) {
         st = dev_alloc(ctx, &ctx->d_row_epoch, N);
@@ -534,7 +544,8 @@ static fb200_status ensure_zero_lists(fb200_ctx* ctx, const OrderedCopy& oc) {
     if (st == FB200_OK) st = exclusive_scan_i64(ctx, ctx->d_zero_off, chunks + 1);
     if (st == FB200_OK && N) {
         cudaMemcpyAsync(d_cursor, ctx->d_zero_off, (chunks + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream);
-        zero_fill_kernel<<<nb, 256, 0, ctx->stream>>>(d_first, N, kHex8Chunk, d_cursor, ctx->d_zero_nodes);
+        zero_fill_kernel<<<nb, 256, 0, ctx->stream>>>(d_first, N, kHex8Chunk, d_cursor, ctx->d_zero_nodes, ctx->d_blk_off, ctx->sdim * ctx->sdim,
+                                                      ctx->d_zero_base, ctx->d_zero_len);
         st = check_launch(ctx, "zero_fill_kernel");
     }
     cudaStreamSynchronize(ctx->stream);
@@ -636,6 +647,8 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
                     FB200_TRY(ensure_zero_lists(ctx, ctx->ord_morton));
                     p.zero_off = ctx->d_zero_off;
                     p.zero_nodes = ctx->d_zero_nodes;
+                    p.zero_base = ctx->d_zero_base;
+                    p.zero_len = ctx->d_zero_len;
                     p.row_epoch = ctx->d_row_epoch;
                     p.epoch = ++ctx->epoch;
                     p.num_chunks = (uint32_t)((ctx->ord_morton.count + kHex8Chunk - 1) / kHex8Chunk);
@@ -728,6 +741,8 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
 void free_ordered(fb200_ctx* ctx) {
     dev_free(ctx->d_zero_off);
     dev_free(ctx->d_zero_nodes);
+    dev_free(ctx->d_zero_base);
+    dev_free(ctx->d_zero_len);
     ctx->zero_valid = false;
     for (OrderedCopy* oc : {&ctx->ord_morton, &ctx->ord_colors}) {
         dev_free(oc->conn);
@@ -782,7 +797,9 @@ fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator
     p.accumulate = accumulate ? 1 : 0;
     // values = contributions: the Hex8 atomic kernel clears rows itself just before their first contribution (fused zero-fill);
     // every other path starts from an explicit memset
-    static const bool no_zfuse = std::getenv("FB200_NO_ZFUSE") != nullptr || std::getenv("FB200_STATIC_SCHED") != nullptr ||
+    // (measured slower than memset + kernel so far - the clearing warps stall on the fence that publishes the rows - so it is
+    //  opt-in: FB200_ZFUSE=1; see profiles/r01/README.md)
+    static const bool no_zfuse = std::getenv("FB200_ZFUSE") == nullptr || std::getenv("FB200_STATIC_SCHED") != nullptr ||
                                  std::getenv("FB200_NO_ORDER") != nullptr || std::getenv("FB200_HEX8_V1") != nullptr;
     p.zfuse = (!accumulate && scatter_mode == FB200_SCATTER_ATOMIC && ctx->elem_type == FB200_HEX8 && p.uniform && !no_zfuse && ctx->d_order &&
                ctx->order_count == p.count && p.count > 0)

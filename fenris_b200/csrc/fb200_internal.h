@@ -79,6 +79,8 @@ struct fb200_ctx {
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;
+    int64_t* d_zero_base = nullptr;
+    int32_t* d_zero_len = nullptr;
     uint32_t* d_row_epoch = nullptr;
     uint32_t epoch = 0;
     bool zero_valid = false;

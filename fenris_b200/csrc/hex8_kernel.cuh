@@ -129,16 +129,24 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
                     // that follow hit them there, so the separate 3.9 GB memset pass and its DRAM round trip disappear.
                     if (t < p.num_chunks) {
                         const long long zb = p.zero_off[t], ze = p.zero_off[t + 1];
-                        for (long long k = zb; k < ze; ++k) {
-                            const int zn = p.zero_nodes[k];
-                            const long long rb = p.blk_off[zn];
-                            const int len = (int)(p.blk_off[zn + 1] - rb) * (S * S);
-                            double* row = p.values + (long long)(S * S) * rb;
-                            for (int w = lane; w < len; w += 32) row[w] = 0.0;
+                        for (long long k0 = zb; k0 < ze; k0 += 32) {  // one round of (coalesced) list loads for up to 32 rows
+                            long long rbase = 0;
+                            int rlen = 0, zn = -1;
+                            if (k0 + lane < ze) {
+                                rbase = p.zero_base[k0 + lane];
+                                rlen = p.zero_len[k0 + lane];
+                                zn = p.zero_nodes[k0 + lane];
+                            }
+                            const int rows = (int)(ze - k0 < 32 ? ze - k0 : 32);
+                            for (int j = 0; j < rows; ++j) {
+                                double* row = p.values + __shfl_sync(FULL, rbase, j);
+                                const int len = __shfl_sync(FULL, rlen, j);
+                                for (int w = lane; w < len; w += 32) row[w] = 0.0;
+                            }
+                            __threadfence();
+                            __syncwarp();
+                            if (zn >= 0) st_release_u32(p.row_epoch + zn, p.epoch);
                         }
-                        __threadfence();
-                        __syncwarp();
-                        for (long long k = zb + lane; k < ze; k += 32) st_release_u32(p.row_epoch + p.zero_nodes[k], p.epoch);
                     }
                 }
             }
