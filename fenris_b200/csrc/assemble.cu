@@ -57,6 +57,7 @@ struct AssembleParams {
     uint32_t* row_epoch;         // per node: epoch of the last clear
     uint32_t epoch;
     uint32_t num_chunks;
+    uint32_t zero_look;          // how many chunks the clearing warps may run ahead of the ticket counter
     uint64_t count;             // elements to process
     unsigned long long* errword;
     double* dump;               // MODE_DUMP: count * (S N)^2 doubles, column-major per element
@@ -606,7 +607,8 @@ static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     auto kernel = assemble_hex8_kernel<OP, MODE, THREADS, MINB, DYN, HINT, CHUNK, ZFUSE>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+    constexpr int BLOCK = THREADS + (ZFUSE ? 32 : 0);
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem));
     if (per_sm < 1) return fail(ctx, FB200_ERR_UNSUPPORTED, "quadrature rule too large for shared memory");
     const uint64_t want = (p.count + WARPS - 1) / WARPS;
     // Resident CTAs per SM.  More warps hide latency better, but every element in flight widens the front of CSR rows that must
@@ -617,7 +619,13 @@ static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     const int blocks = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm);
     p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
     if (DYN) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
-    kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+    if (ZFUSE) {
+        // element warps wait on flags written by the clearing warps of OTHER CTAs: all CTAs must be co-resident
+        void* args[] = {(void*)&p};
+        FB200_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(BLOCK), args, smem, ctx->stream));
+        return check_launch(ctx, "assemble_hex8_kernel<zfuse>");
+    }
+    kernel<<<blocks, BLOCK, smem, ctx->stream>>>(p);
     return check_launch(ctx, "assemble_hex8_kernel");
 }
 
@@ -652,6 +660,8 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
                     p.row_epoch = ctx->d_row_epoch;
                     p.epoch = ++ctx->epoch;
                     p.num_chunks = (uint32_t)((ctx->ord_morton.count + kHex8Chunk - 1) / kHex8Chunk);
+                    static const int look = std::getenv("FB200_ZERO_LOOK") ? std::atoi(std::getenv("FB200_ZERO_LOOK")) : 2048;
+                    p.zero_look = (uint32_t)look;
                 }
             } else {
                 FB200_TRY(ensure_ordered(ctx, ctx->ord_colors, ctx->d_color_elems, ctx->h_color_elems.size()));
@@ -664,7 +674,7 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
             static const bool dyn = std::getenv("FB200_STATIC_SCHED") == nullptr;
             static const bool hint = std::getenv("FB200_NO_L2_HINTS") == nullptr;
             if constexpr (MODE == MODE_ATOMIC) {
-                if (p.zfuse) return launch_hex8<OP, MODE, 6, true, true, kHex8Chunk, true>(ctx, p);
+                if (p.zfuse) return launch_hex8<OP, MODE, 4, true, true, kHex8Chunk, true>(ctx, p);  // 160-thread CTAs: 4 per SM keep ~96 registers
                 if (dyn) return hint ? launch_hex8<OP, MODE, 6, true, true, kHex8Chunk>(ctx, p) : launch_hex8<OP, MODE, 6, true, false, kHex8Chunk>(ctx, p);
                 return hint ? launch_hex8<OP, MODE, 6, false, true>(ctx, p) : launch_hex8<OP, MODE, 6, false, false>(ctx, p);
             } else {

@@ -50,7 +50,8 @@ __device__ __forceinline__ uint32_t ld_u32_hint(const void* addr, uint64_t pol) 
 }
 
 template <int OP, int MODE, int THREADS, int MINB, bool DYN, bool HINT, int CHUNK = 8, bool ZFUSE = false>
-__global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const AssembleParams p) {
+__global__ void __launch_bounds__(THREADS + (ZFUSE ? 32 : 0), MINB) assemble_hex8_kernel(const AssembleParams p) {
+    constexpr int BLOCK = THREADS + (ZFUSE ? 32 : 0);  // with the fused zero-fill one extra warp per CTA only clears rows
     constexpr int N = 8, D = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
     constexpr int SN = S * N;
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
     double* s_ggeo = s_w + nq;
     double* s_gref = s_ggeo + nq * TS;
     const int tab_len = (nq * (1 + 2 * TS) + 1) & ~1;
-    for (int i = threadIdx.x; i < nq; i += THREADS) s_w[i] = p.tab[i];
-    for (int i = threadIdx.x; i < nq * N * D; i += THREADS) {
+    for (int i = threadIdx.x; i < nq; i += BLOCK) s_w[i] = p.tab[i];
+    for (int i = threadIdx.x; i < nq * N * D; i += BLOCK) {
         const int q = i / (N * D), r = i - q * (N * D);
         const int a = r / D, j = r - a * D;
         s_ggeo[q * TS + 4 * a + (a >> 2) + j] = p.tab[3 * nq + i];
@@ -81,6 +82,45 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
     uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_rowlen + N);
     const uint16_t* s_pos16 = reinterpret_cast<const uint16_t*>(s_pos);
     __syncthreads();
+
+    if constexpr (ZFUSE) {
+        // ---- fused zero-fill (values = contributions without a separate memset pass).
+        // The extra warp of every CTA is a "clearing" warp: it walks the chunks of the processing order a bounded distance AHEAD
+        // of the ticket counter, clears the CSR rows whose first contribution comes from those chunks (coalesced stores that
+        // create the lines in L2 without a DRAM read), fences, and publishes each row with the current epoch.  Only these warps
+        // pay for the fence; the element warps just check the (prefetched) row flags before they add.  The reductions then hit
+        // lines that are already in L2, and DRAM sees every CSR value once - on its final write-back.
+        if (warp == WARPS) {
+            constexpr uint32_t ZB = 32 / CHUNK > 0 ? 32 / CHUNK : 1;  // chunks per round (~32 rows = one round of list loads)
+            for (uint32_t c0 = blockIdx.x * ZB; c0 < p.num_chunks; c0 += gridDim.x * ZB) {
+                while (true) {  // stay within p.zero_look chunks of the front so the cleared lines are still in L2 when used
+                    const uint32_t t = *reinterpret_cast<volatile unsigned int*>(p.ticket32);
+                    if (c0 < t + p.zero_look) break;
+                    __nanosleep(256);
+                }
+                const uint32_t c1 = c0 + ZB < p.num_chunks ? c0 + ZB : p.num_chunks;
+                const long long zb = p.zero_off[c0], ze = p.zero_off[c1];
+                for (long long k0 = zb; k0 < ze; k0 += 32) {
+                    long long rbase = 0;
+                    int rlen = 0;
+                    if (k0 + lane < ze) {
+                        rbase = p.zero_base[k0 + lane];
+                        rlen = p.zero_len[k0 + lane];
+                    }
+                    const int rows = (int)(ze - k0 < 32 ? ze - k0 : 32);
+                    for (int j = 0; j < rows; ++j) {
+                        double* row = p.values + __shfl_sync(FULL, rbase, j);
+                        const int len = __shfl_sync(FULL, rlen, j);
+                        for (int w = lane; w < len; w += 32) row[w] = 0.0;
+                    }
+                }
+                __threadfence();
+                __syncwarp();
+                for (long long k = zb + lane; k < ze; k += 32) st_release_u32(p.row_epoch + p.zero_nodes[k], p.epoch);
+            }
+            return;
+        }
+    }
 
     const int qs = lane >> 2, s4 = lane & 3;                // geometry role
     const int ga0 = 4 * s4, ga1 = 4 * (s4 + 4) + 1;         // row offsets of this lane's two nodes (s4, s4 + 4)
@@ -122,33 +162,6 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_kernel(const Asse
                 gen_base = t >= 0x3fffffffu ? 0xfffffff0u : t * CHUNK;
                 gen_left = CHUNK;
                 if (lane == 0) tick_next = atomicAdd(p.ticket32, 1u);  // consumed CHUNK iterations from now
-                if constexpr (ZFUSE) {
-                    // Fused zero-fill (values = contributions): the rows whose FIRST contribution comes from this chunk are
-                    // cleared here - two or three iterations before the chunk's elements are scattered - and published with
-                    // a release store of the current epoch.  The lines are created in L2 (no DRAM read) and the reductions
-                    // that follow hit them there, so the separate 3.9 GB memset pass and its DRAM round trip disappear.
-                    if (t < p.num_chunks) {
-                        const long long zb = p.zero_off[t], ze = p.zero_off[t + 1];
-                        for (long long k0 = zb; k0 < ze; k0 += 32) {  // one round of (coalesced) list loads for up to 32 rows
-                            long long rbase = 0;
-                            int rlen = 0, zn = -1;
-                            if (k0 + lane < ze) {
-                                rbase = p.zero_base[k0 + lane];
-                                rlen = p.zero_len[k0 + lane];
-                                zn = p.zero_nodes[k0 + lane];
-                            }
-                            const int rows = (int)(ze - k0 < 32 ? ze - k0 : 32);
-                            for (int j = 0; j < rows; ++j) {
-                                double* row = p.values + __shfl_sync(FULL, rbase, j);
-                                const int len = __shfl_sync(FULL, rlen, j);
-                                for (int w = lane; w < len; w += 32) row[w] = 0.0;
-                            }
-                            __threadfence();
-                            __syncwarp();
-                            if (zn >= 0) st_release_u32(p.row_epoch + zn, p.epoch);
-                        }
-                    }
-                }
             }
             const uint32_t r = gen_base + (uint32_t)(CHUNK - gen_left);
             --gen_left;
