@@ -68,6 +68,7 @@ struct AssembleParams {
     uint64_t num_nodes;
     uint64_t num_owned;
     int accumulate;
+    int debug;                  // measurement knobs of the Hex8 DMMA kernel (FB200_DEBUG)
 };
 
 __device__ __forceinline__ void flag_error(unsigned long long* errword, uint64_t elem, int code) {
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(THREADS) assemble_elements_kernel(const Assemb
 
 // ------------------------------------------------------------------------------------------------ Hex8 warp-per-element kernel
 #include "hex8_kernel.cuh"
+#include "hex8_mma_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ row-owner (gather) kernel
 // One warp per node row-block.  The warp walks the node's incident elements in groups of 32/GE elements, each group of GE
@@ -629,6 +631,32 @@ static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
     return check_launch(ctx, "assemble_hex8_kernel");
 }
 
+// FP64 tensor-core variant (hex8_mma_kernel.cuh): reference gradients in registers, S = G G^T by DMMA
+template <int OP, int MODE, bool DYN, bool HINT, int CHUNK = 8>
+static fb200_status launch_hex8_mma(fb200_ctx* ctx, AssembleParams& p) {
+    constexpr int THREADS = 128, WARPS = THREADS / 32, MINB = 3;
+    constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8;
+    constexpr int KLEN = S == 1 ? SN * (SN + 1) : SN * SN + 4;
+    if (p.count == 0) return FB200_OK;
+    constexpr int warp_doubles = 24 + 8 * 28 + KLEN + (KLEN & 1) + 28;
+    const size_t smem = sizeof(double) * (size_t)(WARPS * warp_doubles);
+    auto kernel = assemble_hex8_mma_kernel<OP, MODE, THREADS, MINB, DYN, HINT, CHUNK>;
+    int per_sm = 1;
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+    if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_hex8_mma_kernel does not fit on an SM");
+    const uint64_t want = (p.count + WARPS - 1) / WARPS;
+    // resident CTAs per SM: see launch_hex8 (the front of CSR rows under accumulation must stay in L2)
+    static const int grid_cap = std::getenv("FB200_GRID_CAP") ? std::atoi(std::getenv("FB200_GRID_CAP")) : 3;
+    if (grid_cap > 0) per_sm = std::min(per_sm, grid_cap);
+    const int blocks = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * per_sm);
+    p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    static const int debug = std::getenv("FB200_DEBUG") ? std::atoi(std::getenv("FB200_DEBUG")) : 0;
+    p.debug = debug;
+    if (DYN) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "assemble_hex8_mma_kernel");
+}
+
 // element-parallel launch: the Hex8 warp kernel when it applies, the generic kernel otherwise
 template <int N, int NG, int D, int OP, int MODE>
 static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
@@ -673,6 +701,15 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
             // tuning knobs (environment, read once); defaults = best measured on B200 (profiles/r01)
             static const bool dyn = std::getenv("FB200_STATIC_SCHED") == nullptr;
             static const bool hint = std::getenv("FB200_NO_L2_HINTS") == nullptr;
+            static const bool use_mma = std::getenv("FB200_HEX8_DFMA") == nullptr;
+            if (use_mma && p.nq <= 8 && !p.zfuse) {
+                if constexpr (MODE == MODE_ATOMIC) {
+                    if (dyn) return hint ? launch_hex8_mma<OP, MODE, true, true, kHex8Chunk>(ctx, p) : launch_hex8_mma<OP, MODE, true, false, kHex8Chunk>(ctx, p);
+                    return hint ? launch_hex8_mma<OP, MODE, false, true>(ctx, p) : launch_hex8_mma<OP, MODE, false, false>(ctx, p);
+                } else {
+                    return launch_hex8_mma<OP, MODE, false, false>(ctx, p);
+                }
+            }
             if constexpr (MODE == MODE_ATOMIC) {
                 if (p.zfuse) return launch_hex8<OP, MODE, 4, true, true, kHex8Chunk, true>(ctx, p);  // 160-thread CTAs: 4 per SM keep ~96 registers
                 if (dyn) return hint ? launch_hex8<OP, MODE, 6, true, true, kHex8Chunk>(ctx, p) : launch_hex8<OP, MODE, 6, true, false, kHex8Chunk>(ctx, p);
