@@ -69,6 +69,13 @@ struct AssembleParams {
     uint64_t num_owned;
     int accumulate;
     int debug;                  // measurement knobs of the Hex8 DMMA kernel (FB200_DEBUG)
+    // chunk-local scatter lists (chunks.cpp); num_chunks above
+    const int64_t* slot_off;
+    const uint16_t* contrib;
+    const int32_t* slot_node;
+    const uint16_t* slot_k;
+    const uint16_t* slot_cbeg;
+    const uint8_t* slot_flags;
 };
 
 __device__ __forceinline__ void flag_error(unsigned long long* errword, uint64_t elem, int code) {
@@ -311,6 +318,8 @@ __global__ void __launch_bounds__(THREADS) assemble_elements_kernel(const Assemb
 // ------------------------------------------------------------------------------------------------ Hex8 warp-per-element kernel
 #include "hex8_kernel.cuh"
 #include "hex8_mma_kernel.cuh"
+#include "hex27_mma_kernel.cuh"
+#include "tet4_chunk_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ row-owner (gather) kernel
 // One warp per node row-block.  The warp walks the node's incident elements in groups of 32/GE elements, each group of GE
@@ -657,6 +666,110 @@ static fb200_status launch_hex8_mma(fb200_ctx* ctx, AssembleParams& p) {
     return check_launch(ctx, "assemble_hex8_mma_kernel");
 }
 
+// ---- chunk-local scatter lists (host build, see chunks.cpp), cached per (order, pattern)
+static void free_chunks(ChunkLists& cl) {
+    dev_free(cl.d_slot_off);
+    dev_free(cl.d_contrib);
+    dev_free(cl.d_slot_node);
+    dev_free(cl.d_slot_k);
+    dev_free(cl.d_slot_cbeg);
+    dev_free(cl.d_slot_flags);
+    dev_free(cl.d_conn_pos);
+    cl.valid = false;
+    cl.count = 0;
+    cl.ids = nullptr;
+}
+
+template <class T>
+static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T>& h) {
+    FB200_TRY(dev_alloc(ctx, d, h.size()));
+    if (!h.empty()) FB200_CUDA(ctx, cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FB200_OK;
+}
+
+static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t count, int chunk_elems) {
+    ChunkLists& cl = ctx->chunks;
+    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems) return FB200_OK;
+    free_chunks(cl);
+    const int n = ctx->ei.n;
+    FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> conn(ctx->E * n), ids(count);
+    std::vector<int64_t> blk_off(ctx->N + 1);
+    std::vector<uint16_t> map(ctx->E * (uint64_t)(n * n));
+    FB200_CUDA(ctx, cudaMemcpy(conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(ids.data(), d_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    HostChunks hc;
+    build_chunk_lists(n, count, chunk_elems, ids.data(), conn.data(), ctx->N, blk_off.data(), map.data(), hc);
+    cl.num_chunks = (uint32_t)(hc.slot_off.size() - 1);
+    cl.total_slots = hc.slot_node.size();
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_off, hc.slot_off));
+    FB200_TRY(upload_vec(ctx, &cl.d_contrib, hc.contrib));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_node, hc.slot_node));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_k, hc.slot_k));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_cbeg, hc.slot_cbeg));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_flags, hc.slot_flags));
+    FB200_TRY(dev_alloc(ctx, &cl.d_conn_pos, count * n));
+    if (count) {
+        const int blocks = (int)std::min<uint64_t>(div_up(count * n, 256), (uint64_t)ctx->sm_count * 16);
+        permute_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(ctx->d_conn), d_ids, count, n,
+                                                             reinterpret_cast<uint32_t*>(cl.d_conn_pos));
+        FB200_TRY(check_launch(ctx, "permute_rows_kernel<chunk conn>"));
+    }
+    cl.count = count;
+    cl.ids = d_ids;
+    cl.chunk_elems = chunk_elems;
+    cl.valid = true;
+    return FB200_OK;
+}
+
+constexpr int kTet4Chunk = 1024, kTet4Threads = 512;
+
+template <int OP>
+static fb200_status launch_tet4_chunks(fb200_ctx* ctx, AssembleParams& p) {
+    if (p.count == 0) return FB200_OK;
+    FB200_TRY(ensure_chunks(ctx, ctx->d_order, ctx->order_count, kTet4Chunk));
+    const ChunkLists& cl = ctx->chunks;
+    p.conn_pos = cl.d_conn_pos;
+    p.elem_ids = ctx->d_order;
+    p.num_chunks = cl.num_chunks;
+    p.slot_off = cl.d_slot_off;
+    p.contrib = cl.d_contrib;
+    p.slot_node = cl.d_slot_node;
+    p.slot_k = cl.d_slot_k;
+    p.slot_cbeg = cl.d_slot_cbeg;
+    p.slot_flags = cl.d_slot_flags;
+    const size_t smem = sizeof(double) * 12 * kTet4Chunk;
+    auto kernel = assemble_tet4_chunk_kernel<OP, kTet4Threads, kTet4Chunk>;
+    FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTet4Threads, smem));
+    if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_tet4_chunk_kernel does not fit on an SM");
+    const int blocks = (int)std::min<uint64_t>(cl.num_chunks, (uint64_t)ctx->sm_count * per_sm);
+    p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<blocks, kTet4Threads, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "assemble_tet4_chunk_kernel");
+}
+
+// Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)
+template <int OP, int MODE>
+static fb200_status launch_hex27_mma(fb200_ctx* ctx, AssembleParams& p) {
+    if (p.count == 0) return FB200_OK;
+    const size_t smem = hex27_smem_bytes<OP>(p.nq);
+    auto kernel = assemble_hex27_mma_kernel<OP, MODE>;
+    FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kH27Threads, smem));
+    if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_hex27_mma_kernel does not fit on an SM");
+    const int blocks = (int)std::min<uint64_t>(p.count, (uint64_t)ctx->sm_count * per_sm);
+    p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<blocks, kH27Threads, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "assemble_hex27_mma_kernel");
+}
+
 // element-parallel launch: the Hex8 warp kernel when it applies, the generic kernel otherwise
 template <int N, int NG, int D, int OP, int MODE>
 static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
@@ -719,6 +832,10 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
             }
         }
     }
+    if constexpr (N == 27 && NG == 8 && D == 3) {
+        static const bool force_v1 = std::getenv("FB200_HEX27_V1") != nullptr;
+        if (p.uniform && p.nq <= kH27GQ && !force_v1) return launch_hex27_mma<OP, MODE>(ctx, p);
+    }
     return launch_elements<N, NG, D, OP, MODE>(ctx, p);
 }
 
@@ -750,6 +867,10 @@ static fb200_status dispatch_mode(fb200_ctx* ctx, AssembleParams& p, int mode) {
             // arrive while the row is still resident in L2; the sum does not depend on the order (up to fp rounding)
             static const bool no_order = std::getenv("FB200_NO_ORDER") != nullptr;
             if (ctx->d_order && !no_order && ctx->order_count == p.count) p.elem_list = ctx->d_order;
+            if constexpr (N == 4 && NG == 4 && D == 3) {
+                static const bool tet_v1 = std::getenv("FB200_TET4_V1") != nullptr;
+                if (p.uniform && p.nq == 1 && p.elem_list != nullptr && !tet_v1) return launch_tet4_chunks<OP>(ctx, p);
+            }
             return launch_element_parallel<N, NG, D, OP, MODE_ATOMIC>(ctx, p);
         }
         case FB200_SCATTER_GATHER: return launch_gather<N, NG, D, OP>(ctx, p);
@@ -786,6 +907,7 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
 }
 
 void free_ordered(fb200_ctx* ctx) {
+    free_chunks(ctx->chunks);
     dev_free(ctx->d_zero_off);
     dev_free(ctx->d_zero_nodes);
     dev_free(ctx->d_zero_base);

@@ -46,6 +46,33 @@ struct OrderedCopy {
     bool valid = false;
 };
 
+// chunk-local scatter lists (host build: chunks.cpp; consumer: tet4_chunk_kernel.cuh)
+struct HostChunks {
+    std::vector<int64_t> slot_off;     // num_chunks + 1
+    std::vector<uint16_t> contrib;     // count * n^2, chunk c starts at c * chunk_elems * n^2
+    std::vector<int32_t> slot_node;
+    std::vector<uint16_t> slot_k, slot_cbeg;
+    std::vector<uint8_t> slot_flags;
+};
+void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
+                       const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
+
+struct ChunkLists {
+    bool valid = false;
+    uint64_t count = 0;
+    const int32_t* ids = nullptr;  // the device order array it was built from (not owned)
+    int chunk_elems = 0;
+    uint32_t num_chunks = 0;
+    uint64_t total_slots = 0;
+    int64_t* d_slot_off = nullptr;
+    uint16_t* d_contrib = nullptr;
+    int32_t* d_slot_node = nullptr;
+    uint16_t* d_slot_k = nullptr;
+    uint16_t* d_slot_cbeg = nullptr;
+    uint8_t* d_slot_flags = nullptr;
+    int32_t* d_conn_pos = nullptr;  // connectivity rows in processing order
+};
+
 }  // namespace fb200
 
 struct fb200_ctx {
@@ -76,6 +103,7 @@ struct fb200_ctx {
     std::vector<int32_t> h_order;  // over all E elements; filtered to the owned ones on upload
 
     fb200::OrderedCopy ord_morton, ord_colors;
+    fb200::ChunkLists chunks;
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;

@@ -1,0 +1,257 @@
+// Hex27 (tri-quadratic, 27 nodes, 81 x 81 K_e) assembly kernel: one CTA of 10 warps per element, node-block contraction on the FP64
+// tensor pipe (included by assemble.cu; north_star: "tensor cores only on the high-order Hex20/Hex27/Tet10 path").
+//
+// Reference semantics (InteractiveComputerGraphics/fenris @ 7181b15): assemble_element_elliptic_matrix elliptic.rs:361-439;
+// Hex27 is SUB-parametric - the Jacobian comes from the embedded Hex8 of the first 8 vertices (hexahedron.rs:318-335) - and the
+// basis gradients are the tri-quadratic ones (hexahedron.rs:269-315); contraction materials.rs:108-122 / laplace.rs:60-68.
+//
+//   geometry  thread (q, i), 4 threads per quadrature point (q < 28): row i of J from the 8 corner vertices with the trilinear
+//             reference gradients of point q held in registers, rows exchanged by shuffles, cofactor row c_i, det J (first-row
+//             expansion, broadcast), r = sqrt(w |det J|) / det J; then component i of all 27 scaled physical gradients
+//             g_a[i](q) = r (c_i . grad_ref phi_a(q)) from the shared-memory table, stored as G[i][a][q] (node rows padded to 32,
+//             points to 28, pads stay zero).
+//   blocks    S_ab = sum_q g_a(q) (x) g_b(q) = G G^T.  Nodes are split into 4 tiles of 8; warp w owns one of the 10 tile pairs
+//             (ta <= tb) - the other triangle is the transpose - and accumulates the 9 component tiles (m, n) over the 7 k-steps
+//             with mma.sync.m8n8k4.f64 (63 DMMA, fragments G[m][8 ta + lane/4][4 ks + lane%4] / G[n][8 tb + ..] loaded once):
+//             the accumulator fragments hand lane (g, t) the complete 3 x 3 blocks of node pairs (8ta+g, 8tb+2t), (.., 8tb+2t+1).
+//   epilogue  K_ab = mu [tr(S_ab) I + S_ab^T] + lambda S_ab; K_ab and (ta < tb) K_ba = K_ab^T staged row-major in shared memory.
+//   scatter   one third of a K_e row (27 columns = 9 node blocks) per reduction instruction, lane = column.
+// Uniform operator parameters, positive weights, nq <= 28.
+#pragma once
+
+constexpr int kH27GQ = 28;                 // point stride of G (== 12 mod 16: conflict-free fragment loads)
+constexpr int kH27GC = 32 * kH27GQ + 4;    // component stride of G
+constexpr int kH27Threads = 320;
+
+template <int OP>
+__host__ __device__ constexpr int hex27_kstride() { return OP == FB200_LAPLACE ? 29 : 83; }
+
+template <int OP>
+__host__ __device__ inline size_t hex27_smem_bytes(int nq) {
+    constexpr int S = OP == FB200_LAPLACE ? 1 : 3;
+    size_t doubles = (size_t)nq * 81 + 3 * kH27GC + (size_t)(27 * S) * hex27_kstride<OP>() + 24 + 27 /* base */;
+    return doubles * 8 + 27 * 4 /* rowlen */ + 27 * 4 /* nodes */ + 732 * 2 /* map */ + 16;
+}
+
+template <int OP, int MODE>
+__global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(const AssembleParams p) {
+    constexpr int N = 27, D = 3, NG = 8;
+    constexpr int S = OP == FB200_LAPLACE ? 1 : D;
+    constexpr int SN = S * N;
+    constexpr int KST = hex27_kstride<OP>();
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double smem[];
+    const int nq = p.nq;  // <= 28
+    const int ksteps = (nq + 3) >> 2;
+    double* s_gref = smem;                       // [nq][27][3]
+    double* s_G = s_gref + nq * 81;              // [3][32][28] (+4 per component)
+    double* s_K = s_G + 3 * kH27GC;              // [SN][KST]
+    double* s_X = s_K + SN * KST;                // [8][3]
+    long long* s_base = reinterpret_cast<long long*>(s_X + 24);  // [27]
+    int* s_rowlen = reinterpret_cast<int*>(s_base + 27);          // [27]
+    int* s_nodes = s_rowlen + 27;                                 // [27]
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_nodes + 27);  // [27][27]
+    __shared__ unsigned int s_ticket;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < nq * 81; i += kH27Threads) s_gref[i] = p.tab[3 * nq + nq * NG * D + i];
+    for (int i = tid; i < 3 * kH27GC; i += kH27Threads) s_G[i] = 0.0;
+
+    // ---- geometry role
+    const int gq = tid >> 2, s4 = tid & 3;
+    const int gi = s4 == 3 ? 0 : s4;
+    const bool gact = gq < nq;                   // warps 0..3 run the geometry; threads with gq >= nq only take part in the shuffles
+    double R[NG][D];
+    double sqw = 0.0;
+    {
+        const double* tab_g = p.tab + 3 * nq + (gact ? gq : 0) * (NG * D);
+#pragma unroll
+        for (int a = 0; a < NG; ++a)
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[a][j] = gact ? tab_g[a * D + j] : 0.0;
+        if (gact) sqw = sqrt(p.tab[gq]);
+    }
+    const int src1 = (lane & ~3) | (gi == 2 ? 0 : gi + 1), src2 = (lane & ~3) | (gi == 0 ? 2 : gi - 1);
+
+    // ---- block role: warp -> tile pair (ta <= tb)
+    int ta = 0, tb = warp;
+    if (warp >= 4) { ta = 1; tb = warp - 3; }
+    if (warp >= 7) { ta = 2; tb = warp - 5; }
+    if (warp >= 9) { ta = 3; tb = 3; }
+    const int fg = lane >> 2, ft = lane & 3;
+    const int na = 8 * ta + fg, nb0 = 8 * tb + 2 * ft;  // this lane's blocks: (na, nb0), (na, nb0 + 1)
+    const double mu = p.mu, lam = p.lam;
+    __syncthreads();
+
+    while (true) {
+        if (tid == 0) s_ticket = atomicAdd(p.ticket32, 1u);
+        __syncthreads();
+        const uint64_t pos = s_ticket;
+        if (pos >= p.count) break;
+        const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[pos] : pos;
+        // ---- P0: connectivity, corner coordinates, row bases, scatter map
+        if (tid < N) {
+            const int node = p.conn[e * N + tid];
+            s_nodes[tid] = node;
+            if (MODE != MODE_DUMP) {
+                const long long b0 = p.blk_off[node], b1 = p.blk_off[node + 1];
+                s_base[tid] = (long long)(S * S) * b0;
+                s_rowlen[tid] = (int)(b1 - b0) * S;
+            }
+        } else if (tid >= 32 && tid < 32 + NG * D) {
+            const int t = tid - 32, a = t / D, i = t - a * D;
+            s_X[t] = p.vertices[(uint64_t)p.conn[e * N + a] * D + i];
+        }
+        if (MODE != MODE_DUMP) {
+            const uint16_t* mp16 = p.blockmap + e * (uint64_t)(N * N);  // 729 u16: element rows are 2-byte aligned only
+            for (int i = tid; i < N * N; i += kH27Threads) s_map[i] = mp16[i];
+        }
+        __syncthreads();
+
+        // ---- P1: geometry (warps 0..3)
+        if (warp < 4) {
+            double Jr[D];
+            {
+                double lo[D], hi[D];
+                const double x0 = s_X[gi], x4 = s_X[4 * D + gi];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    lo[j] = x0 * R[0][j];
+                    hi[j] = x4 * R[4][j];
+                }
+#pragma unroll
+                for (int a = 1; a < 4; ++a) {
+                    const double xa = s_X[a * D + gi], xb = s_X[(a + 4) * D + gi];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        lo[j] = fma(xa, R[a][j], lo[j]);
+                        hi[j] = fma(xb, R[a + 4][j], hi[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j) Jr[j] = lo[j] + hi[j];
+            }
+            double r1[D], r2[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                r1[j] = __shfl_sync(FULL, Jr[j], src1);
+                r2[j] = __shfl_sync(FULL, Jr[j], src2);
+            }
+            double c[D];
+            c[0] = r1[1] * r2[2] - r1[2] * r2[1];
+            c[1] = r1[2] * r2[0] - r1[0] * r2[2];
+            c[2] = r1[0] * r2[1] - r1[1] * r2[0];
+            double det = Jr[0] * c[0] + Jr[1] * c[1] + Jr[2] * c[2];
+            det = __shfl_sync(FULL, det, lane & ~3);
+            double r = 0.0;
+            if (det != 0.0) {
+                r = copysign(sqw * rsqrt(fabs(det)), det);
+            } else if (gact && s4 == 0) {
+                flag_error(p.errword, e, FB200_ERR_SINGULAR_JACOBIAN);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) c[j] *= r;
+            if (gact && s4 < 3) {
+                const double* tr = s_gref + gq * 81;
+                double* go = s_G + gi * kH27GC + gq;
+#pragma unroll 9
+                for (int a = 0; a < N; ++a) go[a * kH27GQ] = fma(c[2], tr[a * D + 2], fma(c[1], tr[a * D + 1], c[0] * tr[a * D]));
+            }
+        }
+        __syncthreads();
+
+        // ---- P2: S = G G^T for this warp's tile pair, epilogue, stage K_e
+        {
+            double M0[S == 1 ? 1 : D][S == 1 ? 1 : D], M1[S == 1 ? 1 : D][S == 1 ? 1 : D];
+#pragma unroll
+            for (int m = 0; m < (S == 1 ? 1 : D); ++m)
+#pragma unroll
+                for (int n = 0; n < (S == 1 ? 1 : D); ++n) { M0[m][n] = 0.0; M1[m][n] = 0.0; }
+            const double* fa = s_G + (8 * ta + fg) * kH27GQ + ft;
+            const double* fb = s_G + (8 * tb + fg) * kH27GQ + ft;
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double A[D], B[D];
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    A[m] = fa[m * kH27GC + 4 * ks];
+                    B[m] = fb[m * kH27GC + 4 * ks];
+                }
+                if constexpr (S == 1) {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) dmma_m8n8k4(M0[0][0], M1[0][0], A[m], B[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m)
+#pragma unroll
+                        for (int n = 0; n < D; ++n) dmma_m8n8k4(M0[m][n], M1[m][n], A[m], B[n]);
+                }
+            }
+            double K0[S][S], K1[S][S];
+            if constexpr (S == 1) {
+                K0[0][0] = M0[0][0];
+                K1[0][0] = M1[0][0];
+            } else {
+                const double tr0 = M0[0][0] + M0[1][1] + M0[2][2], tr1 = M1[0][0] + M1[1][1] + M1[2][2];
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        K0[i][j] = mu * ((i == j ? tr0 : 0.0) + M0[j][i]) + lam * M0[i][j];
+                        K1[i][j] = mu * ((i == j ? tr1 : 0.0) + M1[j][i]) + lam * M1[i][j];
+                    }
+            }
+            if (na < N) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int nb = nb0 + h;
+                    if (nb < N) {
+#pragma unroll
+                        for (int i = 0; i < S; ++i)
+#pragma unroll
+                            for (int j = 0; j < S; ++j) {
+                                const double v = h == 0 ? K0[i][j] : K1[i][j];
+                                s_K[(S * na + i) * KST + S * nb + j] = v;
+                                if (ta != tb) s_K[(S * nb + j) * KST + S * na + i] = v;  // K_ba = K_ab^T
+                            }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P3: scatter, one third of a K_e row per instruction (elasticity) / one row (Laplace)
+        if (MODE == MODE_DUMP) {
+            double* out = p.dump + pos * (uint64_t)(SN * SN);
+            for (int t = tid; t < SN * SN; t += kH27Threads) {
+                const int c = t / SN, r = t - c * SN;  // column-major output
+                out[t] = s_K[r * KST + c];
+            }
+        } else {
+            // warp w takes K_e rows w, w + 10, ...; lane = column within a third of the row (27 columns = 9 node blocks), so the
+            // lane's (block, component) split is loop invariant and the row's (node, component) advances without divisions
+            constexpr int SEG = S == 1 ? 1 : 3;          // instructions per row
+            constexpr int NW = kH27Threads / 32;
+            const int lb = lane / S, lj = lane - lb * S;  // lane < 27: block lb (+ 9 per segment), component lj
+            int a = warp / S, i = warp - a * S;
+            for (int r = warp; r < SN; r += NW) {
+                if (lane < N) {
+                    double* rowp = p.values + (s_base[a] + (long long)i * s_rowlen[a] + lj);
+                    const uint16_t* mrow = s_map + a * N + lb;
+                    const double* krow = s_K + r * KST + lane;
+#pragma unroll
+                    for (int sg = 0; sg < SEG; ++sg) {
+                        double* dst = rowp + S * (int)mrow[sg * (N / SEG)];
+                        const double v = krow[sg * N];
+                        if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
+                        else *dst += v;
+                    }
+                }
+                i += NW % S;
+                a += NW / S;
+                if (i >= S) { i -= S; ++a; }
+            }
+        }
+        // the next iteration's first __syncthreads (after the ticket) orders these reads against the next element's writes
+    }
+}

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_mma_kernel(const 
         __syncwarp();
 
         // ---- scatter: one K_e row per instruction, lane = column
-        if (lane < SN && !(dbg & 2)) {
+        if (lane < SN && !(dbg & 2) && !((dbg & 16) && col_j != 0)) {
             if (MODE == MODE_DUMP) {
                 double* out = p.dump + (uint64_t)idx * (uint64_t)(SN * SN);
 #pragma unroll
@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_hex8_mma_kernel(const 
                     const int rl = s_rowlen[a];
 #pragma unroll
                     for (int i = 0; i < S; ++i) {
+                        if ((dbg & 32) && i != 0) continue;
                         const int r = S * a + i;
                         const int kr = S == 1 ? r * (SN + 1) : r * SN + (a >> 1);
                         const double v = s_K[kr + lane];
