@@ -724,12 +724,10 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     return FB200_OK;
 }
 
-constexpr int kTet4Chunk = 1024, kTet4Threads = 512;
-
-template <int OP>
-static fb200_status launch_tet4_chunks(fb200_ctx* ctx, AssembleParams& p) {
+template <int OP, int C, int T>
+static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
     if (p.count == 0) return FB200_OK;
-    FB200_TRY(ensure_chunks(ctx, ctx->d_order, ctx->order_count, kTet4Chunk));
+    FB200_TRY(ensure_chunks(ctx, ctx->d_order, ctx->order_count, C));
     const ChunkLists& cl = ctx->chunks;
     p.conn_pos = cl.d_conn_pos;
     p.elem_ids = ctx->d_order;
@@ -740,17 +738,27 @@ static fb200_status launch_tet4_chunks(fb200_ctx* ctx, AssembleParams& p) {
     p.slot_k = cl.d_slot_k;
     p.slot_cbeg = cl.d_slot_cbeg;
     p.slot_flags = cl.d_slot_flags;
-    const size_t smem = sizeof(double) * 12 * kTet4Chunk;
-    auto kernel = assemble_tet4_chunk_kernel<OP, kTet4Threads, kTet4Chunk>;
+    const size_t smem = sizeof(double) * 12 * C;
+    auto kernel = assemble_tet4_chunk_kernel<OP, T, C>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTet4Threads, smem));
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
     if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_tet4_chunk_kernel does not fit on an SM");
     const int blocks = (int)std::min<uint64_t>(cl.num_chunks, (uint64_t)ctx->sm_count * per_sm);
     p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
     FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
-    kernel<<<blocks, kTet4Threads, smem, ctx->stream>>>(p);
+    kernel<<<blocks, T, smem, ctx->stream>>>(p);
     return check_launch(ctx, "assemble_tet4_chunk_kernel");
+}
+
+// chunk size: larger chunks merge more contributions per reduction (BCC tets: 28 / 23 / 17 reductions per element at 512 / 1024 /
+// 2048 elements per chunk instead of 144), smaller ones leave more CTAs per SM to hide the list-load latency
+template <int OP>
+static fb200_status launch_tet4_chunks(fb200_ctx* ctx, AssembleParams& p) {
+    static const int chunk = std::getenv("FB200_TET4_CHUNK") ? std::atoi(std::getenv("FB200_TET4_CHUNK")) : 1024;
+    if (chunk == 512) return launch_tet4_chunks_t<OP, 512, 256>(ctx, p);
+    if (chunk == 2048) return launch_tet4_chunks_t<OP, 2048, 1024>(ctx, p);
+    return launch_tet4_chunks_t<OP, 1024, 512>(ctx, p);
 }
 
 // Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)

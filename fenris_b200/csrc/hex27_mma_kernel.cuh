@@ -29,16 +29,21 @@ __host__ __device__ constexpr int hex27_kstride() { return OP == FB200_LAPLACE ?
 template <int OP>
 __host__ __device__ inline size_t hex27_smem_bytes(int nq) {
     constexpr int S = OP == FB200_LAPLACE ? 1 : 3;
-    size_t doubles = (size_t)nq * 81 + 3 * kH27GC + (size_t)(27 * S) * hex27_kstride<OP>() + 24 + 27 /* base */;
-    return doubles * 8 + 27 * 4 /* rowlen */ + 27 * 4 /* nodes */ + 732 * 2 /* map */ + 16;
+    size_t doubles = (size_t)nq * 81 + 3 * kH27GC + (size_t)(27 * S) * hex27_kstride<OP>() + 2 * 24 /* X */ + 2 * 28 /* base */;
+    return doubles * 8 + 2 * 28 * 4 /* rowlen */ + 2 * 736 * 2 /* map */ + 16;
 }
 
+// Software pipeline of one CTA over its elements e_0, e_1, ... (dynamic tickets):
+//     | P2(j): DMMA + epilogue, all 10 warps | sync A | warps 0-3: P1(j+1) geometry, then the global loads of P0(j+2)   | sync B | P0(j+2) -> smem |
+//     |                                      |        | warps 4-9: P3(j) scatter (the long, reduction-throughput-bound phase) |        |                 |
+// so the dependent global loads (connectivity -> row offsets / vertices) and the geometry never sit on the critical path.
 template <int OP, int MODE>
 __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(const AssembleParams p) {
     constexpr int N = 27, D = 3, NG = 8;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
     constexpr int SN = S * N;
     constexpr int KST = hex27_kstride<OP>();
+    constexpr int GEO_THREADS = 128, SCAT_WARPS = kH27Threads / 32 - 4;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const int nq = p.nq;  // <= 28
@@ -46,21 +51,20 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
     double* s_gref = smem;                       // [nq][27][3]
     double* s_G = s_gref + nq * 81;              // [3][32][28] (+4 per component)
     double* s_K = s_G + 3 * kH27GC;              // [SN][KST]
-    double* s_X = s_K + SN * KST;                // [8][3]
-    long long* s_base = reinterpret_cast<long long*>(s_X + 24);  // [27]
-    int* s_rowlen = reinterpret_cast<int*>(s_base + 27);          // [27]
-    int* s_nodes = s_rowlen + 27;                                 // [27]
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_nodes + 27);  // [27][27]
-    __shared__ unsigned int s_ticket;
+    double* s_X = s_K + SN * KST;                // [2][8][3]
+    long long* s_base = reinterpret_cast<long long*>(s_X + 48);  // [2][28]
+    int* s_rowlen = reinterpret_cast<int*>(s_base + 56);          // [2][28]
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_rowlen + 56); // [2][736]
+    __shared__ unsigned int s_tk[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < nq * 81; i += kH27Threads) s_gref[i] = p.tab[3 * nq + nq * NG * D + i];
     for (int i = tid; i < 3 * kH27GC; i += kH27Threads) s_G[i] = 0.0;
 
-    // ---- geometry role
+    // ---- geometry role (warps 0..3)
     const int gq = tid >> 2, s4 = tid & 3;
     const int gi = s4 == 3 ? 0 : s4;
-    const bool gact = gq < nq;                   // warps 0..3 run the geometry; threads with gq >= nq only take part in the shuffles
+    const bool gact = gq < nq;                   // threads with gq >= nq only take part in the shuffles
     double R[NG][D];
     double sqw = 0.0;
     {
@@ -81,85 +85,129 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
     const int fg = lane >> 2, ft = lane & 3;
     const int na = 8 * ta + fg, nb0 = 8 * tb + 2 * ft;  // this lane's blocks: (na, nb0), (na, nb0 + 1)
     const double mu = p.mu, lam = p.lam;
-    __syncthreads();
 
-    while (true) {
-        if (tid == 0) s_ticket = atomicAdd(p.ticket32, 1u);
-        __syncthreads();
-        const uint64_t pos = s_ticket;
-        if (pos >= p.count) break;
+    // P0 of one element, executed by threads 0..127: global loads into registers, then registers -> buffer `buf`
+    struct P0Regs {
+        long long base;
+        int rowlen;
+        double x;
+        uint16_t m[6];
+    };
+    auto p0_load = [&](uint64_t pos, P0Regs& r) {
         const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[pos] : pos;
-        // ---- P0: connectivity, corner coordinates, row bases, scatter map
+        const int32_t* en = p.conn + e * N;
         if (tid < N) {
-            const int node = p.conn[e * N + tid];
-            s_nodes[tid] = node;
             if (MODE != MODE_DUMP) {
+                const int node = en[tid];
                 const long long b0 = p.blk_off[node], b1 = p.blk_off[node + 1];
-                s_base[tid] = (long long)(S * S) * b0;
-                s_rowlen[tid] = (int)(b1 - b0) * S;
+                r.base = (long long)(S * S) * b0;
+                r.rowlen = (int)(b1 - b0) * S;
             }
         } else if (tid >= 32 && tid < 32 + NG * D) {
             const int t = tid - 32, a = t / D, i = t - a * D;
-            s_X[t] = p.vertices[(uint64_t)p.conn[e * N + a] * D + i];
+            r.x = p.vertices[(uint64_t)en[a] * D + i];
         }
         if (MODE != MODE_DUMP) {
             const uint16_t* mp16 = p.blockmap + e * (uint64_t)(N * N);  // 729 u16: element rows are 2-byte aligned only
-            for (int i = tid; i < N * N; i += kH27Threads) s_map[i] = mp16[i];
-        }
-        __syncthreads();
-
-        // ---- P1: geometry (warps 0..3)
-        if (warp < 4) {
-            double Jr[D];
-            {
-                double lo[D], hi[D];
-                const double x0 = s_X[gi], x4 = s_X[4 * D + gi];
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    lo[j] = x0 * R[0][j];
-                    hi[j] = x4 * R[4][j];
-                }
-#pragma unroll
-                for (int a = 1; a < 4; ++a) {
-                    const double xa = s_X[a * D + gi], xb = s_X[(a + 4) * D + gi];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        lo[j] = fma(xa, R[a][j], lo[j]);
-                        hi[j] = fma(xb, R[a + 4][j], hi[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < D; ++j) Jr[j] = lo[j] + hi[j];
+            for (int k = 0; k < 6; ++k) {
+                const int i = tid + k * GEO_THREADS;
+                r.m[k] = i < N * N ? mp16[i] : (uint16_t)0;
             }
-            double r1[D], r2[D];
+        }
+    };
+    auto p0_store = [&](int buf, const P0Regs& r) {
+        if (tid < N) {
+            if (MODE != MODE_DUMP) {
+                s_base[buf * 28 + tid] = r.base;
+                s_rowlen[buf * 28 + tid] = r.rowlen;
+            }
+        } else if (tid >= 32 && tid < 32 + NG * D) {
+            s_X[buf * 24 + tid - 32] = r.x;
+        }
+        if (MODE != MODE_DUMP) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const int i = tid + k * GEO_THREADS;
+                if (i < N * N) s_map[buf * 736 + i] = r.m[k];
+            }
+        }
+    };
+    auto geometry = [&](int buf, uint64_t pos) {
+        const double* sx = s_X + buf * 24;
+        double Jr[D];
+        {
+            double lo[D], hi[D];
+            const double x0 = sx[gi], x4 = sx[4 * D + gi];
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                r1[j] = __shfl_sync(FULL, Jr[j], src1);
-                r2[j] = __shfl_sync(FULL, Jr[j], src2);
-            }
-            double c[D];
-            c[0] = r1[1] * r2[2] - r1[2] * r2[1];
-            c[1] = r1[2] * r2[0] - r1[0] * r2[2];
-            c[2] = r1[0] * r2[1] - r1[1] * r2[0];
-            double det = Jr[0] * c[0] + Jr[1] * c[1] + Jr[2] * c[2];
-            det = __shfl_sync(FULL, det, lane & ~3);
-            double r = 0.0;
-            if (det != 0.0) {
-                r = copysign(sqw * rsqrt(fabs(det)), det);
-            } else if (gact && s4 == 0) {
-                flag_error(p.errword, e, FB200_ERR_SINGULAR_JACOBIAN);
+                lo[j] = x0 * R[0][j];
+                hi[j] = x4 * R[4][j];
             }
 #pragma unroll
-            for (int j = 0; j < D; ++j) c[j] *= r;
-            if (gact && s4 < 3) {
-                const double* tr = s_gref + gq * 81;
-                double* go = s_G + gi * kH27GC + gq;
-#pragma unroll 9
-                for (int a = 0; a < N; ++a) go[a * kH27GQ] = fma(c[2], tr[a * D + 2], fma(c[1], tr[a * D + 1], c[0] * tr[a * D]));
+            for (int a = 1; a < 4; ++a) {
+                const double xa = sx[a * D + gi], xb = sx[(a + 4) * D + gi];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    lo[j] = fma(xa, R[a][j], lo[j]);
+                    hi[j] = fma(xb, R[a + 4][j], hi[j]);
+                }
             }
+#pragma unroll
+            for (int j = 0; j < D; ++j) Jr[j] = lo[j] + hi[j];
         }
-        __syncthreads();
+        double r1[D], r2[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            r1[j] = __shfl_sync(FULL, Jr[j], src1);
+            r2[j] = __shfl_sync(FULL, Jr[j], src2);
+        }
+        double c[D];
+        c[0] = r1[1] * r2[2] - r1[2] * r2[1];
+        c[1] = r1[2] * r2[0] - r1[0] * r2[2];
+        c[2] = r1[0] * r2[1] - r1[1] * r2[0];
+        double det = Jr[0] * c[0] + Jr[1] * c[1] + Jr[2] * c[2];
+        det = __shfl_sync(FULL, det, lane & ~3);
+        double r = 0.0;
+        if (det != 0.0) {
+            r = copysign(sqw * rsqrt(fabs(det)), det);
+        } else if (gact && s4 == 0) {
+            flag_error(p.errword, p.elem_list ? (uint64_t)p.elem_list[pos] : pos, FB200_ERR_SINGULAR_JACOBIAN);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) c[j] *= r;
+        if (gact && s4 < 3) {
+            const double* tr = s_gref + gq * 81;
+            double* go = s_G + gi * kH27GC + gq;
+#pragma unroll 9
+            for (int a = 0; a < N; ++a) go[a * kH27GQ] = fma(c[2], tr[a * D + 2], fma(c[1], tr[a * D + 1], c[0] * tr[a * D]));
+        }
+    };
 
+    // ---- prologue: tickets of e_0, e_1; P0(0), P0(1); P1(0)
+    if (tid == 0) {
+        s_tk[0] = atomicAdd(p.ticket32, 1u);
+        s_tk[1] = atomicAdd(p.ticket32, 1u);
+    }
+    __syncthreads();
+    uint64_t pos = s_tk[0], pos_n = s_tk[1];
+    if (pos >= p.count) return;
+    if (tid < GEO_THREADS) {
+        P0Regs r;
+        p0_load(pos, r);
+        p0_store(0, r);
+        if (pos_n < p.count) {
+            p0_load(pos_n, r);
+            p0_store(1, r);
+        }
+    }
+    __syncthreads();
+    if (warp < 4) geometry(0, pos);
+    __syncthreads();
+
+    for (int cur = 0;; cur ^= 1) {
+        // here: s_G = G(e_j), buffer cur = P0(e_j), buffer cur^1 = P0(e_{j+1}) when pos_n is valid
+        if (tid == 0) s_tk[cur] = atomicAdd(p.ticket32, 1u);  // e_{j+2}; read after sync A
         // ---- P2: S = G G^T for this warp's tile pair, epilogue, stage K_e
         {
             double M0[S == 1 ? 1 : D][S == 1 ? 1 : D], M1[S == 1 ? 1 : D][S == 1 ? 1 : D];
@@ -218,40 +266,54 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
                 }
             }
         }
-        __syncthreads();
-
-        // ---- P3: scatter, one third of a K_e row per instruction (elasticity) / one row (Laplace)
-        if (MODE == MODE_DUMP) {
-            double* out = p.dump + pos * (uint64_t)(SN * SN);
-            for (int t = tid; t < SN * SN; t += kH27Threads) {
-                const int c = t / SN, r = t - c * SN;  // column-major output
-                out[t] = s_K[r * KST + c];
-            }
+        __syncthreads();  // sync A: K_e staged, s_G free, ticket of e_{j+2} visible
+        const uint64_t pos_n2 = s_tk[cur];
+        P0Regs pre;
+        if (warp < 4) {
+            // ---- P1(j+1), then the global loads of P0(j+2)
+            if (pos_n < p.count) geometry(cur ^ 1, pos_n);
+            if (pos_n2 < p.count) p0_load(pos_n2, pre);
         } else {
-            // warp w takes K_e rows w, w + 10, ...; lane = column within a third of the row (27 columns = 9 node blocks), so the
-            // lane's (block, component) split is loop invariant and the row's (node, component) advances without divisions
-            constexpr int SEG = S == 1 ? 1 : 3;          // instructions per row
-            constexpr int NW = kH27Threads / 32;
-            const int lb = lane / S, lj = lane - lb * S;  // lane < 27: block lb (+ 9 per segment), component lj
-            int a = warp / S, i = warp - a * S;
-            for (int r = warp; r < SN; r += NW) {
-                if (lane < N) {
-                    double* rowp = p.values + (s_base[a] + (long long)i * s_rowlen[a] + lj);
-                    const uint16_t* mrow = s_map + a * N + lb;
-                    const double* krow = s_K + r * KST + lane;
-#pragma unroll
-                    for (int sg = 0; sg < SEG; ++sg) {
-                        double* dst = rowp + S * (int)mrow[sg * (N / SEG)];
-                        const double v = krow[sg * N];
-                        if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
-                        else *dst += v;
-                    }
+            // ---- P3(j): scatter
+            const int w6 = warp - 4;
+            if (MODE == MODE_DUMP) {
+                double* out = p.dump + pos * (uint64_t)(SN * SN);
+                for (int t = tid - GEO_THREADS; t < SN * SN; t += kH27Threads - GEO_THREADS) {
+                    const int c = t / SN, r = t - c * SN;  // column-major output
+                    out[t] = s_K[r * KST + c];
                 }
-                i += NW % S;
-                a += NW / S;
-                if (i >= S) { i -= S; ++a; }
+            } else {
+                // warp w6 takes K_e rows w6, w6 + 6, ...; lane = column within a third of the row (27 columns = 9 node blocks): the
+                // lane's (block, component) split is loop invariant and the row's (node, component) advances without divisions
+                constexpr int SEG = S == 1 ? 1 : 3;          // instructions per row
+                const int lb = lane / S, lj = lane - lb * S;  // lane < 27: block lb (+ 9 per segment), component lj
+                const long long* sb = s_base + cur * 28;
+                const int* sr = s_rowlen + cur * 28;
+                const uint16_t* sm = s_map + cur * 736;
+                int a = w6 / S, i = w6 - a * S;
+                for (int r = w6; r < SN; r += SCAT_WARPS) {
+                    if (lane < N) {
+                        double* rowp = p.values + (sb[a] + (long long)i * sr[a] + lj);
+                        const uint16_t* mrow = sm + a * N + lb;
+                        const double* krow = s_K + r * KST + lane;
+#pragma unroll
+                        for (int sg = 0; sg < SEG; ++sg) {
+                            double* dst = rowp + S * (int)mrow[sg * (N / SEG)];
+                            const double v = krow[sg * N];
+                            if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
+                            else *dst += v;
+                        }
+                    }
+                    i += SCAT_WARPS % S;
+                    a += SCAT_WARPS / S;
+                    if (i >= S) { i -= S; ++a; }
+                }
             }
         }
-        // the next iteration's first __syncthreads (after the ticket) orders these reads against the next element's writes
+        __syncthreads();  // sync B: buffer cur and s_K are free, s_G = G(e_{j+1})
+        if (pos_n >= p.count) break;
+        if (warp < 4 && pos_n2 < p.count) p0_store(cur, pre);  // read by P1(j+2) / P3(j+2), both after the next sync A
+        pos = pos_n;
+        pos_n = pos_n2;
     }
 }

@@ -17,7 +17,7 @@
 #pragma once
 
 template <int OP, int T, int C>
-__global__ void __launch_bounds__(T, 2) assemble_tet4_chunk_kernel(const AssembleParams p) {
+__global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assemble_tet4_chunk_kernel(const AssembleParams p) {
     constexpr int N = 4, D = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
     extern __shared__ double s_g[];  // [12][C]
@@ -73,13 +73,20 @@ __global__ void __launch_bounds__(T, 2) assemble_tet4_chunk_kernel(const Assembl
         for (int u = tid; u < U; u += T) {
             const int cb = p.slot_cbeg[so + u];
             const int ce = u + 1 < U ? (int)p.slot_cbeg[so + u + 1] : npairs;
+            // slot metadata first: its latency overlaps the contributor loop
+            const int node = p.slot_node[so + u];
+            const int kpos = p.slot_k[so + u];
+            const bool st = overwrite && (p.slot_flags[so + u] & 1);
+            const long long o0 = p.blk_off[node], o1 = p.blk_off[node + 1];
             double M[D][D];
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
                 for (int j = 0; j < D; ++j) M[i][j] = 0.0;
+            unsigned tag_next = __ldg(contrib + cb);  // every slot has at least one contributor
             for (int t = cb; t < ce; ++t) {
-                const unsigned tag = __ldg(contrib + t);
+                const unsigned tag = tag_next;
+                if (t + 1 < ce) tag_next = __ldg(contrib + t + 1);
                 const int el = tag >> 4, a = (tag >> 2) & 3, b = tag & 3;
                 const double* ga = s_g + (a * D) * C + el;
                 const double* gb = s_g + (b * D) * C + el;
@@ -93,11 +100,8 @@ __global__ void __launch_bounds__(T, 2) assemble_tet4_chunk_kernel(const Assembl
                         for (int j = 0; j < D; ++j) M[i][j] = fma(va[i], vb[j], M[i][j]);
                 }
             }
-            const int node = p.slot_node[so + u];
-            const long long o0 = p.blk_off[node], o1 = p.blk_off[node + 1];
             const int rl = (int)(o1 - o0) * S;
-            double* dst = p.values + ((long long)(S * S) * o0 + (long long)S * p.slot_k[so + u]);
-            const bool st = overwrite && (p.slot_flags[so + u] & 1);
+            double* dst = p.values + ((long long)(S * S) * o0 + (long long)S * kpos);
             if constexpr (S == 1) {
                 if (st) dst[0] = M[0][0];
                 else atomicAdd(dst, M[0][0]);
