@@ -78,6 +78,7 @@ def lib():
         "fb200_timer_begin": (i32, [vp]),
         "fb200_timer_end": (i32, [vp, C.POINTER(C.c_float)]),
         "fb200_launch_count": (u64, [vp]),
+        "fb200_set_tuning": (i32, [vp, C.c_char_p, i32]),
         "fb200_space_upload": (i32, [vp, i32, u64, vp, u64, vp]),
         "fb200_space_update_vertices": (i32, [vp, vp]),
         "fb200_connectivity_upload": (i32, [vp, u64, u64, vp, vp]),

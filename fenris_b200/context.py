@@ -68,6 +68,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.fb200_launch_count(self._h))
 
+    def set_tuning(self, name: str, value: int):
+        """Kernel-selection knobs, e.g. ("hex8_tile", 64 | 0)."""
+        self._check(self._lib.fb200_set_tuning(self._h, name.encode(), int(value)))
+
     # -- space
     def space_upload(self, element_type: int, vertices: np.ndarray, connectivity: np.ndarray):
         v = nat.as_f64(vertices)

@@ -76,6 +76,14 @@ struct AssembleParams {
     const uint16_t* slot_k;
     const uint16_t* slot_cbeg;
     const uint8_t* slot_flags;
+    // tile lists of the Hex8 tile kernel (tiles.cpp)
+    uint32_t num_tiles;
+    const uint32_t* tile_hdr;
+    const int32_t* tile_nodes;
+    const uint32_t* tile_flush;
+    const uint8_t* tile_lnodes;
+    const uint16_t* tile_emap;
+    const int32_t* tile_elem;
 };
 
 __device__ __forceinline__ void flag_error(unsigned long long* errword, uint64_t elem, int code) {
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(THREADS) assemble_elements_kernel(const Assemb
 // ------------------------------------------------------------------------------------------------ Hex8 warp-per-element kernel
 #include "hex8_kernel.cuh"
 #include "hex8_mma_kernel.cuh"
+#include "hex8_tile_kernel.cuh"
 #include "hex27_mma_kernel.cuh"
 #include "tet4_chunk_kernel.cuh"
 
@@ -761,6 +770,100 @@ static fb200_status launch_tet4_chunks(fb200_ctx* ctx, AssembleParams& p) {
     return launch_tet4_chunks_t<OP, 1024, 512>(ctx, p);
 }
 
+// ---- tile lists of the Hex8 tile kernel (host build, see tiles.cpp), cached per (order, pattern, tile shape)
+static void free_tiles(TileLists& tl) {
+    dev_free(tl.d_hdr);
+    dev_free(tl.d_nodes);
+    dev_free(tl.d_flush);
+    dev_free(tl.d_lnodes);
+    dev_free(tl.d_emap);
+    dev_free(tl.d_elem);
+    tl.valid = false;
+    tl.unusable = false;
+    tl.count = 0;
+    tl.ids = nullptr;
+    tl.num_tiles = 0;
+}
+
+static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
+    TileLists& tl = ctx->tiles;
+    const int32_t* d_ids = ctx->d_order;
+    const uint64_t count = ctx->order_count;
+    if ((tl.valid || tl.unusable) && tl.count == count && tl.ids == d_ids && tl.tile_bits == shape.tile_bits) return FB200_OK;
+    free_tiles(tl);
+    tl.count = count;
+    tl.ids = d_ids;
+    tl.tile_bits = shape.tile_bits;
+    if (ctx->h_order_codes.size() != count) {
+        tl.unusable = true;
+        return FB200_OK;
+    }
+    FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> conn(ctx->E * 8), ids(count);
+    std::vector<uint16_t> map(ctx->E * (uint64_t)64);
+    FB200_CUDA(ctx, cudaMemcpy(conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(ids.data(), d_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    HostTiles ht;
+    build_tile_lists(shape, count, ids.data(), ctx->h_order_codes.data(), conn.data(), ctx->N, map.data(), ht);
+    if (ht.bank_conflict_share < 0.0 || ht.flush.size() >= (1ull << 32) || ht.nodes.size() >= (1ull << 32)) {
+        tl.unusable = true;  // degenerate elements (repeated nodes) or lists beyond 32-bit offsets: keep the per-element kernel
+        return FB200_OK;
+    }
+    tl.num_tiles = (uint32_t)(ht.hdr.size() / kTileHdrWords);
+    FB200_TRY(upload_vec(ctx, &tl.d_hdr, ht.hdr));
+    FB200_TRY(upload_vec(ctx, &tl.d_nodes, ht.nodes));
+    FB200_TRY(upload_vec(ctx, &tl.d_flush, ht.flush));
+    FB200_TRY(upload_vec(ctx, &tl.d_lnodes, ht.lnodes));
+    FB200_TRY(upload_vec(ctx, &tl.d_emap, ht.emap));
+    FB200_TRY(upload_vec(ctx, &tl.d_elem, ht.elem));
+    tl.valid = true;
+    return FB200_OK;
+}
+
+// Hex8 tile kernel (hex8_tile_kernel.cuh): a CTA accumulates a tile of the Morton order in shared memory and updates every CSR
+// node block of the tile once.  *used = false when the mesh has no usable tile lists (the caller falls back to the element kernel).
+template <int OP, int WARPS, int MAXN, int MAXP>
+static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const TileShape& shape, bool* used) {
+    *used = false;
+    FB200_TRY(ensure_tiles(ctx, shape));
+    const TileLists& tl = ctx->tiles;
+    if (!tl.valid) return FB200_OK;
+    *used = true;
+    if (tl.num_tiles == 0) return FB200_OK;
+    p.num_tiles = tl.num_tiles;
+    p.tile_hdr = tl.d_hdr;
+    p.tile_nodes = tl.d_nodes;
+    p.tile_flush = tl.d_flush;
+    p.tile_lnodes = tl.d_lnodes;
+    p.tile_emap = tl.d_emap;
+    p.tile_elem = tl.d_elem;
+    const size_t smem = Hex8TileSmem<OP, WARPS, MAXN, MAXP>::bytes;
+    auto kernel = assemble_hex8_tile_kernel<OP, WARPS, MAXN, MAXP>;
+    FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_hex8_tile_kernel does not fit on an SM");
+    const int blocks = (int)std::min<uint64_t>(tl.num_tiles, (uint64_t)ctx->sm_count * per_sm);
+    p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    static const int debug = std::getenv("FB200_DEBUG") ? std::atoi(std::getenv("FB200_DEBUG")) : 0;
+    p.debug = debug;
+    FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<blocks, WARPS * 32, smem, ctx->stream>>>(p);
+    return check_launch(ctx, "assemble_hex8_tile_kernel");
+}
+
+// tile shape: 4 x 4 x 4 elements, one CTA of 16 warps per SM (double-buffered accumulators: 2 x 85.5 KB of shared memory);
+// FB200_HEX8_TILE = 64 | 0 (off), overridden by fb200_set_tuning("hex8_tile")
+template <int OP>
+static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* used) {
+    static const int env_tile = std::getenv("FB200_HEX8_TILE") ? std::atoi(std::getenv("FB200_HEX8_TILE")) : 64;
+    const int tile = ctx->tune_hex8_tile >= 0 ? ctx->tune_hex8_tile : env_tile;
+    *used = false;
+    if (tile == 64) return launch_hex8_tile_t<OP, 16, 128, 1216>(ctx, p, TileShape{6, 64, 16, 128, 1216}, used);
+    return FB200_OK;
+}
+
 // Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)
 template <int OP, int MODE>
 static fb200_status launch_hex27_mma(fb200_ctx* ctx, AssembleParams& p) {
@@ -796,6 +899,11 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
                 p.map_pos = p.blockmap;
                 p.elem_ids = nullptr;
             } else if (MODE == MODE_ATOMIC) {
+                if (p.nq <= 8 && !p.zfuse && p.elem_list == ctx->d_order && p.count == ctx->order_count) {
+                    bool used = false;
+                    FB200_TRY(launch_hex8_tile<OP>(ctx, p, &used));
+                    if (used) return FB200_OK;
+                }
                 FB200_TRY(ensure_ordered(ctx, ctx->ord_morton, ctx->d_order, ctx->order_count));
                 p.conn_pos = ctx->ord_morton.conn;
                 p.map_pos = ctx->ord_morton.map;
@@ -916,6 +1024,7 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
 
 void free_ordered(fb200_ctx* ctx) {
     free_chunks(ctx->chunks);
+    free_tiles(ctx->tiles);
     dev_free(ctx->d_zero_off);
     dev_free(ctx->d_zero_nodes);
     dev_free(ctx->d_zero_base);

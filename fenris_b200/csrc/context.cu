@@ -1,5 +1,6 @@
 // Context lifetime, error plumbing, stream/timer helpers and the space (mesh) upload.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "fb200_internal.h"
@@ -41,9 +42,14 @@ void free_pattern(fb200_ctx* ctx) {
 }
 
 // Locality-preserving visiting order: elements sorted by the Morton code of their centroid (host preprocessing, like
-// the colouring).  The assembled sums do not depend on the order; it only decides which CSR rows are live in L2 together.
-static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order) {
+// the colouring).  The assembled sums do not depend on the order; it only decides which CSR rows are live in L2 together and
+// which elements share a cell of the cell-accumulating Hex8 kernel.  Centroids are quantised with the mean element size
+// h = (volume of the bounding box / E)^(1/d), so that on a structured mesh one quantisation cell is exactly one element and
+// aligned 2 x 2 x 2 element blocks are consecutive in the order (the code drops its lowest d bits to name such a block).
+static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order,
+                         std::vector<uint64_t>& codes) {
     order.resize(E);
+    codes.resize(E);
     if (E == 0 || N == 0) return;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (uint64_t i = 0; i < N; ++i)
@@ -51,26 +57,36 @@ static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, 
             lo[k] = std::min(lo[k], v[i * d + k]);
             hi[k] = std::max(hi[k], v[i * d + k]);
         }
-    const int bits = d == 2 ? 15 : 10;
-    const double cells = (double)(1u << bits);
-    double inv[3] = {0, 0, 0};
-    for (int k = 0; k < d; ++k) inv[k] = hi[k] > lo[k] ? cells / (hi[k] - lo[k]) : 0.0;
-    std::vector<uint64_t> keys(E);
+    const int bits = d == 2 ? 31 : 21;
+    const double qmax = (double)((1ull << bits) - 1);
+    double vol = 1.0;
+    int dims = 0;
+    for (int k = 0; k < d; ++k)
+        if (hi[k] > lo[k]) {
+            vol *= hi[k] - lo[k];
+            ++dims;
+        }
+    const double h = dims ? std::pow(vol / (double)E, 1.0 / dims) : 1.0;
+    const double inv = h > 0.0 ? 1.0 / h : 0.0;
+    std::vector<std::pair<uint64_t, uint64_t>> keys(E);
     for (uint64_t e = 0; e < E; ++e) {
-        uint32_t q[3] = {0, 0, 0};
+        uint64_t q[3] = {0, 0, 0};
         for (int k = 0; k < d; ++k) {
             double c = 0.0;
             for (int a = 0; a < n; ++a) c += v[conn[e * n + a] * d + k];
-            c = (c / n - lo[k]) * inv[k];
-            q[k] = (uint32_t)std::min(std::max(c, 0.0), cells - 1.0);
+            c = (c / n - lo[k]) * inv;
+            q[k] = (uint64_t)std::min(std::max(c, 0.0), qmax);
         }
         uint64_t code = 0;
         for (int b = bits - 1; b >= 0; --b)
             for (int k = d - 1; k >= 0; --k) code = (code << 1) | ((q[k] >> b) & 1u);
-        keys[e] = (code << 32) | (uint64_t)e;
+        keys[e] = {code, e};
     }
     std::sort(keys.begin(), keys.end());
-    for (uint64_t e = 0; e < E; ++e) order[e] = (int32_t)(keys[e] & 0xffffffffull);
+    for (uint64_t e = 0; e < E; ++e) {
+        order[e] = (int32_t)keys[e].second;
+        codes[e] = keys[e].first;
+    }
 }
 
 static fb200_status upload_order(fb200_ctx* ctx) {
@@ -80,8 +96,15 @@ static fb200_status upload_order(fb200_ctx* ctx) {
     if (ctx->h_order.empty()) return FB200_OK;
     std::vector<int32_t> owned;
     owned.reserve(ctx->E_owned);
-    for (int32_t e : ctx->h_order)
-        if ((uint64_t)e < ctx->E_owned) owned.push_back(e);
+    ctx->h_order_codes.clear();
+    ctx->h_order_codes.reserve(ctx->E_owned);
+    for (size_t i = 0; i < ctx->h_order.size(); ++i) {
+        const int32_t e = ctx->h_order[i];
+        if ((uint64_t)e < ctx->E_owned) {
+            owned.push_back(e);
+            ctx->h_order_codes.push_back(ctx->h_order_codes_all[i]);
+        }
+    }
     FB200_TRY(dev_alloc(ctx, &ctx->d_order, owned.size()));
     if (!owned.empty()) FB200_CUDA(ctx, cudaMemcpy(ctx->d_order, owned.data(), owned.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     ctx->order_count = owned.size();
@@ -93,6 +116,8 @@ void free_space(fb200_ctx* ctx) {
     dev_free(ctx->d_order);
     ctx->order_count = 0;
     ctx->h_order.clear();
+    ctx->h_order_codes_all.clear();
+    ctx->h_order_codes.clear();
     dev_free(ctx->d_row_epoch);
     dev_free(ctx->d_vertices);
     dev_free(ctx->d_conn);
@@ -266,6 +291,16 @@ fb200_status fb200_timer_end(fb200_ctx* ctx, float* ms) {
 
 uint64_t fb200_launch_count(fb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (name && std::strcmp(name, "hex8_tile") == 0) {
+        if (value != 0 && value != 64) return fail(ctx, FB200_ERR_SHAPE, "hex8_tile must be 0 or 64");
+        ctx->tune_hex8_tile = value;
+        return FB200_OK;
+    }
+    return fail(ctx, FB200_ERR_UNSUPPORTED, "unknown tuning knob");
+}
+
 static fb200_status upload_indices(fb200_ctx* ctx, const uint64_t* host, uint64_t count, uint64_t per_element, int32_t** d_out) {
     uint64_t* d_tmp = nullptr;
     FB200_TRY(dev_alloc(ctx, &d_tmp, count));
@@ -310,7 +345,7 @@ fb200_status fb200_space_upload(fb200_ctx* ctx, int32_t element_type, uint64_t n
     }
     ctx->has_space = ctx->has_connectivity = true;
     ctx->ragged = false;
-    morton_order(ei.d, ei.n, num_nodes, vertices, num_elements, connectivity, ctx->h_order);  // indices were validated above
+    morton_order(ei.d, ei.n, num_nodes, vertices, num_elements, connectivity, ctx->h_order, ctx->h_order_codes_all);  // indices were validated above
     return upload_order(ctx);
 }
 

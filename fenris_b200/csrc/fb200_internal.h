@@ -57,6 +57,44 @@ struct HostChunks {
 void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
                        const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
 
+// tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
+constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
+constexpr int kTileHdrWords = 8;   // elem_begin, n_elems, n_nodes, n_slots(P), node_begin, flush_begin, n_flush, rounds (8 bits per pass)
+struct TileShape {
+    int tile_bits;    // low Morton bits dropped to name a tile (5: 4 x 4 x 2 elements, 6: 4 x 4 x 4)
+    int max_elems;    // elements per tile (= passes * warps, at most 4 passes)
+    int warps;        // warps per CTA: elements processed concurrently in one pass
+    int max_nodes;    // distinct nodes per tile (<= 128)
+    int max_slots;    // accumulator positions per tile (upper-triangle node blocks + padding)
+};
+struct HostTiles {
+    std::vector<uint32_t> hdr;        // num_tiles * kTileHdrWords
+    std::vector<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
+    std::vector<uint32_t> flush;      // per (row node u, coupled node v) in CSR order: position | transposed << 11 | u << 12 | k << 19
+    std::vector<uint8_t> lnodes;      // count * 8: tile-local node index of each element node (7 bits; bit 7 of bytes 0-4 = sub), schedule order
+    std::vector<uint16_t> emap;       // count * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
+    std::vector<uint8_t> sub;         // count: sub-round of the element inside its pass
+    std::vector<int32_t> elem;        // count: element id of each schedule position
+    double bank_conflict_share = 0;   // diagnostic: share of accumulate accesses that collide in a shared-memory bank
+};
+void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
+                      uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out);
+
+struct TileLists {
+    bool valid = false;
+    bool unusable = false;  // the mesh has no usable tile lists (degenerate elements): keep the per-element kernel
+    uint64_t count = 0;
+    const int32_t* ids = nullptr;
+    int tile_bits = 0;
+    uint32_t num_tiles = 0;
+    uint32_t* d_hdr = nullptr;
+    int32_t* d_nodes = nullptr;
+    uint32_t* d_flush = nullptr;
+    uint8_t* d_lnodes = nullptr;
+    uint16_t* d_emap = nullptr;
+    int32_t* d_elem = nullptr;
+};
+
 struct ChunkLists {
     bool valid = false;
     uint64_t count = 0;
@@ -101,9 +139,12 @@ struct fb200_ctx {
     int32_t* d_order = nullptr;
     uint64_t order_count = 0;
     std::vector<int32_t> h_order;  // over all E elements; filtered to the owned ones on upload
+    std::vector<uint64_t> h_order_codes_all, h_order_codes;  // Morton codes of h_order / of the owned elements in d_order
 
     fb200::OrderedCopy ord_morton, ord_colors;
     fb200::ChunkLists chunks;
+    fb200::TileLists tiles;
+    int tune_hex8_tile = -1;  // fb200_set_tuning("hex8_tile"); -1 = FB200_HEX8_TILE from the environment, else 64
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;

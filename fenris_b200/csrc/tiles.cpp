@@ -1,0 +1,345 @@
+// Host preprocessing for the tile-accumulating Hex8 kernel (hex8_tile_kernel.cuh).
+//
+// The reference adds every row of every K_e to the CSR separately (global.rs:155-178, 504-537).  On the device each such addition is
+// an fp64 reduction in L2 and it is the L2 reduction rate - not HBM, not the FP64 pipe - that bounds the Hex8 assembly
+// (profiles/r01/README.md).  Neighbouring elements share most of their node blocks: in a 4 x 4 x 4 block of hexahedra the 64 x 64
+// element blocks land in only 2197 distinct CSR node blocks, and 27 of the 125 nodes have ALL their elements inside the block.  The
+// lists built here let one CTA sum a tile of consecutive elements of the Morton order in shared memory and touch every CSR node
+// block of the tile once - with a plain store when the row node is complete inside the tile.
+//
+// Per tile (a run of positions of the processing order that share the Morton prefix code >> tile_bits, split further if it would
+// exceed the node / accumulator limits):
+//   nodes      the distinct nodes, ascending global id (tile-local index u = rank); bit 31 = complete inside the tile
+//   slots      one accumulator per node pair (u, v), u <= v, coupled inside the tile: K_e is symmetric block-wise
+//              (K_ba = K_ab^T bit for bit, see assemble.cu), so only blocks with u_a <= u_b are accumulated and the flush writes
+//              (u, v) and (v, u)^T from the same sums - the assembled matrix is exactly symmetric, as the reference's
+//              upper-triangle-then-mirror rule makes it (operators.rs:177-180, util.rs:38-50)
+//   positions  accumulator position of a slot, chosen so that the 16 lanes of a half-warp - which hold the blocks (a, b) with
+//              a in {0..3} or {4..7} and b in {0,2,4,6} or {1,3,5,7} (the DMMA accumulator fragment) - fall into 16 different
+//              shared-memory banks: position mod 16 = 4 alpha(u) + (beta(v) + rot(u)) mod 4, where alpha / beta are 4-colourings
+//              of the tile nodes that separate the nodes of every element face {0..3}, {4..7} resp. of {0,2,4,6}, {1,3,5,7}
+//              (greedy; on structured meshes they are the coordinate parities), and rot(u) balances the 16 residue classes
+//   flush      per (u, v) in CSR order of row u, one word: accumulator position (11 bits) | transposed << 11 | u << 12 | k << 19,
+//              k = position of v in the block row of u (from the node-block map; meshes with block rows >= 8192 keep the
+//              per-element kernel)
+//   schedule   the tile's elements ordered by a greedy node-disjoint colouring (fenris-paradis' idea, coloring.rs:6-70, applied
+//              inside the tile): a pass = `warps` consecutive schedule positions computed concurrently; elements of a pass add
+//              their blocks in sub-rounds (one per colour present in the pass) separated by CTA barriers, so no two warps ever
+//              update the same accumulator concurrently
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
+#include "fb200_internal.h"
+
+namespace fb200 {
+
+namespace {
+
+struct TileOut {
+    uint64_t p0 = 0;
+    int ne = 0;
+    uint32_t P = 0, rounds = 0;
+    std::vector<int32_t> nodes;
+    std::vector<uint32_t> flush;
+};
+
+struct Builder {
+    const TileShape& shape;
+    const int32_t* order;
+    const int32_t* conn;
+    const uint16_t* blockmap;
+    const int32_t* degree;
+    HostTiles& out;
+    uint64_t conflicts = 0, accesses = 0;
+    bool degenerate = false;
+
+    struct RowEntry {
+        uint16_t k;
+        uint8_t v;
+        uint16_t pos;  // accumulator position (v >= u only)
+    };
+    std::vector<int32_t> nodes;
+    std::vector<int> inc;
+    std::vector<std::vector<RowEntry>> rows;
+    std::vector<std::vector<int>> node_elems;
+    std::vector<uint8_t> ln;  // ne * 8
+
+    uint64_t elem_at(uint64_t pos) const { return order ? (uint64_t)order[pos] : pos; }
+
+    // 4-colouring of the tile nodes that separates the members of every group (two groups of 4 local nodes per element)
+    void label(int ne, const int (&groups)[2][4], std::vector<uint8_t>& lab) const {
+        const int nn = (int)nodes.size();
+        lab.assign(nn, 0xff);
+        for (int u = 0; u < nn; ++u) {
+            int used[4] = {0, 0, 0, 0};
+            for (int el : node_elems[u])
+                for (int g = 0; g < 2; ++g) {
+                    bool member = false;
+                    for (int t = 0; t < 4; ++t) member |= ln[el * 8 + groups[g][t]] == u;
+                    if (!member) continue;
+                    for (int t = 0; t < 4; ++t) {
+                        const int w = ln[el * 8 + groups[g][t]];
+                        if (w != u && lab[w] != 0xff) ++used[lab[w]];
+                    }
+                }
+            int best = 0;
+            for (int c = 1; c < 4; ++c)
+                if (used[c] < used[best]) best = c;
+            lab[u] = (uint8_t)best;
+        }
+        (void)ne;
+    }
+
+    bool build_one(uint64_t p0, int ne, TileOut& t) {
+        constexpr int n = 8, n2 = 64;
+        // ---- nodes
+        nodes.clear();
+        for (int el = 0; el < ne; ++el) {
+            const uint64_t e = elem_at(p0 + el);
+            for (int a = 0; a < n; ++a) nodes.push_back(conn[e * n + a]);
+        }
+        std::sort(nodes.begin(), nodes.end());
+        inc.clear();
+        {
+            size_t w = 0;
+            for (size_t i = 0; i < nodes.size();) {
+                size_t j = i;
+                while (j < nodes.size() && nodes[j] == nodes[i]) ++j;
+                nodes[w++] = nodes[i];
+                inc.push_back((int)(j - i));
+                i = j;
+            }
+            nodes.resize(w);
+        }
+        const int nn = (int)nodes.size();
+        if (nn > shape.max_nodes) return false;
+        ln.assign((size_t)ne * n, 0);
+        node_elems.assign(nn, {});
+        for (int el = 0; el < ne; ++el) {
+            const uint64_t e = elem_at(p0 + el);
+            for (int a = 0; a < n; ++a) {
+                const int u = (int)(std::lower_bound(nodes.begin(), nodes.end(), conn[e * n + a]) - nodes.begin());
+                ln[el * n + a] = (uint8_t)u;
+                if (node_elems[u].empty() || node_elems[u].back() != el) node_elems[u].push_back(el);
+                else degenerate = true;  // a node repeated inside one element: two lanes would share an accumulator
+            }
+        }
+        if (degenerate) return true;
+        // ---- rows: coupled nodes of every tile node, ordered by their position k in the global block row
+        rows.assign(nn, {});
+        for (int el = 0; el < ne; ++el) {
+            const uint64_t e = elem_at(p0 + el);
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) rows[ln[el * n + a]].push_back({blockmap[e * n2 + a * n + b], ln[el * n + b], 0});
+        }
+        int nslots = 0, nflush = 0;
+        for (int u = 0; u < nn; ++u) {
+            auto& r = rows[u];
+            std::sort(r.begin(), r.end(), [](const RowEntry& x, const RowEntry& y) { return x.k < y.k; });
+            r.erase(std::unique(r.begin(), r.end(), [](const RowEntry& x, const RowEntry& y) { return x.k == y.k; }), r.end());
+            nflush += (int)r.size();
+            for (const RowEntry& x : r) nslots += x.v >= u;
+        }
+        if (nslots > shape.max_slots) return false;
+        // ---- bank-aware accumulator positions
+        static const int kFaces[2][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}};
+        static const int kStripes[2][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}};
+        std::vector<uint8_t> alpha, beta;
+        label(ne, kFaces, alpha);
+        label(ne, kStripes, beta);
+        const int cap = shape.max_slots / 16;
+        int fill[16] = {0};
+        for (int u = 0; u < nn; ++u) {
+            int c[4] = {0, 0, 0, 0};
+            for (const RowEntry& x : rows[u])
+                if (x.v >= u) ++c[beta[x.v]];
+            int best_rot = 0, best_max = 1 << 30;
+            for (int rot = 0; rot < 4; ++rot) {
+                int m = 0;
+                for (int b = 0; b < 4; ++b) m = std::max(m, fill[4 * alpha[u] + ((b + rot) & 3)] + c[b]);
+                if (m < best_max) {
+                    best_max = m;
+                    best_rot = rot;
+                }
+            }
+            for (RowEntry& x : rows[u]) {
+                if (x.v < u) continue;
+                int r = 4 * alpha[u] + ((beta[x.v] + best_rot) & 3);
+                if (fill[r] >= cap) {  // class full: take the emptiest one (costs a bank conflict, never correctness)
+                    r = 0;
+                    for (int q = 1; q < 16; ++q)
+                        if (fill[q] < fill[r]) r = q;
+                }
+                x.pos = (uint16_t)(r + 16 * fill[r]++);
+            }
+        }
+        int maxfill = 0;
+        for (int q = 0; q < 16; ++q) maxfill = std::max(maxfill, fill[q]);
+        t.P = (uint32_t)(16 * maxfill);
+        auto find_pos = [&](int u, uint16_t k) -> const RowEntry& {
+            const auto& r = rows[u];
+            return *std::lower_bound(r.begin(), r.end(), k, [](const RowEntry& x, uint16_t kk) { return x.k < kk; });
+        };
+        // ---- flush list + node list
+        t.p0 = p0;
+        t.ne = ne;
+        t.nodes.resize(nn);
+        for (int u = 0; u < nn; ++u) t.nodes[u] = nodes[u] | (inc[u] == degree[nodes[u]] ? (int32_t)0x80000000 : 0);
+        t.flush.clear();
+        t.flush.reserve(nflush);
+        for (int u = 0; u < nn; ++u)
+            for (const RowEntry& x : rows[u]) {
+                uint32_t pos, tr = 0;
+                if (x.v >= u) {
+                    pos = x.pos;
+                } else {  // mirrored block: find (v, u) in row v
+                    pos = 0xffffu;
+                    for (const RowEntry& y : rows[x.v])
+                        if (y.v == u) {
+                            pos = y.pos;
+                            break;
+                        }
+                    tr = 1;
+                }
+                if (x.k >= (1u << kTileKBits)) degenerate = true;
+                t.flush.push_back(pos | (tr << 11) | ((uint32_t)u << 12) | ((uint32_t)x.k << 19));
+            }
+        // ---- schedule: greedy node-disjoint colouring inside the tile, elements ordered by colour
+        std::vector<uint64_t> node_mask(nn, 0);
+        std::vector<int> colour(ne), sched(ne);
+        for (int el = 0; el < ne; ++el) {
+            uint64_t used = 0;
+            for (int a = 0; a < n; ++a) used |= node_mask[ln[el * n + a]];
+            int c = 0;
+            while (c < 63 && ((used >> c) & 1)) ++c;
+            colour[el] = c;
+            for (int a = 0; a < n; ++a) node_mask[ln[el * n + a]] |= 1ull << c;
+        }
+        for (int el = 0; el < ne; ++el) sched[el] = el;
+        std::stable_sort(sched.begin(), sched.end(), [&](int x, int y) { return colour[x] < colour[y]; });
+        t.rounds = 0;
+        for (int s0 = 0, pass = 0; s0 < ne; s0 += shape.warps, ++pass) {
+            const int s1 = std::min(ne, s0 + shape.warps);
+            int r = -1, last = -1;
+            for (int s = s0; s < s1; ++s) {
+                if (colour[sched[s]] != last) {
+                    ++r;
+                    last = colour[sched[s]];
+                }
+                out.sub[p0 + s] = (uint8_t)r;
+            }
+            t.rounds |= (uint32_t)(r + 1) << (8 * pass);  // <= 4 passes per tile (max_elems = 4 * warps), <= warps rounds each
+        }
+        for (int s = 0; s < ne; ++s) {
+            const int el = sched[s];
+            const uint64_t e = elem_at(p0 + el);
+            out.elem[p0 + s] = (int32_t)e;
+            for (int a = 0; a < n; ++a)  // bit 7 of the first five bytes carries the element's sub-round
+                out.lnodes[(p0 + s) * n + a] = (uint8_t)(ln[el * n + a] | (a < 5 ? ((out.sub[p0 + s] >> a) & 1) << 7 : 0));
+            uint16_t* em = &out.emap[(p0 + s) * (uint64_t)n2];
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) {
+                    const int u = ln[el * n + a], v = ln[el * n + b];
+                    em[a * n + b] = u <= v ? find_pos(u, blockmap[e * n2 + a * n + b]).pos : (uint16_t)0xffffu;
+                }
+            // diagnostic: bank collisions of the four half-warp access groups
+            for (int h = 0; h < 2; ++h)
+                for (int r = 0; r < 2; ++r) {
+                    int seen[16] = {0};
+                    for (int a = 4 * h; a < 4 * h + 4; ++a)
+                        for (int tq = 0; tq < 4; ++tq) {
+                            const uint16_t pos = em[a * n + 2 * tq + r];
+                            if (pos == 0xffffu) continue;
+                            ++accesses;
+                            if (seen[pos & 15]++) ++conflicts;
+                        }
+                }
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
+                      uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out) {
+    constexpr int n = 8;
+    std::vector<int32_t> degree(num_nodes, 0);
+    for (uint64_t pos = 0; pos < count; ++pos) {
+        const uint64_t e = order ? (uint64_t)order[pos] : pos;
+        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
+    }
+    out.hdr.clear();
+    out.nodes.clear();
+    out.flush.clear();
+    out.lnodes.assign(count * n, 0);
+    out.emap.assign(count * 64, 0);
+    out.sub.assign(count, 0);
+    out.elem.assign(count, 0);
+    out.bank_conflict_share = 0;
+    // candidate tiles: runs with a common Morton prefix
+    std::vector<std::pair<uint64_t, int>> cand;
+    for (uint64_t p0 = 0; p0 < count;) {
+        int ne = 1;
+        while (ne < shape.max_elems && p0 + ne < count && (codes[p0 + ne] >> shape.tile_bits) == (codes[p0] >> shape.tile_bits)) ++ne;
+        cand.emplace_back(p0, ne);
+        p0 += ne;
+    }
+    std::vector<std::vector<TileOut>> results(cand.size());
+    std::atomic<uint64_t> next{0};
+    std::atomic<uint64_t> conflicts{0}, accesses{0};
+    std::atomic<bool> degenerate{false};
+    auto worker = [&]() {
+        Builder b{shape, order, conn, blockmap, degree.data(), out};
+        std::vector<std::pair<uint64_t, int>> stack;
+        for (;;) {
+            const uint64_t c0 = next.fetch_add(64);
+            if (c0 >= cand.size() || degenerate.load()) break;
+            for (uint64_t c = c0; c < std::min<uint64_t>(cand.size(), c0 + 64); ++c) {
+                stack.assign(1, cand[c]);
+                while (!stack.empty()) {
+                    const auto [p0, ne] = stack.back();
+                    stack.pop_back();
+                    TileOut t;
+                    if (b.build_one(p0, ne, t)) {
+                        if (b.degenerate) break;
+                        results[c].push_back(std::move(t));
+                    } else {  // over the limits: halve (a single Hex8 element always fits: 8 nodes, 36 slots)
+                        const int h = ne / 2;
+                        stack.emplace_back(p0 + h, ne - h);
+                        stack.emplace_back(p0, h);
+                    }
+                }
+                if (b.degenerate) {
+                    degenerate.store(true);
+                    break;
+                }
+            }
+        }
+        conflicts += b.conflicts;
+        accesses += b.accesses;
+    };
+    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, cand.size() / 64));
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    if (degenerate.load()) {  // elements with repeated nodes (or huge block rows): the caller keeps the per-element kernel
+        out.hdr.clear();
+        out.bank_conflict_share = -1.0;
+        return;
+    }
+    for (auto& rs : results)
+        for (TileOut& t : rs) {
+            const uint32_t hdr[kTileHdrWords] = {(uint32_t)t.p0,          (uint32_t)t.ne,           (uint32_t)t.nodes.size(),   t.P,
+                                                 (uint32_t)out.nodes.size(), (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), t.rounds};
+            out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
+            out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
+            out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
+        }
+    out.bank_conflict_share = accesses.load() ? (double)conflicts.load() / (double)accesses.load() : 0.0;
+}
+
+}  // namespace fb200

@@ -102,6 +102,9 @@ fb200_status fb200_timer_begin(fb200_ctx* ctx);
 fb200_status fb200_timer_end(fb200_ctx* ctx, float* milliseconds); /* synchronizes */
 /* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t fb200_launch_count(fb200_ctx* ctx);
+/* Kernel-selection knobs (no reference counterpart; results never depend on them beyond fp reassociation).
+ * "hex8_tile": elements per shared-memory tile of the Hex8 atomic scatter - 64 (default) or 0 = per-element kernel. */
+fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value);
 
 /* ---- the space: Mesh<f64, D, C>  (src/mesh.rs:23-40) --------------------------------------- */
 /* vertices: num_nodes x d AoS (Vec<OPoint<f64,D>>); connectivity: num_elements x n row-major (Vec<C([usize; n])>).

@@ -1,0 +1,162 @@
+"""GPU parity tests of the Hex8 tile-accumulating scatter (hex8_tile_kernel.cuh + tiles.cpp) against the oracle.
+
+The tile kernel replaces the per-element row scatter of global.rs:155-178, 504-537 for Hex8 + ATOMIC; the per-element
+kernel (hex8_tile = 0), the coloured and the gather scatter are independent implementations of the same sums.
+Tolerance: 1e-12 relative Frobenius norm (north_star); symmetry to rounding."""
+import numpy as np
+import pytest
+
+import fenris_b200 as fb
+from oracle import cpu_ref as cr
+from oracle import fenris_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+MU, LAM = fo.lame_from_young_poisson(1e6, 0.2)
+TILES = [64, 0]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = fb.Context(0)
+    yield c
+    c.close()
+
+
+def _hex(n, jitter=0.0, scramble=False, seed=7):
+    m = fb.create_unit_box_uniform_hex_mesh_3d(n)
+    v, c = m.vertices(), m.connectivity()
+    if jitter:
+        v = fo.jitter_vertices(v, 1.0 / n, amp=jitter)
+    if scramble:  # arbitrary node numbering and element order: nothing structured is left but the geometry
+        rng = np.random.default_rng(seed)
+        perm = rng.permutation(len(v))
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(v))
+        v = v[perm]
+        c = inv[c.astype(np.int64)].astype(np.uint64)
+        c = c[rng.permutation(len(c))]
+    return fb.Mesh(np.ascontiguousarray(v), np.ascontiguousarray(c), fb.HEX8)
+
+
+def _assemble(ctx, m, op, tile, accumulate=False):
+    prob = fo.Problem(fo.HEX8, m.vertices(), m.connectivity().astype(np.int64), op, params=() if op == fo.LAPLACE else (MU, LAM))
+    ctx.set_tuning("hex8_tile", tile)
+    ctx.assemble_into_csr_device(op, prob.weights, prob.points, None if op == fo.LAPLACE else (MU, LAM),
+                                 scatter_mode=fb.SCATTER_ATOMIC, accumulate=accumulate)
+    ctx.synchronize()
+    return prob
+
+
+@pytest.mark.parametrize("tile", TILES)
+@pytest.mark.parametrize("n,op,jit,scramble", [(9, fo.LINEAR_ELASTIC, 0.2, False), (8, fo.LINEAR_ELASTIC, 0.0, False),
+                                              (10, fo.LAPLACE, 0.15, False), (7, fo.LINEAR_ELASTIC, 0.1, True),
+                                              (1, fo.LINEAR_ELASTIC, 0.0, False), (2, fo.LAPLACE, 0.1, False)])
+def test_tile_scatter_equals_oracle(ctx, tile, n, op, jit, scramble):
+    m = _hex(n, jit, scramble)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    sdim = 1 if op == fo.LAPLACE else 3
+    ctx.assemble_pattern(sdim)
+    prob = _assemble(ctx, m, op, tile)
+    oro, oci, ovals = fo.assemble_fast(prob)
+    ro, ci = ctx.pattern_download()
+    assert np.array_equal(ro, oro) and np.array_equal(ci, oci)
+    vals = ctx.values_download()
+    assert fo.rel_frobenius(vals, ovals) < TOL, (tile, n, op)
+    # upper-triangle-then-mirror semantics (operators.rs:177-180, util.rs:38-50): (u, v) and (v, u) get the same per-tile sums;
+    # only the order in which different tiles' partial sums reach a shared row differs
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals, ci.astype(np.int64), ro.astype(np.int64)), shape=(len(ro) - 1,) * 2)
+    assert abs(A - A.T).max() <= 4e-16 * np.abs(vals).max()
+
+
+@pytest.mark.parametrize("tile", TILES)
+def test_tile_accumulate_semantics(ctx, tile):
+    # assemble_into_csr adds to the existing values (global.rs:534): complete rows must not be overwritten then
+    m = _hex(6, 0.1)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(3)
+    prob = _assemble(ctx, m, fo.LINEAR_ELASTIC, tile)
+    once = ctx.values_download().copy()
+    start = np.linspace(-1.0, 3.0, ctx.nnz) * np.abs(once).max()
+    ctx.values_upload(start)
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, tile, accumulate=True)
+    assert fo.rel_frobenius(ctx.values_download() - start, once) < 1e-12
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, tile, accumulate=False)
+    assert np.array_equal(ctx.values_download(), once) or fo.rel_frobenius(ctx.values_download(), once) < 1e-15
+
+
+@pytest.mark.parametrize("tile", [64])
+def test_tile_degenerate_elements_fall_back(ctx, tile):
+    # an element with a repeated node cannot use the tile accumulators (two lanes would share one): the library must fall back to
+    # the per-element kernel and still produce the reference's sums (the collapsed element itself is singular)
+    m = _hex(3)
+    c = m.connectivity().copy()
+    c[5, 1] = c[5, 0]
+    ctx.space_upload(fb.HEX8, m.vertices(), c)
+    ctx.assemble_pattern(1)
+    w, p = fb.canonical_stiffness_quadrature(fb.HEX8)
+    ctx.set_tuning("hex8_tile", tile)
+    ctx.assemble_into_csr_device(fo.LAPLACE, w, p, None, scatter_mode=fb.SCATTER_ATOMIC)
+    a = None
+    try:
+        ctx.synchronize()
+        a = ctx.values_download().copy()
+    except fb.SingularJacobianError:
+        pass
+    ctx.set_tuning("hex8_tile", 0)
+    ctx.assemble_into_csr_device(fo.LAPLACE, w, p, None, scatter_mode=fb.SCATTER_ATOMIC)
+    try:
+        ctx.synchronize()
+        b = ctx.values_download()
+        assert a is not None and fo.rel_frobenius(a, b) < TOL
+    except fb.SingularJacobianError:
+        assert a is None
+
+
+def test_tile_singular_element_index(ctx):
+    # the deferred error reports the smallest offending ELEMENT id, not a schedule position (elliptic.rs:401-404)
+    cube = (np.array(fo._HEX8_NODES) + 1.0) / 2.0
+    v = np.concatenate([cube + [2.0 * k, 0, 0] for k in range(6)])
+    v[16:24] = 0.5
+    v[40:48] = 0.25
+    c = np.arange(48, dtype=np.uint64).reshape(6, 8)
+    ctx.space_upload(fb.HEX8, v, c)
+    ctx.assemble_pattern(3)
+    w, p = fb.canonical_stiffness_quadrature(fb.HEX8)
+    for tile in TILES:
+        ctx.set_tuning("hex8_tile", tile)
+        ctx.assemble_into_csr_device(fo.LINEAR_ELASTIC, w, p, (MU, LAM), scatter_mode=fb.SCATTER_ATOMIC)
+        with pytest.raises(fb.SingularJacobianError) as ei:
+            ctx.synchronize()
+        assert ei.value.element_index == 2
+
+
+@pytest.mark.parametrize("tile", [64])
+def test_tile_40_cubed_vs_c_oracle_and_modes(ctx, tile):
+    n = 40
+    m = _hex(n, 0.1)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(3)
+    ro, ci = ctx.pattern_download()
+    w, p = fb.canonical_stiffness_quadrature(fb.HEX8)
+    colors = cr.color_greedy(m.connectivity(), m.num_nodes())
+    ref = cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, w, p, (MU, LAM), m.vertices(), m.connectivity(), ro, ci, colors=colors)
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, tile)
+    vals = ctx.values_download().copy()
+    assert fo.rel_frobenius(vals, ref) < TOL
+    ctx.assemble_into_csr_device(fo.LINEAR_ELASTIC, w, p, (MU, LAM), scatter_mode=fb.SCATTER_GATHER)
+    ctx.synchronize()
+    assert fo.rel_frobenius(vals, ctx.values_download()) < 1e-14
+
+
+def test_tile_repeatable(ctx):
+    # within a tile the sums are formed in a fixed order; only the reductions into rows shared between tiles commute
+    m = _hex(12, 0.1)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(3)
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, 64)
+    a = ctx.values_download().copy()
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, 64)
+    assert fo.rel_frobenius(ctx.values_download(), a) < 1e-15
