@@ -823,7 +823,7 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
 
 // Hex8 tile kernel (hex8_tile_kernel.cuh): a CTA accumulates a tile of the Morton order in shared memory and updates every CSR
 // node block of the tile once.  *used = false when the mesh has no usable tile lists (the caller falls back to the element kernel).
-template <int OP, int WARPS, int MAXN, int MAXP>
+template <int OP, int MAXN, int MAXP>
 static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const TileShape& shape, bool* used) {
     *used = false;
     FB200_TRY(ensure_tiles(ctx, shape));
@@ -838,29 +838,30 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
     p.tile_lnodes = tl.d_lnodes;
     p.tile_emap = tl.d_emap;
     p.tile_elem = tl.d_elem;
-    const size_t smem = Hex8TileSmem<OP, WARPS, MAXN, MAXP>::bytes;
-    auto kernel = assemble_hex8_tile_kernel<OP, WARPS, MAXN, MAXP>;
+    const size_t smem = Hex8TileSmem<OP, MAXN, MAXP>::bytes;
+    auto kernel = assemble_hex8_tile_kernel<OP, MAXN, MAXP>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    constexpr int THREADS = (2 * kTileGroupWarps + kTileHelperWarps) * 32;
+    FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
     if (per_sm < 1) return fail(ctx, FB200_ERR_CUDA, "assemble_hex8_tile_kernel does not fit on an SM");
-    const int blocks = (int)std::min<uint64_t>(tl.num_tiles, (uint64_t)ctx->sm_count * per_sm);
+    const int blocks = (int)std::min<uint64_t>(tl.num_tiles, (uint64_t)ctx->sm_count);  // one persistent CTA per SM
     p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
     static const int debug = std::getenv("FB200_DEBUG") ? std::atoi(std::getenv("FB200_DEBUG")) : 0;
     p.debug = debug;
     FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
-    kernel<<<blocks, WARPS * 32, smem, ctx->stream>>>(p);
+    kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
     return check_launch(ctx, "assemble_hex8_tile_kernel");
 }
 
-// tile shape: 4 x 4 x 4 elements, one CTA of 16 warps per SM (double-buffered accumulators: 2 x 85.5 KB of shared memory);
+// tile shape: 4 x 4 x 4 elements, one CTA of 16 compute + 8 helper warps per SM (double-buffered accumulators: 2 x 85.5 KB);
 // FB200_HEX8_TILE = 64 | 0 (off), overridden by fb200_set_tuning("hex8_tile")
 template <int OP>
 static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* used) {
     static const int env_tile = std::getenv("FB200_HEX8_TILE") ? std::atoi(std::getenv("FB200_HEX8_TILE")) : 64;
     const int tile = ctx->tune_hex8_tile >= 0 ? ctx->tune_hex8_tile : env_tile;
     *used = false;
-    if (tile == 64) return launch_hex8_tile_t<OP, 16, 128, 1216>(ctx, p, TileShape{6, 64, 16, 128, 1216}, used);
+    if (tile == 64) return launch_hex8_tile_t<OP, 128, 1216>(ctx, p, TileShape{6, 64, kTileGroupWarps, 128, 1216}, used);
     return FB200_OK;
 }
 

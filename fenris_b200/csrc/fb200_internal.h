@@ -59,11 +59,11 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
-constexpr int kTileHdrWords = 8;   // elem_begin, n_elems, n_nodes, n_slots(P), node_begin, flush_begin, n_flush, rounds (8 bits per pass)
+constexpr int kTileHdrWords = 8;   // first schedule position, rounds, n_nodes, n_slots(P), node_begin, flush_begin, n_flush, n_elems
 struct TileShape {
     int tile_bits;    // low Morton bits dropped to name a tile (5: 4 x 4 x 2 elements, 6: 4 x 4 x 4)
-    int max_elems;    // elements per tile (= passes * warps, at most 4 passes)
-    int warps;        // warps per CTA: elements processed concurrently in one pass
+    int max_elems;    // elements per tile
+    int warps;        // elements per round = warps per compute group
     int max_nodes;    // distinct nodes per tile (<= 128)
     int max_slots;    // accumulator positions per tile (upper-triangle node blocks + padding)
 };
@@ -71,10 +71,9 @@ struct HostTiles {
     std::vector<uint32_t> hdr;        // num_tiles * kTileHdrWords
     std::vector<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
     std::vector<uint32_t> flush;      // per (row node u, coupled node v) in CSR order: position | transposed << 11 | u << 12 | k << 19
-    std::vector<uint8_t> lnodes;      // count * 8: tile-local node index of each element node (7 bits; bit 7 of bytes 0-4 = sub), schedule order
-    std::vector<uint16_t> emap;       // count * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
-    std::vector<uint8_t> sub;         // count: sub-round of the element inside its pass
-    std::vector<int32_t> elem;        // count: element id of each schedule position
+    std::vector<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
+    std::vector<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
+    std::vector<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
     double bank_conflict_share = 0;   // diagnostic: share of accumulate accesses that collide in a shared-memory bank
 };
 void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,

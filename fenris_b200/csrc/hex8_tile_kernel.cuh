@@ -6,21 +6,24 @@
 // fenris-solid/src/materials.rs:108-122).  What changes is the scatter (global.rs:155-178, 504-537).
 //
 // Measured on B200 the per-element scatter - 24 reductions of 24 doubles per element - is bound by the L2 reduction rate: every CSR
-// value receives 2.4 reductions on a structured Hex8 mesh.  Here ONE persistent CTA of 16 warps per SM owns a TILE of up to 64
+// value receives 2.4 reductions on a structured Hex8 mesh.  Here ONE persistent, warp-specialised CTA per SM owns a TILE of up to 64
 // consecutive elements of the Morton order at a time (lists from tiles.cpp) and runs a software pipeline over tiles:
-//   tables   the tile's node ids, coordinates and block-row offsets live in shared memory; they are fetched for the NEXT tile with
-//            cp.async while the current one is computed (header -> node ids -> coordinates / offsets: one stage of the dependent
-//            chain per pass; the ticket is drawn two tiles ahead), so no global-load latency is exposed per element
-//   passes   16 elements at a time, one per warp: geometry + DMMA contraction in registers (two 3 x 3 node blocks per lane),
-//            then the blocks with u_a <= u_b are added to the tile's accumulators in shared memory.  Accumulator positions are
-//            chosen on the host so that the 16 lanes of a half-warp hit 16 different banks; elements that share nodes add in
-//            different sub-rounds (CTA barrier in between), so there are no shared-memory atomics.
-//   flush    the accumulators are double buffered: while tile i is computed, every node block (u, v) of tile i-1 goes to the CSR
-//            ONCE - one slice of the flush list per pass, so the reductions drain underneath the FP64 work instead of in a phase
-//            of their own.  Lanes run over (block, column) in CSR order of row u, so an instruction covers whole runs of
-//            neighbouring node blocks (72 B each); blocks below the diagonal are read transposed from the (v, u) accumulator.
-//            Rows of nodes whose elements all lie in the tile are complete: they are written with plain stores (no reduction,
-//            no DRAM read of the line) when the call overwrites.
+//   compute warps (2 groups of 8)  one element per warp and ROUND: geometry + DMMA contraction in registers (two 3 x 3 node blocks
+//            per lane), then the blocks with u_a <= u_b are added to the tile's accumulators in shared memory.  Accumulator
+//            positions are chosen on the host so that the 16 lanes of a half-warp hit 16 different banks.  A round holds up to 8
+//            elements that share no node; the two groups take the rounds alternately and add strictly in round order - group g
+//            waits on a named barrier for the other group's previous round and signals its own (bar.sync / bar.arrive) - so
+//            there are no shared-memory atomics, and one group computes while the other one adds.
+//   helper warps (8)    everything that is not arithmetic, ahead of / behind the compute warps (they give most of their registers
+//            to the compute warps, setmaxnreg):
+//            tables  node ids, coordinates and block-row offsets of the coming tiles are fetched into shared memory with
+//                    cp.async, one stage of the dependent chain (ticket -> header -> node ids -> coordinates / offsets) per
+//                    tile, so neither they nor the compute warps ever wait for a dependent global load;
+//            flush   the accumulators are double buffered: while tile i is computed, every node block (u, v) of tile i-1 goes to
+//                    the CSR ONCE.  Lanes run over (block, column) in CSR order of row u, so an instruction covers whole runs of
+//                    neighbouring node blocks (72 B each); blocks below the diagonal are read transposed from the (v, u)
+//                    accumulator.  Rows of nodes whose elements all lie in the tile are complete: they are written with plain
+//                    stores (no reduction, no DRAM read of the line) when the call overwrites.
 // On the structured C3 mesh this is 1.27 CSR updates per value instead of 2.4, 42 % of them plain stores.  Sums differ from the
 // per-element kernels by fp reassociation only; (u, v) and (v, u) receive identical per-tile partial sums.
 //
@@ -51,46 +54,220 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int OP, int WARPS, int MAXN, int MAXP>
+constexpr int kTileGroupWarps = 8;   // warps per compute group = elements per round (tiles.cpp: TileShape::warps)
+constexpr int kTileHelperWarps = 8;
+constexpr int kTileHelperRegs = 48, kTileComputeRegs = 96;  // setmaxnreg: the helpers hand their registers to the compute warps
+
+template <int OP, int MAXN, int MAXP>
 struct Hex8TileSmem {
     static constexpr int S = OP == FB200_LAPLACE ? 1 : 3;
     static constexpr int BS = S * S;
+    static constexpr int WARPS = 2 * kTileGroupWarps;
     static constexpr int GS = 28;                       // node stride of the transposed gradient array (hex8_mma_kernel.cuh)
     static constexpr int WARP_DOUBLES = 24 + 8 * GS;
     static constexpr int ACC = (MAXP * BS + 1) & ~1;    // one accumulator buffer
-    // per table buffer: X[MAXN][3] doubles, off[MAXN][2] int64, ids[MAXN] int32, header 8 x uint32
-    static constexpr int BUF_BYTES = MAXN * 3 * 8 + MAXN * 2 * 8 + MAXN * 4 + 32;
-    static constexpr int FROW_BYTES = MAXN * 2 * 8;     // flush row table of one tile
+    static constexpr int BIG_BYTES = MAXN * 3 * 8 + MAXN * 2 * 8;  // X[MAXN][3] doubles, off[MAXN][2] int64 (current / next tile)
+    static constexpr int SMALL_BYTES = 32 + MAXN * 4;              // header 8 x uint32, ids[MAXN] int32 (ring of 4 tiles)
+    static constexpr int FROW_BYTES = MAXN * 2 * 8;                // flush row table of one tile
     static constexpr size_t bytes =
-        sizeof(double) * (size_t)(2 * ACC + WARPS * WARP_DOUBLES) + 2 * (size_t)BUF_BYTES + 2 * (size_t)FROW_BYTES + 16;
+        sizeof(double) * (size_t)(2 * ACC + WARPS * WARP_DOUBLES) + 2 * (size_t)BIG_BYTES + 4 * (size_t)SMALL_BYTES + 2 * (size_t)FROW_BYTES + 16;
 };
 
-template <int OP, int WARPS, int MAXN, int MAXP>
-__global__ void __launch_bounds__(WARPS * 32, 1) assemble_hex8_tile_kernel(const AssembleParams p) {
-    using L = Hex8TileSmem<OP, WARPS, MAXN, MAXP>;
-    constexpr int N = 8, D = 3, S = L::S, BS = L::BS, GS = L::GS;
-    constexpr int T = WARPS * 32;
-    constexpr int NSTAGE = 3;   // header, node ids, coordinates / offsets
-    constexpr int NSLICE = 4;   // the previous tile's flush list is drained in this many slices
-    constexpr int FB = 4;       // flush items per thread and slice
+__device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int OP, int MAXN, int MAXP>
+__global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32, 1) assemble_hex8_tile_kernel(const AssembleParams p) {
+    using L = Hex8TileSmem<OP, MAXN, MAXP>;
+    constexpr int N = 8, D = 3, S = L::S, BS = L::BS, GS = L::GS, WARPS = L::WARPS, GW = kTileGroupWarps;
+    constexpr int TC = WARPS * 32;              // compute threads
+    constexpr int TH = kTileHelperWarps * 32;   // helper threads
+    constexpr int BAR_HELPER = 3;               // named barriers: 1, 2 = round hand-over of the compute groups, 3 = helpers, 0 = everybody
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert(MAXN <= T && MAXN <= 128, "one thread per tile node, 7-bit node index");
-    static_assert(NSLICE * FB * T >= 3 * 2 * MAXP, "the slices must cover the flush list of a full tile");
+    static_assert(MAXN <= TH && MAXN <= 128 && GW % 4 == 0 && kTileHelperWarps % 4 == 0, "one helper thread per tile node, 7-bit node index, whole warpgroups");
     extern __shared__ __align__(16) double smem[];
     double* wbase = smem + 2 * L::ACC;
     unsigned char* bufbase = reinterpret_cast<unsigned char*>(wbase + WARPS * L::WARP_DOUBLES);
-    auto buf_X = [&](int b) { return reinterpret_cast<double*>(bufbase + b * L::BUF_BYTES); };
-    auto buf_off = [&](int b) { return reinterpret_cast<long long*>(bufbase + b * L::BUF_BYTES + MAXN * 24); };
-    auto buf_ids = [&](int b) { return reinterpret_cast<int*>(bufbase + b * L::BUF_BYTES + MAXN * 40); };
-    auto buf_hdr = [&](int b) { return reinterpret_cast<uint32_t*>(bufbase + b * L::BUF_BYTES + MAXN * 44); };
-    auto buf_frow = [&](int b) { return reinterpret_cast<long long*>(bufbase + 2 * L::BUF_BYTES + b * L::FROW_BYTES); };
-    uint32_t* s_tick = reinterpret_cast<uint32_t*>(bufbase + 2 * L::BUF_BYTES + 2 * L::FROW_BYTES);  // [2]: tile held by each buffer
+    auto big_X = [&](int b) { return reinterpret_cast<double*>(bufbase + b * L::BIG_BYTES); };
+    auto big_off = [&](int b) { return reinterpret_cast<long long*>(bufbase + b * L::BIG_BYTES + MAXN * 24); };
+    unsigned char* smallbase = bufbase + 2 * L::BIG_BYTES;
+    auto small_hdr = [&](int sl) { return reinterpret_cast<uint32_t*>(smallbase + sl * L::SMALL_BYTES); };
+    auto small_ids = [&](int sl) { return reinterpret_cast<int*>(smallbase + sl * L::SMALL_BYTES + 32); };
+    unsigned char* frowbase = smallbase + 4 * L::SMALL_BYTES;
+    auto buf_frow = [&](int b) { return reinterpret_cast<long long*>(frowbase + b * L::FROW_BYTES); };
+    uint32_t* s_tick = reinterpret_cast<uint32_t*>(frowbase + 2 * L::FROW_BYTES);  // [4]: tile number held by each ring slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dbg = p.debug;  // measurement knobs (results are wrong when set): 1 skip compute, 2 skip the global writes, 4 skip accumulate
+    const bool overwrite = p.accumulate == 0;
+
+    for (int i = tid; i < 2 * L::ACC; i += TC + TH) smem[i] = 0.0;
+
+    if (warp >= WARPS) {
+        // =========================================================================================== helper warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTileHelperRegs));
+        const int ht = tid - TC;
+        const uint64_t pol_keep = l2_policy_evict_last();
+        // the table pipeline: stage 0 header, stage 1 node ids, stage 2 coordinates + block-row offsets.  A stage reads what the
+        // previous one left in shared memory; consecutive stages of a tile run in consecutive iterations (tables_done() between).
+        auto stage0 = [&](int sl) {
+            const uint32_t tn = s_tick[sl];
+            if (tn < p.num_tiles && ht < 2) cp_async_16(small_hdr(sl) + 4 * ht, p.tile_hdr + (size_t)tn * 8 + 4 * ht);
+        };
+        auto stage1 = [&](int sl) {
+            if (s_tick[sl] < p.num_tiles) {
+                const uint32_t* h = small_hdr(sl);
+                if (ht < (int)h[2]) cp_async_4(small_ids(sl) + ht, p.tile_nodes + h[4] + ht);
+            }
+        };
+        auto stage2 = [&](int sl, int bb) {
+            if (s_tick[sl] < p.num_tiles && ht < (int)small_hdr(sl)[2]) {
+                const int I = small_ids(sl)[ht] & 0x7fffffff;
+                const double* v = p.vertices + (uint64_t)I * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) cp_async_8(big_X(bb) + ht * D + c, v + c);
+                cp_async_8(big_off(bb) + 2 * ht, p.blk_off + I);
+                cp_async_8(big_off(bb) + 2 * ht + 1, p.blk_off + I + 1);
+            }
+        };
+        auto tables_done = [&]() {
+            cp_async_wait_all();
+            named_barrier(BAR_HELPER, TH);
+        };
+        unsigned int tick_next = 0;
+        if (ht == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_tick[k] = atomicAdd(p.ticket32, 1u);
+            tick_next = atomicAdd(p.ticket32, 1u);
+        }
+        named_barrier(BAR_HELPER, TH);
+        stage0(0);
+        stage0(1);
+        stage0(2);
+        tables_done();
+        stage1(0);
+        stage1(1);
+        tables_done();
+        stage2(0, 0);
+        tables_done();
+        __syncthreads();  // (A) prologue done
+
+        uint32_t pf_begin = 0, pf_items = 0;  // previous tile: first list word, S * entries
+        int pf_P = 0;                         // ... accumulator positions in use
+        uint32_t it = 0;
+        bool have_prev = false;
+        while (true) {
+            const int sl = (int)(it & 3u), b = (int)(it & 1u), nb = b ^ 1;
+            const uint32_t tile = s_tick[sl];
+            const bool valid = tile < p.num_tiles;
+            if (!valid && !have_prev) break;
+            const uint32_t* hdr = small_hdr(sl);
+            const int nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
+            const uint32_t flush_begin = valid ? hdr[5] : 0u, nflush = valid ? hdr[6] : 0u;
+            if (valid) {
+                // row table of this tile's flush (used during the NEXT tile): first value of node u's rows, row length | complete << 31
+                if (ht < nn) {
+                    const long long o0 = big_off(b)[2 * ht], o1 = big_off(b)[2 * ht + 1];
+                    long long* fr = buf_frow(b);
+                    fr[2 * ht] = (long long)BS * o0;
+                    fr[2 * ht + 1] = (long long)(((int)(o1 - o0) * S) | ((small_ids(sl)[ht] < 0 && overwrite) ? (int)0x80000000 : 0));
+                }
+                // pull this tile's flush list into L2 (it is read during the next tile)
+                const char* f0 = reinterpret_cast<const char*>(p.tile_flush + flush_begin);
+                const uint32_t bytes = nflush * 4u;
+                for (uint32_t o = (uint32_t)ht * 128u; o < bytes; o += (uint32_t)TH * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(f0 + o));
+            }
+            // ---- one stage for each of the next three tiles
+            stage2((int)((it + 1) & 3u), nb);
+            stage1((int)((it + 2) & 3u));
+            stage0((int)((it + 3) & 3u));
+            // ---- flush of the previous tile: every node block goes to the CSR once.  A warp whose 32 items all belong to complete
+            // rows uses plain stores; a reduction onto the zero-filled row is equally correct, so mixed warps simply reduce.
+            {
+                const uint32_t* fl = p.tile_flush + pf_begin;
+                const double* pacc = smem + nb * L::ACC;
+                const long long* prow = buf_frow(nb);
+                constexpr int FB = 8;
+                const uint32_t wbase_t = (uint32_t)(ht - lane);
+                auto load_words = [&](uint32_t tb, uint32_t (&w)[FB]) {
+#pragma unroll
+                    for (int q = 0; q < FB; ++q) {
+                        const uint32_t t = tb + q * TH + lane;
+                        w[q] = t < pf_items ? fl[S == 1 ? t : t / 3u] : 0u;
+                    }
+                };
+                auto send_words = [&](uint32_t tb, const uint32_t (&w)[FB]) {
+#pragma unroll
+                    for (int q = 0; q < FB; ++q) {
+                        if (tb + q * TH >= pf_items) break;  // warp-uniform
+                        const uint32_t t = tb + q * TH + lane;
+                        const bool ok = t < pf_items;
+                        const uint32_t a = w[q];
+                        const int u = (int)((a >> 12) & 0x7fu);
+                        const int j = S == 1 ? 0 : (int)(t % 3u);
+                        const long long base = prow[2 * u];
+                        const int rlf = (int)prow[2 * u + 1];
+                        const int rl = rlf & 0x7fffffff;
+                        const bool tr = (a >> 11) & 1u;
+                        const double* src = pacc + (int)(a & 0x7ffu) * BS + (tr ? j * S : j);
+                        const int sstride = tr ? 1 : S;
+                        double* dst = p.values + (base + (long long)(S * (int)(a >> 19) + j));
+                        double v[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) v[i] = src[i * sstride];
+                        if (dbg & 2) continue;
+                        if (__all_sync(FULL, rlf < 0 || !ok)) {
+                            if (ok) {
+#pragma unroll
+                                for (int i = 0; i < S; ++i) dst[(long long)i * rl] = v[i];
+                            }
+                        } else if (ok) {
+#pragma unroll
+                            for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
+                        }
+                    }
+                };
+                // two batches in flight: the list words of batch k + 1 are loaded before batch k is sent
+                uint32_t wa[FB], wb[FB];
+                uint32_t tb = wbase_t;
+                if (tb < pf_items) load_words(tb, wa);
+                while (tb < pf_items) {  // warp-uniform
+                    const uint32_t tb1 = tb + FB * TH;
+                    if (tb1 < pf_items) load_words(tb1, wb);
+                    send_words(tb, wa);
+                    if (tb1 >= pf_items) break;
+                    const uint32_t tb2 = tb1 + FB * TH;
+                    if (tb2 < pf_items) load_words(tb2, wa);
+                    send_words(tb1, wb);
+                    tb = tb2;
+                }
+            }
+            tables_done();  // the stages have landed, and every helper has read its accumulators
+            {
+                double* old = smem + nb * L::ACC;
+                for (int i = ht; i < pf_P * BS; i += TH) old[i] = 0.0;
+            }
+            pf_begin = flush_begin;
+            pf_items = nflush * S;
+            pf_P = P;
+            have_prev = valid;
+            __syncthreads();  // (B) the compute warps are done with tile `it`; the helpers with the previous one and the next tables
+            if (ht == 0) {    // ring slot sl is free again: it receives the tile four ahead
+                s_tick[sl] = tick_next;
+                tick_next = atomicAdd(p.ticket32, 1u);
+            }
+            named_barrier(BAR_HELPER, TH);
+            ++it;
+        }
+        return;
+    }
+
+    // =============================================================================================== compute warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTileComputeRegs));
+    const int grp = warp / GW, gwarp = warp - grp * GW;
     double* s_X = wbase + warp * L::WARP_DOUBLES;
     double* s_G = s_X + 24;
     const int nq = p.nq;  // <= 8
-
-    // ---- per-lane constants: lane (gq, gi) owns row gi of the Jacobian at point gq (the 4th lane of a point shadows row 0)
+    // lane (gq, gi) owns row gi of the Jacobian at point gq (the 4th lane of a point shadows row 0)
     const int gq = lane >> 2, s4 = lane & 3;
     const int gi = s4 == 3 ? 0 : s4;
     const bool gact = gq < nq;
@@ -113,162 +290,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) assemble_hex8_tile_kernel(const
     const int xl = lane < N * D ? lane : 0;
     const int x_node = xl / D, x_comp = xl - x_node * D;
     const double mu = p.mu, lam = p.lam;
-    const bool overwrite = p.accumulate == 0;
-    const int dbg = p.debug;  // measurement knobs (results are wrong when set): 1 skip compute, 2 skip the global writes, 4 skip accumulate
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const uint64_t pol_stream = l2_policy_evict_first();
     const uint32_t* emap32 = reinterpret_cast<const uint32_t*>(p.tile_emap);
 
-    // ---- the table pipeline: stage k of the fetch of a tile's tables into buffer nb; consecutive stages must be separated by
-    // cp_async_wait_all() + a CTA barrier (the pass loop provides both).  s_tick[nb] was published a barrier earlier.
-    auto fetch_stage = [&](int stage, int nb) {
-        const uint32_t tn = s_tick[nb];
-        if (tn >= p.num_tiles) return;
-        if (stage == 0) {
-            if (tid < 2) cp_async_16(buf_hdr(nb) + 4 * tid, p.tile_hdr + (size_t)tn * 8 + 4 * tid);
-        } else if (stage == 1) {
-            const uint32_t* h = buf_hdr(nb);
-            if (tid < (int)h[2]) cp_async_4(buf_ids(nb) + tid, p.tile_nodes + h[4] + tid);
-        } else if (stage == 2) {
-            if (tid < (int)buf_hdr(nb)[2]) {
-                const int I = buf_ids(nb)[tid] & 0x7fffffff;
-                const double* v = p.vertices + (uint64_t)I * D;
-#pragma unroll
-                for (int c = 0; c < D; ++c) cp_async_8(buf_X(nb) + tid * D + c, v + c);
-                cp_async_8(buf_off(nb) + 2 * tid, p.blk_off + I);
-                cp_async_8(buf_off(nb) + 2 * tid + 1, p.blk_off + I + 1);
-            }
-        }
-    };
-
-    // ---- one slice of the previous tile's flush: load the list words (pf_load, before the element's arithmetic), then send
-    // the node blocks (pf_send).  A warp whose 32 items all belong to complete rows uses plain stores; a reduction onto the
-    // zero-filled row is equally correct, so mixed warps simply reduce.
-    uint32_t pf_begin = 0, pf_items = 0, pf_q = 0;  // previous tile: first list word, S * entries, items per slice (multiple of T)
-    int pf_P = 0;                                   // ... accumulator positions in use
-    const double* pf_acc = smem;
-    const long long* pf_row = buf_frow(0);
-    auto pf_load = [&](int slice, uint32_t (&w)[FB]) {
-        const uint32_t* fl = p.tile_flush + pf_begin;
-#pragma unroll
-        for (int q = 0; q < FB; ++q) {
-            const uint32_t t = slice * pf_q + q * T + tid;
-            w[q] = ((uint32_t)(q * T) < pf_q && t < pf_items) ? fl[S == 1 ? t : t / 3u] : 0u;
-        }
-    };
-    auto pf_send = [&](int slice, const uint32_t (&w)[FB]) {
-#pragma unroll
-        for (int q = 0; q < FB; ++q) {
-            const uint32_t tw = slice * pf_q + q * T + (uint32_t)(tid - lane);
-            if ((uint32_t)(q * T) >= pf_q || tw >= pf_items) break;  // warp-uniform (__all_sync below)
-            const uint32_t t = tw + lane;
-            const bool ok = t < pf_items;
-            const uint32_t a = w[q];
-            const int u = (int)((a >> 12) & 0x7fu);
-            const int j = S == 1 ? 0 : (int)(t % 3u);
-            const long long base = pf_row[2 * u];
-            const int rlf = (int)pf_row[2 * u + 1];
-            const int rl = rlf & 0x7fffffff;
-            const bool tr = (a >> 11) & 1u;
-            const double* src = pf_acc + (int)(a & 0x7ffu) * BS + (tr ? j * S : j);
-            const int sstride = tr ? 1 : S;
-            double* dst = p.values + (base + (long long)(S * (int)(a >> 19) + j));
-            double v[S];
-#pragma unroll
-            for (int i = 0; i < S; ++i) v[i] = src[i * sstride];
-            if (dbg & 2) continue;
-            if (__all_sync(FULL, rlf < 0 || !ok)) {
-                if (ok) {
-#pragma unroll
-                    for (int i = 0; i < S; ++i) dst[(long long)i * rl] = v[i];
-                }
-            } else if (ok) {
-#pragma unroll
-                for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
-            }
-        }
-    };
-
-    // ---- element data: tile-local node indices (lanes 0-7, one byte each; bit 7 of the first five bytes = the element's
-    // sub-round), accumulator positions of the lane's two blocks
-    auto load_elem = [&](uint32_t p0_, int ne_, int s, uint32_t& ln_, uint32_t& em_) {
+    // element data of a schedule position: tile-local node indices (lanes 0-7, one byte each; byte 0 = 0xff: padding position),
+    // accumulator positions of the lane's two blocks
+    auto load_elem = [&](uint64_t pos, uint32_t& ln_, uint32_t& em_) {
         ln_ = 0;
-        em_ = 0xffffffffu;
-        if (s < ne_) {
-            const uint64_t pos = (uint64_t)p0_ + s;
-            if (lane < N) ln_ = p.tile_lnodes[pos * N + lane];
-            em_ = ld_u32_hint(emap32 + pos * 32 + lane, pol_stream);
-        }
+        if (lane < N) ln_ = p.tile_lnodes[pos * N + lane];
+        em_ = ld_u32_hint(emap32 + pos * 32 + lane, pol_stream);
     };
 
-    for (int i = tid; i < 2 * L::ACC; i += T) smem[i] = 0.0;
-    // ---- prologue: tickets of the first tiles, tables of the first one
-    unsigned int tick_next = 0;
-    if (tid == 0) {
-        s_tick[0] = atomicAdd(p.ticket32, 1u);
-        s_tick[1] = atomicAdd(p.ticket32, 1u);
-        tick_next = atomicAdd(p.ticket32, 1u);
-    }
-    __syncthreads();
-    for (int st = 0; st < NSTAGE; ++st) {
-        fetch_stage(st, 0);
-        cp_async_wait_all();
-        __syncthreads();
-    }
-
-    int b = 0;
+    __syncthreads();  // (A)
+    uint32_t it = 0;
     bool have_prev = false, preloaded = false;
-    uint32_t ln = 0, em = 0xffffffffu;
+    uint32_t ln = 0xffu, em = 0xffffffffu;
     while (true) {
-        const uint32_t tile = s_tick[b];
+        const int sl = (int)(it & 3u), b = (int)(it & 1u);
+        const uint32_t tile = s_tick[sl];
         const bool valid = tile < p.num_tiles;
         if (!valid && !have_prev) break;
-        const int nb = b ^ 1;
-        const uint32_t* hdr = buf_hdr(b);
+        const uint32_t* hdr = small_hdr(sl);
         const uint32_t p0 = valid ? hdr[0] : 0u;
-        const int ne = valid ? (int)hdr[1] : 0, nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
-        const uint32_t flush_begin = valid ? hdr[5] : 0u, nflush = valid ? hdr[6] : 0u, rounds = valid ? hdr[7] : 0u;
-        const double* tX = buf_X(b);
+        const int R = valid ? (int)hdr[1] : 0;
+        const double* tX = big_X(b);
         double* acc = smem + b * L::ACC;
-
-        if (valid) {
-            // row table of this tile's flush (used during the NEXT tile): first value of node u's rows, row length | complete << 31
-            if (tid < nn) {
-                const long long o0 = buf_off(b)[2 * tid], o1 = buf_off(b)[2 * tid + 1];
-                long long* fr = buf_frow(b);
-                fr[2 * tid] = (long long)BS * o0;
-                fr[2 * tid + 1] = (long long)(((int)(o1 - o0) * S) | ((buf_ids(b)[tid] < 0 && overwrite) ? (int)0x80000000 : 0));
-            }
-            // pull this tile's flush list into L2 (it is read during the next tile)
-            const char* f0 = reinterpret_cast<const char*>(p.tile_flush + flush_begin);
-            const uint32_t bytes = nflush * 4u;
-            for (uint32_t o = (uint32_t)tid * 128u; o < bytes; o += (uint32_t)T * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(f0 + o));
-            if (!preloaded) load_elem(p0, ne, warp, ln, em);
-        }
+        if (!preloaded && grp < R) load_elem((uint64_t)p0 + grp * GW + gwarp, ln, em);
         preloaded = false;
 
-        const int npass = (ne + WARPS - 1) / WARPS;
-        for (int pass = 0; pass < npass; ++pass) {
-            const int s = pass * WARPS + warp;
-            const bool active = s < ne;
+        for (int r = grp; r < R; r += 2) {
             const uint32_t em_c = em;
+            const bool active = (__shfl_sync(FULL, ln, 0) & 0xffu) != 0xffu;
             const int u_x = (int)(__shfl_sync(FULL, ln, x_node) & 0x7fu);
-            const int sb_c = (int)(__ballot_sync(FULL, (ln >> 7) & 1u) & 0x1fu);
-            if (pass + 1 < npass) {
-                load_elem(p0, ne, s + WARPS, ln, em);
-            } else if (pass >= 1 && s_tick[nb] < p.num_tiles) {  // the next tile's header landed a pass ago: its first elements
-                const uint32_t* hn = buf_hdr(nb);
-                load_elem(hn[0], (int)hn[1], warp, ln, em);
-                preloaded = true;
+            if (r + 2 < R) {
+                load_elem((uint64_t)p0 + (r + 2) * GW + gwarp, ln, em);
+            } else {
+                const int sn = (int)((it + 1) & 3u);
+                if (s_tick[sn] < p.num_tiles) {  // the next tile's header landed long ago: this group's first round of it
+                    const uint32_t* hn = small_hdr(sn);
+                    if (grp < (int)hn[1]) load_elem((uint64_t)hn[0] + grp * GW + gwarp, ln, em);
+                    preloaded = true;
+                }
             }
-            if (pass < NSTAGE) fetch_stage(pass, nb);  // next tile's tables
-            uint32_t fw[FB];
-            if (pass < NSLICE) pf_load(pass, fw);
-
             double K0[S][S], K1[S][S];
-#pragma unroll
-            for (int i = 0; i < S; ++i)
-#pragma unroll
-                for (int j = 0; j < S; ++j) K0[i][j] = K1[i][j] = 0.0;
             if (active && !(dbg & 1)) {
                 if (lane < N * D) s_X[lane] = tX[u_x * D + x_comp];
                 __syncwarp();
@@ -293,14 +357,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) assemble_hex8_tile_kernel(const
                 c[2] = r1[0] * r2[1] - r1[1] * r2[0];
                 double det = Jr[0] * c[0] + Jr[1] * c[1] + Jr[2] * c[2];
                 det = __shfl_sync(FULL, det, lane & ~3);
-                double r = 0.0;
+                double rs = 0.0;
                 if (det != 0.0) {
-                    r = copysign(sqw * rsqrt(fabs(det)), det);
+                    rs = copysign(sqw * rsqrt(fabs(det)), det);
                 } else if (gact && s4 == 0) {
-                    flag_error(p.errword, (uint64_t)p.tile_elem[(uint64_t)p0 + s], FB200_ERR_SINGULAR_JACOBIAN);
+                    flag_error(p.errword, (uint64_t)p.tile_elem[(uint64_t)p0 + r * GW + gwarp], FB200_ERR_SINGULAR_JACOBIAN);
                 }
 #pragma unroll
-                for (int j = 0; j < D; ++j) c[j] *= r;
+                for (int j = 0; j < D; ++j) c[j] *= rs;
                 if (s4 < 3) {
                     // g_a[gi] = c . grad_ref phi_a,  grad_ref phi_a = (sx P0[sy, sz], sy P1[sx, sz], sz P2[sx, sy])
                     double* go = s_G + 3 * gq + gi;
@@ -349,49 +413,27 @@ __global__ void __launch_bounds__(WARPS * 32, 1) assemble_hex8_tile_kernel(const
                             K1[i][j] = mu * ((i == j ? tr1 : 0.0) + M1[j][i]) + lam * M1[i][j];
                         }
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i)
+#pragma unroll
+                    for (int j = 0; j < S; ++j) K0[i][j] = K1[i][j] = 0.0;
             }
-            if (pass < NSLICE) pf_send(pass, fw);
-            cp_async_wait_all();  // this pass's stage of the table pipeline has landed (issued before the element's arithmetic)
-            // ---- add the blocks with u_a <= u_b to the tile accumulators, one sub-round per colour present in the pass
-            const int nround = (int)((rounds >> (8 * pass)) & 0xffu);
-            const uint32_t e0 = em_c & 0xffffu, e1 = em_c >> 16;
-            for (int rr = 0; rr < nround; ++rr) {
-                if (active && sb_c == rr && !(dbg & 4)) {
-                    if (e0 != 0xffffu) tile_accumulate<S>(acc + e0 * BS, K0);
-                    if (e1 != 0xffffu) tile_accumulate<S>(acc + e1 * BS, K1);
-                }
-                __syncthreads();
+            // ---- add the blocks with u_a <= u_b to the tile accumulators, strictly in round order: wait for the other group's
+            // round r - 1, add, release its round r + 1
+            if (r > 0) named_barrier(1 + grp, TC);
+            if (active && !(dbg & 4)) {
+                const uint32_t e0 = em_c & 0xffffu, e1 = em_c >> 16;
+                if (e0 != 0xffffu) tile_accumulate<S>(acc + e0 * BS, K0);
+                if (e1 != 0xffffu) tile_accumulate<S>(acc + e1 * BS, K1);
+            }
+            if (r + 1 < R) {
+                __threadfence_block();
+                named_barrier_arrive(1 + (grp ^ 1), TC);
             }
         }
-        // short tiles (and the drain iteration): finish the table stages and the flush slices here
-        for (int st = npass; st < NSTAGE; ++st) {
-            fetch_stage(st, nb);
-            cp_async_wait_all();
-            __syncthreads();
-        }
-        for (int sl = npass; sl < NSLICE; ++sl) {
-            uint32_t fw[FB];
-            pf_load(sl, fw);
-            pf_send(sl, fw);
-        }
-        // ---- hand over: this tile becomes the one being flushed; its table buffer b receives the tile after next
-        __syncthreads();  // every slice of the previous flush has read its accumulators
-        {
-            double* old = smem + nb * L::ACC;
-            for (int i = tid; i < pf_P * BS; i += T) old[i] = 0.0;
-        }
-        pf_begin = flush_begin;
-        pf_items = nflush * S;
-        pf_q = ((pf_items + NSLICE * T - 1) / (NSLICE * T)) * T;
-        pf_acc = acc;
-        pf_row = buf_frow(b);
-        pf_P = P;
         have_prev = valid;
-        if (tid == 0) {
-            s_tick[b] = tick_next;
-            tick_next = atomicAdd(p.ticket32, 1u);
-        }
-        __syncthreads();
-        b = nb;
+        __syncthreads();  // (B)
+        ++it;
     }
 }

@@ -23,9 +23,9 @@
 //              k = position of v in the block row of u (from the node-block map; meshes with block rows >= 8192 keep the
 //              per-element kernel)
 //   schedule   the tile's elements ordered by a greedy node-disjoint colouring (fenris-paradis' idea, coloring.rs:6-70, applied
-//              inside the tile): a pass = `warps` consecutive schedule positions computed concurrently; elements of a pass add
-//              their blocks in sub-rounds (one per colour present in the pass) separated by CTA barriers, so no two warps ever
-//              update the same accumulator concurrently
+//              inside the tile) and cut into ROUNDS of at most `warps` elements of one colour (padded to `warps` schedule
+//              positions).  The kernel's two groups of compute warps take the rounds alternately and add their blocks strictly
+//              in round order (named-barrier hand-over), so no two warps ever update the same accumulator concurrently
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -42,6 +42,9 @@ struct TileOut {
     uint32_t P = 0, rounds = 0;
     std::vector<int32_t> nodes;
     std::vector<uint32_t> flush;
+    std::vector<uint8_t> lnodes;   // rounds * warps * 8
+    std::vector<uint16_t> emap;    // rounds * warps * 64
+    std::vector<int32_t> elem;     // rounds * warps
 };
 
 struct Builder {
@@ -205,7 +208,8 @@ struct Builder {
                 if (x.k >= (1u << kTileKBits)) degenerate = true;
                 t.flush.push_back(pos | (tr << 11) | ((uint32_t)u << 12) | ((uint32_t)x.k << 19));
             }
-        // ---- schedule: greedy node-disjoint colouring inside the tile, elements ordered by colour
+        // ---- schedule: greedy node-disjoint colouring inside the tile; every colour class is cut into rounds of at most
+        // `warps` elements; rounds are padded to `warps` schedule positions (padding: node byte 0 = 0xff, no accumulators)
         std::vector<uint64_t> node_mask(nn, 0);
         std::vector<int> colour(ne), sched(ne);
         for (int el = 0; el < ne; ++el) {
@@ -218,26 +222,28 @@ struct Builder {
         }
         for (int el = 0; el < ne; ++el) sched[el] = el;
         std::stable_sort(sched.begin(), sched.end(), [&](int x, int y) { return colour[x] < colour[y]; });
+        const int gw = shape.warps;
+        t.lnodes.clear();
+        t.emap.clear();
+        t.elem.clear();
         t.rounds = 0;
-        for (int s0 = 0, pass = 0; s0 < ne; s0 += shape.warps, ++pass) {
-            const int s1 = std::min(ne, s0 + shape.warps);
-            int r = -1, last = -1;
-            for (int s = s0; s < s1; ++s) {
-                if (colour[sched[s]] != last) {
-                    ++r;
-                    last = colour[sched[s]];
-                }
-                out.sub[p0 + s] = (uint8_t)r;
+        auto pad_round = [&]() {
+            while (t.elem.size() % gw) {
+                t.elem.push_back(-1);
+                t.lnodes.insert(t.lnodes.end(), n, (uint8_t)0);
+                t.lnodes[t.lnodes.size() - n] = 0xff;
+                t.emap.insert(t.emap.end(), n2, (uint16_t)0xffffu);
             }
-            t.rounds |= (uint32_t)(r + 1) << (8 * pass);  // <= 4 passes per tile (max_elems = 4 * warps), <= warps rounds each
-        }
+        };
         for (int s = 0; s < ne; ++s) {
             const int el = sched[s];
+            if (s > 0 && colour[el] != colour[sched[s - 1]]) pad_round();
             const uint64_t e = elem_at(p0 + el);
-            out.elem[p0 + s] = (int32_t)e;
-            for (int a = 0; a < n; ++a)  // bit 7 of the first five bytes carries the element's sub-round
-                out.lnodes[(p0 + s) * n + a] = (uint8_t)(ln[el * n + a] | (a < 5 ? ((out.sub[p0 + s] >> a) & 1) << 7 : 0));
-            uint16_t* em = &out.emap[(p0 + s) * (uint64_t)n2];
+            t.elem.push_back((int32_t)e);
+            for (int a = 0; a < n; ++a) t.lnodes.push_back(ln[el * n + a]);
+            const size_t eb = t.emap.size();
+            t.emap.resize(eb + n2);
+            uint16_t* em = &t.emap[eb];
             for (int a = 0; a < n; ++a)
                 for (int b = 0; b < n; ++b) {
                     const int u = ln[el * n + a], v = ln[el * n + b];
@@ -256,6 +262,8 @@ struct Builder {
                         }
                 }
         }
+        pad_round();
+        t.rounds = (uint32_t)(t.elem.size() / gw);
         return true;
     }
 };
@@ -273,10 +281,9 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
     out.hdr.clear();
     out.nodes.clear();
     out.flush.clear();
-    out.lnodes.assign(count * n, 0);
-    out.emap.assign(count * 64, 0);
-    out.sub.assign(count, 0);
-    out.elem.assign(count, 0);
+    out.lnodes.clear();
+    out.emap.clear();
+    out.elem.clear();
     out.bank_conflict_share = 0;
     // candidate tiles: runs with a common Morton prefix
     std::vector<std::pair<uint64_t, int>> cand;
@@ -333,11 +340,14 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
     }
     for (auto& rs : results)
         for (TileOut& t : rs) {
-            const uint32_t hdr[kTileHdrWords] = {(uint32_t)t.p0,          (uint32_t)t.ne,           (uint32_t)t.nodes.size(),   t.P,
-                                                 (uint32_t)out.nodes.size(), (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), t.rounds};
+            const uint32_t hdr[kTileHdrWords] = {(uint32_t)out.elem.size(), t.rounds,                    (uint32_t)t.nodes.size(),   t.P,
+                                                 (uint32_t)out.nodes.size(), (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), (uint32_t)t.ne};
             out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
             out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
             out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
+            out.lnodes.insert(out.lnodes.end(), t.lnodes.begin(), t.lnodes.end());
+            out.emap.insert(out.emap.end(), t.emap.begin(), t.emap.end());
+            out.elem.insert(out.elem.end(), t.elem.begin(), t.elem.end());
         }
     out.bank_conflict_share = accesses.load() ? (double)conflicts.load() / (double)accesses.load() : 0.0;
 }
