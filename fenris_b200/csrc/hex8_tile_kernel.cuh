@@ -66,11 +66,11 @@ struct Hex8TileSmem {
     static constexpr int GS = 28;                       // node stride of the transposed gradient array (hex8_mma_kernel.cuh)
     static constexpr int WARP_DOUBLES = 24 + 8 * GS;
     static constexpr int ACC = (MAXP * BS + 1) & ~1;    // one accumulator buffer
-    static constexpr int BIG_BYTES = MAXN * 3 * 8 + MAXN * 2 * 8;  // X[MAXN][3] doubles, off[MAXN][2] int64 (current / next tile)
-    static constexpr int SMALL_BYTES = 32 + MAXN * 4;              // header 8 x uint32, ids[MAXN] int32 (ring of 4 tiles)
+    static constexpr int BIG_BYTES = MAXN * 3 * 8 + MAXN * 2 * 8;  // X[MAXN][3] doubles, off[MAXN][2] int64 (ring of 3 tiles)
+    static constexpr int SMALL_BYTES = 32 + MAXN * 4;              // header 8 x uint32, ids[MAXN] int32 (ring of 8 tiles)
     static constexpr int FROW_BYTES = MAXN * 2 * 8;                // flush row table of one tile
     static constexpr size_t bytes =
-        sizeof(double) * (size_t)(2 * ACC + WARPS * WARP_DOUBLES) + 2 * (size_t)BIG_BYTES + 4 * (size_t)SMALL_BYTES + 2 * (size_t)FROW_BYTES + 16;
+        sizeof(double) * (size_t)(2 * ACC + WARPS * WARP_DOUBLES) + 3 * (size_t)BIG_BYTES + 8 * (size_t)SMALL_BYTES + 2 * (size_t)FROW_BYTES + 32;
 };
 
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -82,7 +82,9 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     constexpr int N = 8, D = 3, S = L::S, BS = L::BS, GS = L::GS, WARPS = L::WARPS, GW = kTileGroupWarps;
     constexpr int TC = WARPS * 32;              // compute threads
     constexpr int TH = kTileHelperWarps * 32;   // helper threads
-    constexpr int BAR_HELPER = 3;               // named barriers: 1, 2 = round hand-over of the compute groups, 3 = helpers, 0 = everybody
+    // named barriers: 0 everybody (prologue), 1 / 2 round hand-over of the compute groups, 3 helpers,
+    // 4 / 5 "tile done" (compute arrives, helpers wait; by tile parity), 6 / 7 "accumulators ready" (helpers arrive, compute waits)
+    constexpr int BAR_HELPER = 3, BAR_DONE = 4, BAR_READY = 6;
     constexpr unsigned FULL = 0xffffffffu;
     static_assert(MAXN <= TH && MAXN <= 128 && GW % 4 == 0 && kTileHelperWarps % 4 == 0, "one helper thread per tile node, 7-bit node index, whole warpgroups");
     extern __shared__ __align__(16) double smem[];
@@ -90,12 +92,12 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     unsigned char* bufbase = reinterpret_cast<unsigned char*>(wbase + WARPS * L::WARP_DOUBLES);
     auto big_X = [&](int b) { return reinterpret_cast<double*>(bufbase + b * L::BIG_BYTES); };
     auto big_off = [&](int b) { return reinterpret_cast<long long*>(bufbase + b * L::BIG_BYTES + MAXN * 24); };
-    unsigned char* smallbase = bufbase + 2 * L::BIG_BYTES;
+    unsigned char* smallbase = bufbase + 3 * L::BIG_BYTES;
     auto small_hdr = [&](int sl) { return reinterpret_cast<uint32_t*>(smallbase + sl * L::SMALL_BYTES); };
     auto small_ids = [&](int sl) { return reinterpret_cast<int*>(smallbase + sl * L::SMALL_BYTES + 32); };
-    unsigned char* frowbase = smallbase + 4 * L::SMALL_BYTES;
+    unsigned char* frowbase = smallbase + 8 * L::SMALL_BYTES;
     auto buf_frow = [&](int b) { return reinterpret_cast<long long*>(frowbase + b * L::FROW_BYTES); };
-    uint32_t* s_tick = reinterpret_cast<uint32_t*>(frowbase + 2 * L::FROW_BYTES);  // [4]: tile number held by each ring slot
+    uint32_t* s_tick = reinterpret_cast<uint32_t*>(frowbase + 2 * L::FROW_BYTES);  // [8]: tile number held by each ring slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dbg = p.debug;  // measurement knobs (results are wrong when set): 1 skip compute, 2 skip the global writes, 4 skip accumulate
     const bool overwrite = p.accumulate == 0;
@@ -136,50 +138,59 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         unsigned int tick_next = 0;
         if (ht == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s_tick[k] = atomicAdd(p.ticket32, 1u);
+            for (int k = 0; k < 5; ++k) s_tick[k] = atomicAdd(p.ticket32, 1u);
             tick_next = atomicAdd(p.ticket32, 1u);
         }
         named_barrier(BAR_HELPER, TH);
-        stage0(0);
-        stage0(1);
-        stage0(2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stage0(k);
         tables_done();
-        stage1(0);
-        stage1(1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) stage1(k);
         tables_done();
         stage2(0, 0);
+        stage2(1, 1);
         tables_done();
-        __syncthreads();  // (A) prologue done
+        __syncthreads();  // (A) prologue done: tables of tiles 0 and 1 are there, both accumulator buffers are clear
+        if (s_tick[0] < p.num_tiles) named_barrier_arrive(BAR_READY + 0, TC + TH);
 
         uint32_t pf_begin = 0, pf_items = 0;  // previous tile: first list word, S * entries
         int pf_P = 0;                         // ... accumulator positions in use
-        uint32_t it = 0;
-        bool have_prev = false;
-        while (true) {
-            const int sl = (int)(it & 3u), b = (int)(it & 1u), nb = b ^ 1;
-            const uint32_t tile = s_tick[sl];
-            const bool valid = tile < p.num_tiles;
-            if (!valid && !have_prev) break;
+        // iteration `it`: tables of tiles it + 2 .. it + 4, flush of tile it - 1 (after the compute warps have finished it)
+        for (uint32_t it = 0;; ++it) {
+            const int sl = (int)(it & 7u), b = (int)(it & 1u), nb = b ^ 1;
+            if (it > 0) {
+                if (s_tick[(it - 1) & 7u] >= p.num_tiles) break;
+                named_barrier(BAR_DONE + nb, TC + TH);  // tile it - 1 is complete in accumulator buffer nb
+            } else if (s_tick[0] >= p.num_tiles) {
+                break;
+            }
+            const bool valid = s_tick[sl] < p.num_tiles;
             const uint32_t* hdr = small_hdr(sl);
             const int nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
             const uint32_t flush_begin = valid ? hdr[5] : 0u, nflush = valid ? hdr[6] : 0u;
             if (valid) {
-                // row table of this tile's flush (used during the NEXT tile): first value of node u's rows, row length | complete << 31
+                // row table of this tile's flush (used in the next iteration): first value of node u's rows, row length | complete << 31
                 if (ht < nn) {
-                    const long long o0 = big_off(b)[2 * ht], o1 = big_off(b)[2 * ht + 1];
+                    const long long* off = big_off((int)(it % 3u));
+                    const long long o0 = off[2 * ht], o1 = off[2 * ht + 1];
                     long long* fr = buf_frow(b);
                     fr[2 * ht] = (long long)BS * o0;
                     fr[2 * ht + 1] = (long long)(((int)(o1 - o0) * S) | ((small_ids(sl)[ht] < 0 && overwrite) ? (int)0x80000000 : 0));
                 }
-                // pull this tile's flush list into L2 (it is read during the next tile)
+                // pull this tile's flush list into L2 (it is read in the next iteration)
                 const char* f0 = reinterpret_cast<const char*>(p.tile_flush + flush_begin);
                 const uint32_t bytes = nflush * 4u;
                 for (uint32_t o = (uint32_t)ht * 128u; o < bytes; o += (uint32_t)TH * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(f0 + o));
             }
-            // ---- one stage for each of the next three tiles
-            stage2((int)((it + 1) & 3u), nb);
-            stage1((int)((it + 2) & 3u));
-            stage0((int)((it + 3) & 3u));
+            // ---- one stage for each of three coming tiles; the ring slot of tile it - 3 receives the ticket of tile it + 5
+            stage2((int)((it + 2) & 7u), (int)((it + 2) % 3u));
+            stage1((int)((it + 3) & 7u));
+            stage0((int)((it + 4) & 7u));
+            if (ht == 0) {
+                s_tick[(it + 5) & 7u] = tick_next;
+                tick_next = atomicAdd(p.ticket32, 1u);
+            }
             // ---- flush of the previous tile: every node block goes to the CSR once.  A warp whose 32 items all belong to complete
             // rows uses plain stores; a reduction onto the zero-filled row is equally correct, so mixed warps simply reduce.
             {
@@ -249,14 +260,11 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             pf_begin = flush_begin;
             pf_items = nflush * S;
             pf_P = P;
-            have_prev = valid;
-            __syncthreads();  // (B) the compute warps are done with tile `it`; the helpers with the previous one and the next tables
-            if (ht == 0) {    // ring slot sl is free again: it receives the tile four ahead
-                s_tick[sl] = tick_next;
-                tick_next = atomicAdd(p.ticket32, 1u);
+            // accumulator buffer nb is clear (again) and the tables of tile it + 2 are there: release tile it + 1
+            if (s_tick[(it + 1) & 7u] < p.num_tiles) {
+                __threadfence_block();
+                named_barrier_arrive(BAR_READY + nb, TC + TH);
             }
-            named_barrier(BAR_HELPER, TH);
-            ++it;
         }
         return;
     }
@@ -302,21 +310,19 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     };
 
     __syncthreads();  // (A)
-    uint32_t it = 0;
-    bool have_prev = false, preloaded = false;
+    bool preloaded = false;
     uint32_t ln = 0xffu, em = 0xffffffffu;
-    while (true) {
-        const int sl = (int)(it & 3u), b = (int)(it & 1u);
-        const uint32_t tile = s_tick[sl];
-        const bool valid = tile < p.num_tiles;
-        if (!valid && !have_prev) break;
+    for (uint32_t it = 0;; ++it) {
+        const int sl = (int)(it & 7u), b = (int)(it & 1u);
+        if (s_tick[sl] >= p.num_tiles) break;
         const uint32_t* hdr = small_hdr(sl);
-        const uint32_t p0 = valid ? hdr[0] : 0u;
-        const int R = valid ? (int)hdr[1] : 0;
-        const double* tX = big_X(b);
+        const uint32_t p0 = hdr[0];
+        const int R = (int)hdr[1];
+        const double* tX = big_X((int)(it % 3u));
         double* acc = smem + b * L::ACC;
         if (!preloaded && grp < R) load_elem((uint64_t)p0 + grp * GW + gwarp, ln, em);
         preloaded = false;
+        bool ready = false;  // has this warp waited for the helpers to release accumulator buffer b?
 
         for (int r = grp; r < R; r += 2) {
             const uint32_t em_c = em;
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             if (r + 2 < R) {
                 load_elem((uint64_t)p0 + (r + 2) * GW + gwarp, ln, em);
             } else {
-                const int sn = (int)((it + 1) & 3u);
+                const int sn = (int)((it + 1) & 7u);
                 if (s_tick[sn] < p.num_tiles) {  // the next tile's header landed long ago: this group's first round of it
                     const uint32_t* hn = small_hdr(sn);
                     if (grp < (int)hn[1]) load_elem((uint64_t)hn[0] + grp * GW + gwarp, ln, em);
@@ -421,6 +427,10 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             }
             // ---- add the blocks with u_a <= u_b to the tile accumulators, strictly in round order: wait for the other group's
             // round r - 1, add, release its round r + 1
+            if (!ready) {
+                named_barrier(BAR_READY + b, TC + TH);
+                ready = true;
+            }
             if (r > 0) named_barrier(1 + grp, TC);
             if (active && !(dbg & 4)) {
                 const uint32_t e0 = em_c & 0xffffu, e1 = em_c >> 16;
@@ -432,8 +442,8 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                 named_barrier_arrive(1 + (grp ^ 1), TC);
             }
         }
-        have_prev = valid;
-        __syncthreads();  // (B)
-        ++it;
+        if (!ready) named_barrier(BAR_READY + b, TC + TH);  // (a group without a round in this tile)
+        __threadfence_block();
+        named_barrier_arrive(BAR_DONE + b, TC + TH);  // this warp has added everything it has for tile `it`
     }
 }
