@@ -288,8 +288,10 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"atomic": "assemble_elements_kernel<ATOMIC>", "colored": "assemble_elements_kernel<COLORED> x colours",
-                           "gather": "assemble_gather_kernel"}[args.scatter].replace("assemble_elements_kernel<ATOMIC>", "assemble_hex8_kernel<LINEAR_ELASTIC, ATOMIC>"),
+                "kernel": {"atomic": "assemble_hex8_tile_kernel<LINEAR_ELASTIC> (accumulate launch: every CSR value read-modify-written)"
+                           if os.environ.get("FB200_HEX8_TILE", "64") != "0" else "assemble_hex8_mma_kernel<LINEAR_ELASTIC, ATOMIC>",
+                           "colored": "assemble_hex8_mma_kernel<LINEAR_ELASTIC, COLORED> x colours",
+                           "gather": "assemble_gather_kernel"}[args.scatter],
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": b_algo, "bytes_per_element": b_algo / max(E_loc, 1), "peak_source": peak_src}
 
     other = None
