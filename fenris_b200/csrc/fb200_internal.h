@@ -77,7 +77,7 @@ struct HostTiles {
     double bank_conflict_share = 0;   // diagnostic: share of accumulate accesses that collide in a shared-memory bank
 };
 void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
-                      uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out);
+                      uint64_t num_elements, uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out);
 
 struct TileLists {
     bool valid = false;

@@ -271,13 +271,14 @@ struct Builder {
 }  // namespace
 
 void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
-                      uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out) {
+                      uint64_t num_elements, uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out) {
     constexpr int n = 8;
+    // incidences of every node over ALL elements of the space - also the ghost elements of a partition, which are in the pattern
+    // but are not assembled here: a node is complete only if every element it belongs to is processed inside one tile (then
+    // the flush writes every entry of its rows)
     std::vector<int32_t> degree(num_nodes, 0);
-    for (uint64_t pos = 0; pos < count; ++pos) {
-        const uint64_t e = order ? (uint64_t)order[pos] : pos;
+    for (uint64_t e = 0; e < num_elements; ++e)
         for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
-    }
     out.hdr.clear();
     out.nodes.clear();
     out.flush.clear();

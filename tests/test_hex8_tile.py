@@ -151,6 +151,21 @@ def test_tile_40_cubed_vs_c_oracle_and_modes(ctx, tile):
     assert fo.rel_frobenius(vals, ctx.values_download()) < 1e-14
 
 
+@pytest.mark.parametrize("tile", TILES)
+@pytest.mark.parametrize("n", [5, 12])
+def test_tile_overwrite_ignores_previous_values(ctx, tile, n):
+    # assemble() starts from zeros (global.rs:126): whatever the value array held before must not leak into the result - the
+    # tile path clears only the rows that receive reductions and overwrites the rows of tile-complete nodes with plain stores
+    m = _hex(n, 0.1)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(3)
+    prob = fo.Problem(fo.HEX8, m.vertices(), m.connectivity().astype(np.int64), fo.LINEAR_ELASTIC, params=(MU, LAM))
+    _, _, ovals = fo.assemble_fast(prob)
+    ctx.values_upload(np.full(ctx.nnz, 1e300))
+    _assemble(ctx, m, fo.LINEAR_ELASTIC, tile)
+    assert fo.rel_frobenius(ctx.values_download(), ovals) < TOL
+
+
 def test_tile_repeatable(ctx):
     # within a tile the sums are formed in a fixed order; only the reductions into rows shared between tiles commute
     m = _hex(12, 0.1)
