@@ -43,10 +43,10 @@ void free_pattern(fb200_ctx* ctx) {
 
 // Locality-preserving visiting order: elements sorted by the Morton code of their centroid (host preprocessing, like
 // the colouring).  The assembled sums do not depend on the order; it only decides which CSR rows are live in L2 together and
-// which elements share a cell of the cell-accumulating Hex8 kernel.  Centroids are quantised with the mean element size
+// which elements share a tile of the tile-accumulating Hex8 kernel.  Centroids are quantised with the mean element size
 // h = (volume of the bounding box / E)^(1/d), so that on a structured mesh one quantisation cell is exactly one element and
-// aligned 2 x 2 x 2 element blocks are consecutive in the order (the code drops its lowest d bits to name such a block).
-static void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order,
+// aligned 4 x 4 x 4 element blocks are consecutive in the order (the code drops its lowest 2 d bits to name such a block).
+void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order,
                          std::vector<uint64_t>& codes) {
     order.resize(E);
     codes.resize(E);

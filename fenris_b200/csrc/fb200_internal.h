@@ -235,6 +235,10 @@ void free_pattern(fb200_ctx* ctx);
 void free_space(fb200_ctx* ctx);
 fb200_status exclusive_scan_i64(fb200_ctx* ctx, int64_t* d_data, uint64_t count);  // in place, count elements
 
+// context.cu: locality-preserving (Morton) processing order of the elements and the codes it was sorted by
+void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order,
+                  std::vector<uint64_t>& codes);
+
 // assemble.cu
 void free_ordered(fb200_ctx* ctx);
 fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q);

@@ -354,3 +354,157 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
 }
 
 }  // namespace fb200
+
+// ---------------------------------------------------------------------------------------------------------------- host self check
+extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
+                                                  uint64_t num_owned, uint64_t stats[8], int32_t* failed_check) {
+    using namespace fb200;
+    constexpr int n = 8, n2 = 64;
+    if (failed_check) *failed_check = 0;
+    if (!vertices || !connectivity || !stats || num_owned > num_elements) return FB200_ERR_SHAPE;
+    for (uint64_t i = 0; i < num_elements * n; ++i)
+        if (connectivity[i] >= num_nodes) return FB200_ERR_INDEX_OOB;
+    auto fail_check = [&](int id) {
+        if (failed_check) *failed_check = id;
+        return FB200_ERR_STATE;
+    };
+    // node-block rows (sorted coupled nodes, global.rs:65-120) and the block map: position of node b in the block row of node a
+    std::vector<std::vector<int32_t>> rows(num_nodes);
+    std::vector<int32_t> conn(num_elements * n);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) {
+            conn[e * n + a] = (int32_t)connectivity[e * n + a];
+            for (int b = 0; b < n; ++b) rows[connectivity[e * n + a]].push_back((int32_t)connectivity[e * n + b]);
+        }
+    for (auto& r : rows) {
+        std::sort(r.begin(), r.end());
+        r.erase(std::unique(r.begin(), r.end()), r.end());
+        if (r.size() >= 65536) return FB200_ERR_UNSUPPORTED;
+    }
+    std::vector<uint16_t> map(num_elements * (uint64_t)n2);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) {
+            const auto& r = rows[conn[e * n + a]];
+            for (int b = 0; b < n; ++b) map[e * n2 + a * n + b] = (uint16_t)(std::lower_bound(r.begin(), r.end(), conn[e * n + b]) - r.begin());
+        }
+    // processing order of the owned elements, as fb200_space_upload / fb200_set_num_owned_elements build it
+    std::vector<int32_t> order_all, order;
+    std::vector<uint64_t> codes_all, codes;
+    morton_order(3, n, num_nodes, vertices, num_elements, connectivity, order_all, codes_all);
+    for (size_t i = 0; i < order_all.size(); ++i)
+        if ((uint64_t)order_all[i] < num_owned) {
+            order.push_back(order_all[i]);
+            codes.push_back(codes_all[i]);
+        }
+    const TileShape shape{6, 64, 8, 128, 1216};
+    HostTiles ht;
+    build_tile_lists(shape, order.size(), order.data(), codes.data(), conn.data(), num_elements, num_nodes, map.data(), ht);
+    if (ht.bank_conflict_share < 0.0) return FB200_ERR_UNSUPPORTED;
+    // ---- checks
+    std::vector<int32_t> degree(num_nodes, 0);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
+    std::vector<uint8_t> seen(num_elements, 0);
+    const size_t ntiles = ht.hdr.size() / kTileHdrWords;
+    uint64_t max_nodes = 0, max_P = 0, complete = 0, max_rounds = 0, scheduled = 0;
+    for (size_t t = 0; t < ntiles; ++t) {
+        const uint32_t* h = &ht.hdr[t * kTileHdrWords];
+        const uint32_t p0 = h[0], R = h[1], nn = h[2], P = h[3], nb = h[4], fb = h[5], nf = h[6], ne = h[7];
+        max_nodes = std::max<uint64_t>(max_nodes, nn);
+        max_P = std::max<uint64_t>(max_P, P);
+        max_rounds = std::max<uint64_t>(max_rounds, R);
+        if (nn > (uint32_t)shape.max_nodes || P > (uint32_t)shape.max_slots || (P & 15u) || ne > (uint32_t)shape.max_elems || R > 255) return fail_check(1);
+        if ((uint64_t)p0 + (uint64_t)R * shape.warps > ht.elem.size() || (uint64_t)nb + nn > ht.nodes.size() || (uint64_t)fb + nf > ht.flush.size())
+            return fail_check(2);
+        // nodes ascending, complete flags
+        std::vector<int> inc(nn, 0);
+        for (uint32_t u = 0; u < nn; ++u)
+            if (u && (ht.nodes[nb + u] & 0x7fffffff) <= (ht.nodes[nb + u - 1] & 0x7fffffff)) return fail_check(3);
+        // schedule: every position is an element of the tile or padding; rounds are node-disjoint
+        std::vector<std::pair<uint32_t, uint32_t>> pairs;  // (u << 8 | v) -> accumulator position, from the element maps
+        std::vector<uint32_t> pair_pos;
+        uint32_t real = 0;
+        for (uint32_t r = 0; r < R; ++r) {
+            std::vector<uint8_t> used(nn, 0);
+            for (int w = 0; w < shape.warps; ++w) {
+                const uint64_t pos = (uint64_t)p0 + r * shape.warps + w;
+                const int32_t e = ht.elem[pos];
+                const uint8_t* ln = &ht.lnodes[pos * n];
+                const uint16_t* em = &ht.emap[pos * n2];
+                if (e < 0) {
+                    if (ln[0] != 0xff) return fail_check(4);
+                    for (int k = 0; k < n2; ++k)
+                        if (em[k] != 0xffffu) return fail_check(4);
+                    continue;
+                }
+                if ((uint64_t)e >= num_owned || seen[e]) return fail_check(5);
+                seen[e] = 1;
+                ++real;
+                for (int a = 0; a < n; ++a) {
+                    if (ln[a] >= nn || (ht.nodes[nb + ln[a]] & 0x7fffffff) != conn[(uint64_t)e * n + a]) return fail_check(6);
+                    if (used[ln[a]]) return fail_check(7);  // two elements of a round share a node (or an element repeats one)
+                    used[ln[a]] = 1;
+                    ++inc[ln[a]];
+                }
+                for (int a = 0; a < n; ++a)
+                    for (int b = 0; b < n; ++b) {
+                        const uint16_t ps = em[a * n + b];
+                        if (ln[a] > ln[b]) {
+                            if (ps != 0xffffu) return fail_check(8);
+                            continue;
+                        }
+                        if (ps >= P) return fail_check(8);
+                        pairs.emplace_back(((uint32_t)ln[a] << 8) | ln[b], ps);
+                    }
+            }
+        }
+        if (real != ne) return fail_check(9);
+        scheduled += (uint64_t)R * shape.warps;
+        // a node pair always maps to the same accumulator, and different pairs to different accumulators
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+        std::vector<uint8_t> taken(P, 0);
+        for (size_t i = 0; i < pairs.size(); ++i) {
+            if (i && pairs[i].first == pairs[i - 1].first) return fail_check(10);
+            if (taken[pairs[i].second]) return fail_check(11);
+            taken[pairs[i].second] = 1;
+        }
+        // flush list: every coupled ordered pair (u, v) exactly once, in CSR order of row u, with the position of v in u's block row
+        if (nf != 2 * pairs.size() - [&] { size_t d = 0; for (auto& pr : pairs) d += (pr.first >> 8) == (pr.first & 0xffu); return d; }()) return fail_check(12);
+        uint32_t last_u = 0, last_k = 0;
+        for (uint32_t f = 0; f < nf; ++f) {
+            const uint32_t w = ht.flush[fb + f];
+            const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = w >> 19;
+            if (u >= nn) return fail_check(13);
+            if (f && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
+            last_u = u;
+            last_k = k;
+            const auto& r = rows[ht.nodes[nb + u] & 0x7fffffff];
+            if (k >= r.size()) return fail_check(15);
+            const int32_t vg = r[k];
+            const auto it = std::lower_bound(ht.nodes.begin() + nb, ht.nodes.begin() + nb + nn, vg, [](int32_t x, int32_t y) { return (x & 0x7fffffff) < y; });
+            if (it == ht.nodes.begin() + nb + nn || (*it & 0x7fffffff) != vg) return fail_check(16);
+            const uint32_t v = (uint32_t)(it - (ht.nodes.begin() + nb));
+            if (tr != (u > v ? 1u : 0u)) return fail_check(17);
+            const uint32_t key = ((std::min(u, v)) << 8) | std::max(u, v);
+            const auto pit = std::lower_bound(pairs.begin(), pairs.end(), std::make_pair(key, 0u));
+            if (pit == pairs.end() || pit->first != key || pit->second != ps) return fail_check(18);
+        }
+        for (uint32_t u = 0; u < nn; ++u) {
+            const bool flag = ht.nodes[nb + u] < 0;
+            if (flag != (inc[u] == degree[ht.nodes[nb + u] & 0x7fffffff])) return fail_check(19);
+            complete += flag;
+        }
+    }
+    for (uint64_t e = 0; e < num_owned; ++e)
+        if (!seen[e]) return fail_check(20);
+    stats[0] = ntiles;
+    stats[1] = max_nodes;
+    stats[2] = max_P;
+    stats[3] = ht.flush.size();
+    stats[4] = complete;
+    stats[5] = (uint64_t)(ht.bank_conflict_share * 1e6);
+    stats[6] = scheduled;
+    stats[7] = max_rounds;
+    return FB200_OK;
+}

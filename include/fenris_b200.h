@@ -188,6 +188,16 @@ fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_point
 /* LameParameters::from(YoungPoisson) (fenris-solid/src/materials.rs:31-43). */
 void fb200_lame_from_young_poisson(double young, double poisson, double* mu, double* lambda);
 
+/* Host-only self check of the Hex8 tile lists (csrc/tiles.cpp) on a caller-supplied Hex8 mesh; no GPU needed.  Builds the node-block
+ * map the way fb200_assemble_pattern does, the Morton order, the tile lists, and verifies them: every element scheduled exactly once,
+ * rounds node-disjoint, every block (a, b) with u_a <= u_b mapped to the accumulator of its node pair, the flush list covering every
+ * coupled pair of the tile exactly once with the right position in the CSR block row, complete flags, size limits.
+ * stats[0..7] = tiles, max nodes, max accumulator positions, flush entries, complete nodes, bank-conflict share * 1e6, schedule positions,
+ * max rounds.  Returns FB200_OK, FB200_ERR_UNSUPPORTED when the mesh cannot use tiles (repeated nodes), FB200_ERR_STATE + (*failed_check = id)
+ * when a check fails. */
+fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
+                                       uint64_t num_owned, uint64_t stats[8], int32_t* failed_check);
+
 #ifdef __cplusplus
 }
 #endif
