@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scatter", default=os.environ.get("FB200_SCATTER", "atomic"), choices=list(MODE_NAMES))
     ap.add_argument("--cells", type=int, default=CELLS, help="cells per edge per GPU (126 = BASELINE config C3)")
+    ap.add_argument("--exchange", default="peers", choices=["peers", "allreduce"],
+                    help="N > 1: interface rows by neighbour ncclSend/ncclRecv (default) or one world ncclAllReduce")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra JSON field)")
@@ -225,7 +227,10 @@ def main():
         uid = [fb.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
-        ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
+        if args.exchange == "peers":
+            ctx.interface_set_peers(iface["peers"])
+        else:
+            ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
     ctx.synchronize()
     setup_s = time.perf_counter() - t_setup
 
@@ -350,7 +355,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C3: Hex8 linear elasticity (fenris-solid), unit cube {cells}^3 cells per GPU, Gauss 2^3, Lame(E=1e6, nu=0.2), u=0",
                        "elements_per_gpu": int(n_owned), "nnz_per_gpu": int(nnz), "scatter": args.scatter,
-                       "parallelism": "1 GPU" if world == 1 else f"z-slab element partition x{world}, interface-row ncclAllReduce",
+                       "parallelism": "1 GPU" if world == 1 else f"z-slab element partition x{world}, interface rows: " +
+                                      ("neighbour ncclSend/ncclRecv, summed on arrival" if args.exchange == "peers" else "world ncclAllReduce"),
                        "l2": "inputs+outputs >> L2 (values 3.9 GB per GPU); no L2 flush needed", "setup_s": setup_s},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }

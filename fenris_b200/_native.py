@@ -98,6 +98,7 @@ def lib():
         "fb200_comm_unique_id": (i32, [C.c_char_p]),
         "fb200_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
         "fb200_interface_set": (i32, [vp, u64, vp, vp, u64]),
+        "fb200_interface_set_peers": (i32, [vp, u64, vp, vp, vp]),
         "fb200_interface_allreduce": (i32, [vp]),
         "fb200_gen_hex_mesh": (i32, [u64, u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_gen_tet_mesh": (i32, [u64, u64, u64, dbl, pu64, pu64, vp, vp]),

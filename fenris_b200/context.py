@@ -205,5 +205,15 @@ class Context:
             o = np.zeros(1, dtype=np.uint64)
         self._check(self._lib.fb200_interface_set(self._h, cnt, nat.ptr(n), nat.ptr(o), packed_len))
 
+    def interface_set_peers(self, peers):
+        """peers: sequence of (peer_rank, local_node_ids) - the neighbour-exchange form of the interface (partition.py)."""
+        ranks = np.ascontiguousarray([int(r) for r, _ in peers] or [0], dtype=np.int32)
+        lists = [nat.as_u64(n) for _, n in peers]
+        begin = np.zeros(len(peers) + 1, dtype=np.uint64)
+        if lists:
+            begin[1:] = np.cumsum([len(x) for x in lists])
+        nodes = np.concatenate(lists) if lists and int(begin[-1]) else np.zeros(1, dtype=np.uint64)
+        self._check(self._lib.fb200_interface_set_peers(self._h, len(peers), nat.ptr(ranks), nat.ptr(begin), nat.ptr(nat.as_u64(nodes))))
+
     def interface_allreduce(self):
         self._check(self._lib.fb200_interface_allreduce(self._h))

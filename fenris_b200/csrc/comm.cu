@@ -22,6 +22,10 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -47,6 +51,10 @@ static bool load_nccl(std::string* why) {
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
         if (why) *why = "libnccl.so.2 lacks required symbols";
@@ -77,6 +85,22 @@ __global__ void iface_copy_kernel(const int32_t* __restrict__ nodes, const int64
         for (int64_t t = lane; t < len; t += 32) {
             if (PACK) pk[t] = v[t]; else v[t] = pk[t];
         }
+    }
+}
+
+// values of node row blocks += received blocks (a node shared with several peers gets several additions: reductions)
+__global__ void iface_add_kernel(const int32_t* __restrict__ nodes, const int64_t* __restrict__ offsets, uint64_t count,
+                                 const int64_t* __restrict__ blk_off, int ss, double* values, const double* __restrict__ recv) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t k = gwarp; k < count; k += nwarps) {
+        const int32_t node = nodes[k];
+        const int64_t b = blk_off[node];
+        const int64_t len = (blk_off[node + 1] - b) * ss;
+        double* v = values + b * ss;
+        const double* pk = recv + offsets[k];
+        for (int64_t t = lane; t < len; t += 32) atomicAdd(v + t, pk[t]);
     }
 }
 
@@ -155,11 +179,90 @@ fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t*
     return FB200_OK;
 }
 
+fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const int32_t* peer_ranks, const uint64_t* peer_begin,
+                                       const uint64_t* nodes) {
+    if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_set_peers needs a pattern");
+    if (num_peers && (!peer_ranks || !peer_begin || !nodes)) return fail(ctx, FB200_ERR_SHAPE, "null peer arrays");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    dev_free(ctx->d_peer_nodes);
+    dev_free(ctx->d_peer_offsets);
+    dev_free(ctx->d_peer_send);
+    dev_free(ctx->d_peer_recv);
+    ctx->peer_ranks.clear();
+    ctx->peer_seg_off.clear();
+    ctx->peer_count = 0;
+    if (num_peers == 0) return FB200_OK;
+    std::vector<int64_t> off(ctx->N + 1);
+    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    const uint64_t ss = (uint64_t)ctx->sdim * ctx->sdim, total_nodes = peer_begin[num_peers];
+    std::vector<int32_t> h_nodes(total_nodes);
+    std::vector<int64_t> h_offs(total_nodes);
+    std::vector<uint64_t> seg(num_peers + 1, 0);
+    uint64_t pos = 0;
+    for (uint64_t pr = 0; pr < num_peers; ++pr) {
+        if (peer_begin[pr] > peer_begin[pr + 1]) return fail(ctx, FB200_ERR_SHAPE, "peer_begin must be non-decreasing");
+        if (peer_ranks[pr] < 0 || peer_ranks[pr] == ctx->rank || (ctx->nranks > 1 && peer_ranks[pr] >= ctx->nranks))
+            return fail(ctx, FB200_ERR_SHAPE, "bad peer rank");
+        seg[pr] = pos;
+        for (uint64_t k = peer_begin[pr]; k < peer_begin[pr + 1]; ++k) {
+            if (nodes[k] >= ctx->N) return fail(ctx, FB200_ERR_INDEX_OOB, "interface node out of range");
+            h_nodes[k] = (int32_t)nodes[k];
+            h_offs[k] = (int64_t)pos;
+            pos += (uint64_t)(off[nodes[k] + 1] - off[nodes[k]]) * ss;
+        }
+    }
+    seg[num_peers] = pos;
+    FB200_TRY(dev_alloc(ctx, &ctx->d_peer_nodes, total_nodes));
+    FB200_TRY(dev_alloc(ctx, &ctx->d_peer_offsets, total_nodes));
+    FB200_TRY(dev_alloc(ctx, &ctx->d_peer_send, pos));
+    FB200_TRY(dev_alloc(ctx, &ctx->d_peer_recv, pos));
+    if (total_nodes) {
+        FB200_CUDA(ctx, cudaMemcpy(ctx->d_peer_nodes, h_nodes.data(), total_nodes * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FB200_CUDA(ctx, cudaMemcpy(ctx->d_peer_offsets, h_offs.data(), total_nodes * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    ctx->peer_ranks.assign(peer_ranks, peer_ranks + num_peers);
+    ctx->peer_seg_off = seg;
+    ctx->peer_count = total_nodes;
+    return FB200_OK;
+}
+
+// neighbour exchange: every rank sends the packed rows it shares with a peer and adds what the peer sends back
+static fb200_status interface_exchange_peers(fb200_ctx* ctx) {
+    if (!ctx->nccl_comm) return fail(ctx, FB200_ERR_STATE, "fb200_comm_init has not been called");
+    if (!g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) return fail(ctx, FB200_ERR_NCCL, "libnccl lacks ncclSend/ncclRecv");
+    const int ss = ctx->sdim * ctx->sdim;
+    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(ctx->peer_count * 32, 256), (uint64_t)ctx->sm_count * 8));
+    if (ctx->peer_count) {
+        iface_copy_kernel<true><<<blocks, 256, 0, ctx->stream>>>(ctx->d_peer_nodes, ctx->d_peer_offsets, ctx->peer_count, ctx->d_blk_off, ss,
+                                                                ctx->d_values, ctx->d_peer_send);
+        FB200_TRY(check_launch(ctx, "iface_copy_kernel<pack peers>"));
+    }
+    int rc = g_nccl.GroupStart();
+    if (rc != 0) return nccl_fail(ctx, rc, "ncclGroupStart");
+    for (size_t pr = 0; pr < ctx->peer_ranks.size(); ++pr) {
+        const uint64_t o = ctx->peer_seg_off[pr], len = ctx->peer_seg_off[pr + 1] - o;
+        if (len == 0) continue;
+        rc = g_nccl.Send(ctx->d_peer_send + o, len, /*ncclFloat64*/ 8, ctx->peer_ranks[pr], ctx->nccl_comm, ctx->stream);
+        if (rc == 0) rc = g_nccl.Recv(ctx->d_peer_recv + o, len, /*ncclFloat64*/ 8, ctx->peer_ranks[pr], ctx->nccl_comm, ctx->stream);
+        if (rc != 0) break;
+    }
+    const int rc_end = g_nccl.GroupEnd();
+    if (rc != 0) return nccl_fail(ctx, rc, "ncclSend/ncclRecv");
+    if (rc_end != 0) return nccl_fail(ctx, rc_end, "ncclGroupEnd");
+    if (ctx->peer_count) {
+        iface_add_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_peer_nodes, ctx->d_peer_offsets, ctx->peer_count, ctx->d_blk_off, ss, ctx->d_values,
+                                                         ctx->d_peer_recv);
+        FB200_TRY(check_launch(ctx, "iface_add_kernel"));
+    }
+    return FB200_OK;
+}
+
 fb200_status fb200_interface_allreduce(fb200_ctx* ctx) {
     if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_allreduce needs a pattern");
     if (ctx->nranks > 1 && !ctx->nccl_comm) return fail(ctx, FB200_ERR_STATE, "fb200_comm_init has not been called");
-    if (ctx->iface_packed_len == 0) return FB200_OK;
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->peer_ranks.empty()) return interface_exchange_peers(ctx);
+    if (ctx->iface_packed_len == 0) return FB200_OK;
     const int ss = ctx->sdim * ctx->sdim;
     const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(ctx->iface_count * 32, 256), (uint64_t)ctx->sm_count * 8));
     FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_iface_packed, 0, ctx->iface_packed_len * sizeof(double), ctx->stream));

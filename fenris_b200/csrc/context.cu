@@ -245,6 +245,13 @@ void fb200_destroy(fb200_ctx* ctx) {
     dev_free(ctx->d_iface_nodes);
     dev_free(ctx->d_iface_offsets);
     dev_free(ctx->d_iface_packed);
+    dev_free(ctx->d_peer_nodes);
+    dev_free(ctx->d_peer_offsets);
+    dev_free(ctx->d_peer_send);
+    dev_free(ctx->d_peer_recv);
+    ctx->peer_ranks.clear();
+    ctx->peer_seg_off.clear();
+    ctx->peer_count = 0;
     if (ctx->h_errword) cudaFreeHost(ctx->h_errword);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -193,6 +193,14 @@ struct fb200_ctx {
     int32_t* d_iface_nodes = nullptr;
     int64_t* d_iface_offsets = nullptr;
     double* d_iface_packed = nullptr;
+    // neighbour exchange (fb200_interface_set_peers): per-peer segments of the send / receive buffers
+    std::vector<int32_t> peer_ranks;
+    std::vector<uint64_t> peer_seg_off;   // num_peers + 1, in doubles
+    uint64_t peer_count = 0;              // interface incidences (nodes over all segments)
+    int32_t* d_peer_nodes = nullptr;
+    int64_t* d_peer_offsets = nullptr;
+    double* d_peer_send = nullptr;
+    double* d_peer_recv = nullptr;
 };
 
 namespace fb200 {

@@ -2,7 +2,8 @@
 
 The mesh is split by ELEMENTS; a rank assembles only the elements it owns.  Rows of nodes that touch elements of
 more than one rank ("interface nodes") receive partial sums on each of them and are completed by
-`fb200_interface_allreduce` (ncclAllReduce over a packed buffer of interface rows only).  To make the CSR row layout
+`fb200_interface_allreduce`: a neighbour exchange of the packed interface rows (ncclSend/ncclRecv per peer, summed on arrival) when the
+interface is given as peer lists, else an ncclAllReduce over a packed buffer of all interface rows.  To make the CSR row layout
 of an interface node identical on every sharing rank, each rank also receives the other ranks' elements that touch
 its interface nodes as GHOST elements: they take part in the sparsity pattern but are not assembled
 (`fb200_set_num_owned_elements`).
@@ -73,7 +74,13 @@ def structured_hex_slab(cx: int, cy: int, cz: int, h: float, rank: int, nranks: 
             zplane = pidx * per
             local_nodes.append(np.arange(plane, dtype=np.uint64) + np.uint64(plane * (zplane - z0)))
             offsets.append(within + np.uint64((pidx - 1) * plane_len))
+    peers = []  # neighbour-exchange form: (peer rank, local ids of the shared plane in plane order - the same order on both sides)
+    if rank > 0:
+        peers.append((rank - 1, np.arange(plane, dtype=np.uint64) + np.uint64(plane * (k0 - z0))))
+    if rank < nranks - 1:
+        peers.append((rank + 1, np.arange(plane, dtype=np.uint64) + np.uint64(plane * (k1 - z0))))
     iface = {
+        "peers": peers,
         "local_nodes": np.concatenate(local_nodes) if local_nodes else np.zeros(0, dtype=np.uint64),
         "packed_offsets": np.concatenate(offsets) if offsets else np.zeros(0, dtype=np.uint64),
         "packed_len": plane_len * max(nranks - 1, 0),
@@ -107,7 +114,14 @@ def general_partition(connectivity: np.ndarray, part_of_element: np.ndarray, num
         ghost_mask = (part != r) & mine[conn].any(axis=1)
         ghosts = np.nonzero(ghost_mask)[0]
         sel = np.isin(iface_global, np.nonzero(mine)[0])
-        out.append({"owned": owned, "ghosts": ghosts, "iface_global": iface_global[sel], "packed_offsets": offs[sel], "packed_len": packed_len})
+        peers = {}  # peer rank -> global ids (ascending) of the nodes shared with it: the neighbour-exchange form
+        for q in range(nranks):
+            if q != r:
+                both = np.nonzero(mine & touched[q])[0]
+                if len(both):
+                    peers[q] = both
+        out.append({"owned": owned, "ghosts": ghosts, "iface_global": iface_global[sel], "packed_offsets": offs[sel], "packed_len": packed_len,
+                    "peers": peers})
     return out
 
 

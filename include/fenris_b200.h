@@ -167,7 +167,14 @@ fb200_status fb200_comm_init(fb200_ctx* ctx, const char id[FB200_UNIQUE_ID_BYTES
  * layout on every rank. */
 fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t* local_nodes, const uint64_t* packed_offsets,
                                  uint64_t packed_len);
-/* pack interface rows -> ncclAllReduce(sum, f64) over NVLink -> unpack.  Enqueued on the ctx stream. */
+/* Optional, instead of fb200_interface_set: the interface as a list of PEERS.  Segment p = the local nodes shared with rank
+ * peer_ranks[p], nodes[peer_begin[p] .. peer_begin[p+1]), in an order both ranks agree on (e.g. ascending global id); a node shared
+ * with several ranks appears in each of their segments.  The exchange then is a neighbour exchange (ncclSend / ncclRecv of the packed
+ * segments inside one group, sum on arrival) instead of a world all-reduce whose buffer grows with the number of ranks. */
+fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const int32_t* peer_ranks, const uint64_t* peer_begin,
+                                       const uint64_t* nodes);
+/* Sum the interface rows over the ranks that share them.  Peers set: pack per peer -> ncclSend/ncclRecv (one group) -> add the
+ * received blocks; otherwise pack -> ncclAllReduce(sum, f64) -> unpack.  Over NVLink, enqueued on the ctx stream. */
 fb200_status fb200_interface_allreduce(fb200_ctx* ctx);
 
 /* ---- host-side helpers restating the reference's generators (no GPU needed) ----------------- */

@@ -15,7 +15,7 @@ def _num_gpus():
         return 0
 
 
-def _worker(rank, world, uid, cx, cy, cz, scatter_mode, q):
+def _worker(rank, world, uid, cx, cy, cz, scatter_mode, exchange, q):
     try:
         import fenris_b200 as fb
         from fenris_b200 import partition
@@ -31,7 +31,10 @@ def _worker(rank, world, uid, cx, cy, cz, scatter_mode, q):
         ctx.assemble_pattern(3)
         ctx.color_nodes()
         ctx.comm_init(uid, rank, world)
-        ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
+        if exchange == "peers":
+            ctx.interface_set_peers(iface["peers"])
+        else:
+            ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
         for _ in range(2):  # twice: the exchange must be repeatable (overwrite semantics)
             ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, (mu, lam), scatter_mode=scatter_mode, accumulate=False)
             ctx.interface_allreduce()
@@ -64,8 +67,8 @@ def _worker(rank, world, uid, cx, cy, cz, scatter_mode, q):
 
 
 @pytest.mark.skipif(_num_gpus() < 2, reason="needs at least two GPUs")
-@pytest.mark.parametrize("scatter_mode", [0, 2])
-def test_slab_partition_nccl_equals_global(scatter_mode):
+@pytest.mark.parametrize("scatter_mode,exchange", [(0, "peers"), (0, "allreduce"), (2, "peers")])
+def test_slab_partition_nccl_equals_global(scatter_mode, exchange):
     import torch.multiprocessing as mp
 
     import fenris_b200 as fb
@@ -75,7 +78,7 @@ def test_slab_partition_nccl_equals_global(scatter_mode):
     uid = fb.Context.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, uid, cx, cy, cz, scatter_mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, uid, cx, cy, cz, scatter_mode, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]

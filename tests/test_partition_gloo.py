@@ -35,7 +35,7 @@ def _assemble_owned(verts, conn, n_owned, sdim_op):
     return ro, ci, values
 
 
-def _worker(rank, world, port, cx, cy, cz, q):
+def _worker(rank, world, port, cx, cy, cz, exchange, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,15 +45,33 @@ def _worker(rank, world, port, cx, cy, cz, q):
         ro, ci, values = _assemble_owned(verts, conn, n_owned, fo.LINEAR_ELASTIC)
         s = 3
         # pack (same arithmetic as iface_copy_kernel<PACK>): node row block = values[s*s*blk_off[node] ...]
-        packed = np.zeros(iface["packed_len"])
-        for node, off in zip(iface["local_nodes"].astype(np.int64), iface["packed_offsets"].astype(np.int64)):
-            b, e = int(ro[s * node]), int(ro[s * node + s])
-            packed[off:off + (e - b)] = values[b:e]
-        t = torch.from_numpy(packed)
-        dist.all_reduce(t)
-        for node, off in zip(iface["local_nodes"].astype(np.int64), iface["packed_offsets"].astype(np.int64)):
-            b, e = int(ro[s * node]), int(ro[s * node + s])
-            values[b:e] = packed[off:off + (e - b)]
+        if exchange == "peers":
+            # neighbour exchange (fb200_interface_set_peers): pack the rows shared with each peer, swap, add what arrives
+            sends, recvs, reqs = [], [], []
+            for peer, nodes in iface["peers"]:
+                seg = np.concatenate([values[int(ro[s * n]):int(ro[s * n + s])] for n in nodes.astype(np.int64)])
+                sends.append(torch.from_numpy(seg.copy()))
+                recvs.append(torch.zeros(len(seg), dtype=torch.float64))
+                reqs.append(dist.isend(sends[-1], dst=peer))
+                reqs.append(dist.irecv(recvs[-1], src=peer))
+            for r in reqs:
+                r.wait()
+            for (peer, nodes), got in zip(iface["peers"], recvs):
+                got, o = got.numpy(), 0
+                for n in nodes.astype(np.int64):
+                    b, e = int(ro[s * n]), int(ro[s * n + s])
+                    values[b:e] += got[o:o + (e - b)]
+                    o += e - b
+        else:
+            packed = np.zeros(iface["packed_len"])
+            for node, off in zip(iface["local_nodes"].astype(np.int64), iface["packed_offsets"].astype(np.int64)):
+                b, e = int(ro[s * node]), int(ro[s * node + s])
+                packed[off:off + (e - b)] = values[b:e]
+            t = torch.from_numpy(packed)
+            dist.all_reduce(t)
+            for node, off in zip(iface["local_nodes"].astype(np.int64), iface["packed_offsets"].astype(np.int64)):
+                b, e = int(ro[s * node]), int(ro[s * node + s])
+                values[b:e] = packed[off:off + (e - b)]
         # rows of the nodes in the planes this rank's owned cells touch, with global ids
         per = cz // world
         plane = (cx + 1) * (cy + 1)
@@ -70,13 +88,13 @@ def _worker(rank, world, port, cx, cy, cz, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,cz", [(2, 4), (3, 6)])
-def test_slab_partition_allreduce_equals_global(world, cz):
+@pytest.mark.parametrize("world,cz,exchange", [(2, 4, "allreduce"), (3, 6, "allreduce"), (2, 4, "peers"), (3, 6, "peers")])
+def test_slab_partition_allreduce_equals_global(world, cz, exchange):
     cx = cy = 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, cx, cy, cz, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cx, cy, cz, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
@@ -98,6 +116,23 @@ def test_slab_partition_allreduce_equals_global(world, cz):
             assert np.allclose(v, vals[b:e], rtol=1e-13, atol=1e-9 * np.abs(vals).max()), (rank, grow)
             checked += 1
     assert checked >= len(ro) - 1  # every global row is held (complete) by at least one rank
+
+
+def test_general_partition_peer_lists_are_symmetric():
+    # the neighbour-exchange form: rank r's list for peer q and q's list for r name the same global nodes in the same order,
+    # and together the lists of a rank cover exactly its interface nodes
+    v, c = fo.create_unit_box_uniform_tet_mesh_3d(3)
+    ro, _ = fo.assemble_pattern_fast(1, len(v), c)
+    centroid = v[c].mean(axis=1)
+    part = (centroid[:, 0] > 0.5).astype(np.int64) + 2 * (centroid[:, 1] > 0.5).astype(np.int64)  # 4 parts meeting along a line
+    layout = partition.general_partition(c, part, len(v), 4, 1, np.diff(ro.astype(np.int64)))
+    for r, l in enumerate(layout):
+        union = np.zeros(0, dtype=np.int64)
+        for q, ids in l["peers"].items():
+            assert q != r and np.array_equal(ids, layout[q]["peers"][r]) and np.all(np.diff(ids) > 0)
+            union = np.union1d(union, ids)
+        assert np.array_equal(union, l["iface_global"])
+    assert any(len(l["peers"]) == 3 for l in layout)  # nodes on the common line are shared by all four ranks
 
 
 def test_general_partition_layout_is_consistent():
