@@ -6,9 +6,9 @@ The numerical path is libfenris_b200.so (hand-written CUDA); there is no CPU fal
 from ._native import (ERR_COLORING, ERR_COLUMN_NOT_IN_PATTERN, ERR_CUDA, ERR_INDEX_OOB, ERR_NCCL, ERR_SHAPE,  # noqa: F401
                       ERR_SINGULAR_JACOBIAN, ERR_STATE, ERR_UNSUPPORTED, HEX8, HEX27, LAPLACE, LINEAR_ELASTIC, OK, QUAD4,
                       SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER, TET4, TET10, Fb200Error, SingularJacobianError)
-from .api import (CsrAssembler, CsrMatrix, CsrParAssembler, DisjointSubsets, ElementConnectivityAssembler,  # noqa: F401
-                  ElementEllipticAssembler, ElementEllipticAssemblerBuilder, LameParameters, LaplaceOperator,
-                  LinearElasticMaterial, MaterialEllipticOperator, Mesh, SparsityPattern, UniformQuadratureTable, YoungPoisson,
+from .api import (CsrAssembler, CsrMatrix, CsrParAssembler, Density, DisjointSubsets, ElementConnectivityAssembler,  # noqa: F401
+                  ElementEllipticAssembler, ElementEllipticAssemblerBuilder, ElementMassAssembler, ElementSourceAssembler, LameParameters, LaplaceOperator,
+                  LinearElasticMaterial, MaterialEllipticOperator, Mesh, SparsityPattern, UniformQuadratureTable, VectorAssembler, VectorParAssembler, YoungPoisson,
                   canonical_stiffness_quadrature, color_nodes, create_rectangular_uniform_hex_mesh,
                   create_rectangular_uniform_tet_mesh, create_unit_box_uniform_hex_mesh_3d, create_unit_box_uniform_tet_mesh_3d,
                   create_unit_square_uniform_quad_mesh_2d, hex27_mesh_from)

@@ -95,6 +95,10 @@ def lib():
         "fb200_values_download": (i32, [vp, vp]),
         "fb200_values_upload": (i32, [vp, vp]),
         "fb200_element_matrices": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), u64, u64, vp]),
+        "fb200_assemble_mass_into_csr_device": (i32, [vp, C.POINTER(Quadrature), i32, i32]),
+        "fb200_assemble_mass_into_csr": (i32, [vp, C.POINTER(Quadrature), i32, i32, vp]),
+        "fb200_assemble_vector": (i32, [vp, C.POINTER(Quadrature), i32, vp, i32, i32, i32, vp]),
+        "fb200_physical_quadrature_points": (i32, [vp, C.POINTER(Quadrature), vp]),
         "fb200_comm_unique_id": (i32, [C.c_char_p]),
         "fb200_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
         "fb200_interface_set": (i32, [vp, u64, vp, vp, u64]),

@@ -308,6 +308,136 @@ class ElementEllipticAssemblerBuilder:
         return ElementEllipticAssembler(self._space, self._op, self._qt, self._u)
 
 
+class Density(float):
+    """Parameters of the mass matrix: a density per quadrature point (src/assembly/local/mass.rs:23-31)."""
+
+
+class ElementMassAssembler:
+    """src/assembly/local/mass.rs:33-159: M_IJ = I_s int rho phi_I phi_J.  qtable.data = one Density per point."""
+
+    def __init__(self, space: Mesh, qtable: UniformQuadratureTable, solution_dim: int):
+        self.space, self.qtable, self._s = space, qtable, int(solution_dim)
+
+    @staticmethod
+    def with_finite_element_space(space):  # builder-style spelling of the reference (mass.rs:52-107)
+        return _MassBuilder(space)
+
+    def solution_dim(self):
+        return self._s
+
+    def num_elements(self):
+        return self.space.num_elements()
+
+    def num_nodes(self):
+        return self.space.num_nodes()
+
+    def element_node_count(self, i):
+        return self.space.element_node_count(i)
+
+    def populate_element_nodes(self, output, i):
+        self.space.populate_element_nodes(output, i)
+
+    def _density(self):
+        if self.qtable.data is None:
+            raise Fb200Error(nat.ERR_SHAPE, "quadrature table carries no Density data")
+        return np.array([float(d) for d in self.qtable.data], dtype=np.float64)
+
+
+class _MassBuilder:
+    def __init__(self, space):
+        self._space, self._qt, self._s = space, None, None
+
+    def with_quadrature_table(self, qt):
+        self._qt = qt
+        return self
+
+    def with_solution_dim(self, s):
+        self._s = s
+        return self
+
+    def build(self) -> ElementMassAssembler:
+        assert self._qt is not None and self._s is not None
+        return ElementMassAssembler(self._space, self._qt, self._s)
+
+
+class ElementSourceAssembler:
+    """src/assembly/local/source.rs:24-190: f_I = int f(x) phi_I.  `source` is a callable (x: (..., d) array, data) -> (..., s) array
+    (SourceFunction::evaluate, vectorised); it runs on the host at the physical quadrature points the device computes."""
+
+    def __init__(self, space: Mesh, qtable: UniformQuadratureTable, source, solution_dim: int):
+        self.space, self.qtable, self.source, self._s = space, qtable, source, int(solution_dim)
+
+    def solution_dim(self):
+        return self._s
+
+    def num_elements(self):
+        return self.space.num_elements()
+
+    def num_nodes(self):
+        return self.space.num_nodes()
+
+    def element_node_count(self, i):
+        return self.space.element_node_count(i)
+
+    def populate_element_nodes(self, output, i):
+        self.space.populate_element_nodes(output, i)
+
+
+class VectorAssembler:
+    """src/assembly/global.rs:569-617 (serial semantics); on the device element-parallel with f64 atomics."""
+
+    def __init__(self, device: int = 0, scatter_mode: int = nat.SCATTER_ATOMIC):
+        self.ctx = Context(device)
+        self.scatter_mode = scatter_mode
+
+    def _colors(self):
+        return None
+
+    def assemble_vector_into(self, output: np.ndarray, ea: ElementSourceAssembler):
+        ctx = self.ctx
+        ctx.space_upload(ea.space.element_type, ea.space.vertices_, ea.space.connectivity_)
+        s, n = ea.solution_dim(), ea.num_nodes()
+        assert len(output) == s * n, "Output dimensions mismatch"  # global.rs:592
+        mode = self.scatter_mode
+        colors = self._colors()
+        if colors is not None:
+            offs = np.zeros(len(colors) + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(c.labels()) for c in colors])
+            elems = np.concatenate([c.labels() for c in colors]) if len(colors) else np.zeros(0, dtype=np.uint64)
+            ctx.colors_adopt(offs, elems)
+            mode = nat.SCATTER_COLORED
+        qt = ea.qtable
+        x = ctx.physical_quadrature_points(qt.weights, qt.points, ea.num_elements())
+        data = qt.data if qt.data is not None else [None] * len(qt.weights)
+        f = np.stack([np.asarray(ea.source(x[:, q], data[q]), dtype=np.float64).reshape(ea.num_elements(), s) for q in range(len(qt.weights))], axis=1)
+        ctx.assemble_vector(qt.weights, qt.points, np.ascontiguousarray(f), n, out=output, scatter_mode=mode, accumulate=True)
+        return output
+
+    def assemble_vector(self, ea: ElementSourceAssembler) -> np.ndarray:
+        return self.assemble_vector_into(np.zeros(ea.solution_dim() * ea.num_nodes()), ea)
+
+
+class VectorParAssembler(VectorAssembler):
+    """src/assembly/global.rs:619-686: coloured; one launch per colour, plain read-modify-write."""
+
+    def __init__(self, device: int = 0):
+        super().__init__(device, nat.SCATTER_COLORED)
+        self._cols = None
+
+    def _colors(self):
+        return self._cols
+
+    def assemble_vector(self, colors, ea):  # type: ignore[override]
+        self._cols = list(colors)
+        return super().assemble_vector(ea)
+
+    def assemble_vector_into(self, output, colors=None, ea=None):  # type: ignore[override]
+        if ea is None:  # called through the base class with (output, ea)
+            return super().assemble_vector_into(output, colors)
+        self._cols = list(colors)
+        return super().assemble_vector_into(output, ea)
+
+
 # ----------------------------------------------------------------------------- CSR containers / colours
 class SparsityPattern:
     def __init__(self, major_offsets, minor_indices, nrows):
@@ -348,7 +478,7 @@ class DisjointSubsets:
 
 
 def _upload(ctx: Context, assembler):
-    if isinstance(assembler, ElementEllipticAssembler):
+    if isinstance(assembler, (ElementEllipticAssembler, ElementMassAssembler, ElementSourceAssembler)):
         ctx.space_upload(assembler.space.element_type, assembler.space.vertices_, assembler.space.connectivity_)
     elif isinstance(assembler, Mesh):
         ctx.space_upload(assembler.element_type, assembler.vertices_, assembler.connectivity_)
@@ -413,6 +543,11 @@ class CsrAssembler:
             self.ctx.colors_adopt(offs, elems)
             mode = nat.SCATTER_COLORED
         if len(csr.values) == 0:
+            return
+        if isinstance(ea, ElementMassAssembler):
+            if mode == nat.SCATTER_GATHER:
+                mode = nat.SCATTER_ATOMIC
+            self.ctx.assemble_mass_into_csr(ea.qtable.weights, ea.qtable.points, ea._density(), csr.values, scatter_mode=mode, accumulate=True)
             return
         self.ctx.assemble_into_csr(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), csr.values, scatter_mode=mode, accumulate=True)
 

@@ -162,6 +162,51 @@ class Context:
         self._check(self._lib.fb200_assemble_into_csr(self._h, C.byref(op), C.byref(q), None, scatter_mode, int(accumulate), nat.ptr(values)))
         return values
 
+    # -- mass matrix / source vector / physical points
+    def _quad_only(self, weights, points, density=None):
+        w = nat.as_f64(weights)
+        p = nat.as_f64(points).reshape(len(w), -1)
+        d = None
+        if density is not None:
+            d = nat.as_f64(density).reshape(-1)
+            if d.size == 1:
+                d = np.full(len(w), float(d[0]))
+            assert d.shape == (len(w),)
+        self._keep = [w, p, d]
+        return nat.Quadrature(len(w), p.shape[1], w.ctypes.data_as(C.POINTER(C.c_double)), p.ctypes.data_as(C.POINTER(C.c_double)),
+                              d.ctypes.data_as(C.POINTER(C.c_double)) if d is not None else None)
+
+    def assemble_mass_into_csr_device(self, weights, points, density, scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False):
+        q = self._quad_only(weights, points, density)
+        self._check(self._lib.fb200_assemble_mass_into_csr_device(self._h, C.byref(q), scatter_mode, int(accumulate)))
+
+    def assemble_mass_into_csr(self, weights, points, density, values: np.ndarray, scatter_mode: int = nat.SCATTER_ATOMIC,
+                               accumulate: bool = True):
+        assert values.dtype == np.float64 and values.flags["C_CONTIGUOUS"] and values.size >= self.nnz
+        q = self._quad_only(weights, points, density)
+        self._check(self._lib.fb200_assemble_mass_into_csr(self._h, C.byref(q), scatter_mode, int(accumulate), nat.ptr(values)))
+        return values
+
+    def assemble_vector(self, weights, points, source_values, num_nodes: int, out: Optional[np.ndarray] = None,
+                        scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False) -> np.ndarray:
+        """source_values: (q, s) shared by all elements, or (E, q, s)."""
+        f = nat.as_f64(source_values)
+        assert f.ndim in (2, 3)
+        s = f.shape[-1]
+        if out is None:
+            out = np.zeros(s * num_nodes)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == s * num_nodes
+        q = self._quad_only(weights, points)
+        self._check(self._lib.fb200_assemble_vector(self._h, C.byref(q), s, nat.ptr(f), int(f.ndim == 3), scatter_mode, int(accumulate), nat.ptr(out)))
+        return out
+
+    def physical_quadrature_points(self, weights, points, num_elements: int) -> np.ndarray:
+        q = self._quad_only(weights, points)
+        d = q.dim
+        out = np.zeros((max(num_elements, 1), len(self._keep[0]), d))
+        self._check(self._lib.fb200_physical_quadrature_points(self._h, C.byref(q), nat.ptr(out)))
+        return out[:num_elements]
+
     def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.zeros(max(self.nnz, 1))

@@ -245,6 +245,12 @@ void fb200_destroy(fb200_ctx* ctx) {
     dev_free(ctx->d_iface_nodes);
     dev_free(ctx->d_iface_offsets);
     dev_free(ctx->d_iface_packed);
+    dev_free(ctx->d_ms_tab);
+    dev_free(ctx->d_vector);
+    dev_free(ctx->d_source);
+    ctx->ms_tab_capacity = 0;
+    ctx->h_ms_tab.clear();
+    ctx->vector_len = ctx->vector_capacity = ctx->source_capacity = 0;
     dev_free(ctx->d_peer_nodes);
     dev_free(ctx->d_peer_offsets);
     dev_free(ctx->d_peer_send);

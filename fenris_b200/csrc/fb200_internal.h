@@ -24,6 +24,7 @@ bool element_info(int element_type, ElementInfo* out);
 
 // Host restatement of the reference-element gradient tables (see hostgen.cpp).
 void reference_gradients(int element_type, const double* xi, double* g /* [n*d], node-major */);
+void reference_basis(int element_type, const double* xi, double* phi /* [n] */);
 int geometry_type(int element_type);
 
 // Device-side error word: [63:8] smallest offending element index, [7:0] status code. atomicMin keeps the first element.
@@ -179,6 +180,15 @@ struct fb200_ctx {
     // ---- values
     double* d_values = nullptr;
     uint64_t values_capacity = 0;
+
+    // ---- mass / source vector path: tables w | rho | ggeo | phi_geo | phi, the global vector, source values
+    double* d_ms_tab = nullptr;
+    std::vector<double> h_ms_tab;
+    size_t ms_tab_capacity = 0;
+    double* d_vector = nullptr;
+    uint64_t vector_len = 0, vector_capacity = 0;
+    double* d_source = nullptr;
+    uint64_t source_capacity = 0;
 
     // ---- tables + deferred error word
     fb200::DeviceTables tab;

@@ -101,6 +101,35 @@ void reference_gradients(int t, const double* xi, double* g) {
     }
 }
 
+// phi(xi): Quad4 quadrilateral.rs:79-91, Tet4 tetrahedron.rs:551-558, Tet10 tetrahedron.rs:179-196, Hex8 hexahedron.rs:43-60,
+// Hex27 hexahedron.rs:223-268 (mass matrix / source vector / map_reference_coords)
+void reference_basis(int t, const double* xi, double* phi) {
+    switch (t) {
+        case FB200_QUAD4:
+            for (int k = 0; k < 4; ++k) phi[k] = lin(kQuad[k][0], xi[0]) * lin(kQuad[k][1], xi[1]);
+            break;
+        case FB200_TET4:
+        case FB200_TET10: {
+            const double psi[4] = {-0.5 * xi[0] - 0.5 * xi[1] - 0.5 * xi[2] - 0.5, 0.5 * xi[0] + 0.5, 0.5 * xi[1] + 0.5,
+                                   0.5 * xi[2] + 0.5};
+            if (t == FB200_TET4) {
+                for (int k = 0; k < 4; ++k) phi[k] = psi[k];
+            } else {
+                for (int k = 0; k < 4; ++k) phi[k] = psi[k] * (2.0 * psi[k] - 1.0);
+                for (int e = 0; e < 6; ++e) phi[4 + e] = 4.0 * psi[kTet10Edges[e][0]] * psi[kTet10Edges[e][1]];
+            }
+            break;
+        }
+        case FB200_HEX8:
+            for (int k = 0; k < 8; ++k) phi[k] = lin(kHex[k][0], xi[0]) * lin(kHex[k][1], xi[1]) * lin(kHex[k][2], xi[2]);
+            break;
+        case FB200_HEX27:
+            for (int k = 0; k < 27; ++k) phi[k] = quad(kHex[k][0], xi[0]) * quad(kHex[k][1], xi[1]) * quad(kHex[k][2], xi[2]);
+            break;
+        default: break;
+    }
+}
+
 namespace {
 // Hex8 basis values, hexahedron.rs:43-60 (used to place Hex27 face/centre nodes)
 void hex8_basis(const double* xi, double* N) {

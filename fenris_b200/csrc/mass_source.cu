@@ -1,0 +1,298 @@
+// SURVEY 8(f) rank 1 - the neighbours of the stiffness path that complete "assemble a linear system" (examples/poisson2d.rs:33-86):
+//   element mass matrix        assemble_element_mass_matrix   src/assembly/local/mass.rs:218-286  (through the CSR scatter)
+//   element source vector      assemble_element_source_vector src/assembly/local/source.rs:217-278
+//   global vector assembly     VectorAssembler / VectorParAssembler::assemble_vector_into, add_local_to_global
+//                              src/assembly/global.rs:569-686, 779-796
+//   physical quadrature points FiniteElement::map_reference_coords (what SourceFunction::evaluate receives, source.rs:253-255)
+// Same skeleton as the stiffness kernels (assemble.cu): tables of the uniform quadrature rule staged in shared memory, one warp
+// per element, geometry per quadrature point per lane, scatter through the node-block map (matrix) or by node id (vector) with
+// f64 reductions (ATOMIC) or plain read-modify-write inside a colour (COLORED = CsrParAssembler / VectorParAssembler semantics).
+// These kernels are not tuned like the Hex8 tile kernel; they are HBM/atomic bound at a few percent of the stiffness cost.
+#include <algorithm>
+#include <cstring>
+
+#include "fb200_internal.h"
+
+namespace fb200 {
+
+struct MsParams {
+    const double* vertices;
+    const int32_t* conn;
+    const int64_t* blk_off;
+    const uint16_t* blockmap;
+    const int32_t* elem_list;  // colour list or nullptr
+    uint64_t count;
+    const double* tab;         // w[nq] | rho[nq] | ggeo[nq*ng*d] | phigeo[nq*ng] | phi[nq*n]
+    int nq, n, ng, d, s;
+    int plain;                 // COLORED: plain read-modify-write
+    double* values;            // CSR values (mass)
+    double* vector;            // global vector (source)
+    const double* source;      // [count_all or 1][nq][s]
+    int source_per_element;
+    double* points_out;        // physical points [E][nq][d]
+};
+
+__device__ __forceinline__ double det_small_dev(const double* J, int d) {
+    if (d == 2) return J[0] * J[3] - J[2] * J[1];
+    // first-row cofactor expansion, as nalgebra's determinant()
+    const double c00 = J[4] * J[8] - J[7] * J[5], c01 = J[3] * J[8] - J[6] * J[5], c02 = J[3] * J[7] - J[6] * J[4];
+    return J[0] * c00 - J[1] * c01 + J[2] * c02;
+}
+
+template <int WHAT>  // 0 mass matrix, 1 source vector, 2 physical points
+__global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
+    extern __shared__ double sm[];
+    const int nq = p.nq, n = p.n, ng = p.ng, d = p.d, s = p.s;
+    const int tab_len = nq * (2 + ng * d + ng + n);
+    for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sm[i] = p.tab[i];
+    const double* t_w = sm;
+    const double* t_rho = t_w + nq;
+    const double* t_ggeo = t_rho + nq;
+    const double* t_pgeo = t_ggeo + nq * ng * d;
+    const double* t_phi = t_pgeo + nq * ng;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int warp_doubles = ng * d + nq + 2 * n + (n & 1);  // X | scale | base (int64) | ids + row lengths (int32)
+    double* w_X = sm + ((tab_len + 1) & ~1) + warp * warp_doubles;
+    double* w_scale = w_X + ng * d;
+    long long* w_base = reinterpret_cast<long long*>(w_scale + nq);
+    int* w_ids = reinterpret_cast<int*>(w_base + n);
+    int* w_len = w_ids + n;
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * warps + warp; k < p.count; k += (uint64_t)gridDim.x * warps) {
+        const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[k] : k;
+        for (int a = lane; a < n; a += 32) {
+            const int id = p.conn[e * n + a];
+            w_ids[a] = id;
+            if (WHAT == 0) {
+                const long long o0 = p.blk_off[id], o1 = p.blk_off[id + 1];
+                w_base[a] = (long long)(s * s) * o0;
+                w_len[a] = (int)(o1 - o0) * s;
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < ng * d; t += 32) w_X[t] = p.vertices[(uint64_t)w_ids[t / d] * d + (t % d)];
+        __syncwarp();
+        if constexpr (WHAT == 2) {
+            for (int t = lane; t < nq * d; t += 32) {
+                const int q = t / d, c = t - q * d;
+                double x = 0.0;
+                for (int a = 0; a < ng; ++a) x = fma(t_pgeo[q * ng + a], w_X[a * d + c], x);
+                p.points_out[(e * nq + q) * d + c] = x;
+            }
+        }
+        for (int q = lane; WHAT != 2 && q < nq; q += 32) {  // scale_q = w |det J_q| rho_q  (mass.rs:262-267, source.rs:254-267)
+            double J[9];
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    double acc = 0.0;
+                    for (int a = 0; a < ng; ++a) acc = fma(w_X[a * d + i], t_ggeo[(q * ng + a) * d + j], acc);
+                    J[i * d + j] = acc;
+                }
+            w_scale[q] = t_w[q] * fabs(det_small_dev(J, d)) * (WHAT == 0 ? t_rho[q] : 1.0);
+        }
+        __syncwarp();
+        if constexpr (WHAT == 0) {
+            // M_IJ = I_s sum_q scale_q phi_I phi_J; both triangles with the factors in (min, max) order: bitwise the
+            // reference's upper-triangle-then-mirror result (mass.rs:270-283)
+            for (int t = lane; t < n * n; t += 32) {
+                const int a = t / n, b = t - a * n;
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                double m = 0.0;
+                for (int q = 0; q < nq; ++q) m += w_scale[q] * t_phi[q * n + lo] * t_phi[q * n + hi];
+                const int kk = p.blockmap[e * (uint64_t)(n * n) + t];
+                double* row = p.values + (w_base[a] + (long long)(s * kk));
+                for (int i = 0; i < s; ++i) {
+                    double* dst = row + (long long)i * w_len[a] + i;
+                    if (p.plain) *dst += m;
+                    else atomicAdd(dst, m);
+                }
+            }
+        } else if constexpr (WHAT == 1) {
+            // f_I = sum_q scale_q phi_I f(x_q)  (source.rs:268-276), added at s I + i (add_local_to_global, global.rs:779-796)
+            const double* F = p.source + (p.source_per_element ? e * (uint64_t)(nq * s) : 0);
+            for (int t = lane; t < n * s; t += 32) {
+                const int a = t / s, i = t - a * s;
+                double f = 0.0;
+                for (int q = 0; q < nq; ++q) f += (w_scale[q] * F[q * s + i]) * t_phi[q * n + a];
+                double* dst = p.vector + (uint64_t)w_ids[a] * s + i;
+                if (p.plain) *dst += f;
+                else atomicAdd(dst, f);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static fb200_status ms_validate(fb200_ctx* ctx, const fb200_quadrature* q) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!q) return fail(ctx, FB200_ERR_SHAPE, "null quadrature");
+    if (!ctx->has_space) return fail(ctx, FB200_ERR_STATE, "needs fb200_space_upload (a finite element space)");
+    if (q->dim != ctx->ei.d) return fail(ctx, FB200_ERR_SHAPE, "quadrature dimension != element reference dimension");
+    if (q->num_points < 1 || q->num_points > 64) return fail(ctx, FB200_ERR_UNSUPPORTED, "1..64 quadrature points supported");
+    if (!q->weights || !q->points) return fail(ctx, FB200_ERR_SHAPE, "null quadrature arrays");
+    return FB200_OK;
+}
+
+static fb200_status ms_tables(fb200_ctx* ctx, const fb200_quadrature* q, bool with_density) {
+    const int nq = q->num_points, n = ctx->ei.n, ng = ctx->ei.ng, d = ctx->ei.d;
+    std::vector<double> h((size_t)nq * (2 + ng * d + ng + n), 0.0);
+    double* w = h.data();
+    double* rho = w + nq;
+    double* ggeo = rho + nq;
+    double* pgeo = ggeo + (size_t)nq * ng * d;
+    double* phi = pgeo + (size_t)nq * ng;
+    for (int k = 0; k < nq; ++k) {
+        w[k] = q->weights[k];
+        rho[k] = with_density ? q->data[k] : 1.0;
+        reference_gradients(geometry_type(ctx->elem_type), q->points + (size_t)k * d, ggeo + (size_t)k * ng * d);
+        reference_basis(geometry_type(ctx->elem_type), q->points + (size_t)k * d, pgeo + (size_t)k * ng);
+        reference_basis(ctx->elem_type, q->points + (size_t)k * d, phi + (size_t)k * n);
+    }
+    if (ctx->d_ms_tab && ctx->h_ms_tab == h) return FB200_OK;
+    if (ctx->ms_tab_capacity < h.size()) {
+        dev_free(ctx->d_ms_tab);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_ms_tab, h.size()));
+        ctx->ms_tab_capacity = h.size();
+    }
+    FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_ms_tab, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is pageable
+    ctx->h_ms_tab = h;
+    return FB200_OK;
+}
+
+template <int WHAT>
+static fb200_status ms_launch(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
+    p.vertices = ctx->d_vertices;
+    p.conn = ctx->d_conn;
+    p.blk_off = ctx->d_blk_off;
+    p.blockmap = ctx->d_blockmap;
+    p.tab = ctx->d_ms_tab;
+    p.n = ctx->ei.n;
+    p.ng = ctx->ei.ng;
+    p.d = ctx->ei.d;
+    const int tab_len = p.nq * (2 + p.ng * p.d + p.ng + p.n);
+    const int warp_doubles = p.ng * p.d + p.nq + 2 * p.n + (p.n & 1);
+    const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + 4 * warp_doubles);
+    auto kernel = mass_source_kernel<WHAT>;
+    if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto run = [&](const int32_t* list, uint64_t count) -> fb200_status {
+        if (count == 0) return FB200_OK;
+        p.elem_list = list;
+        p.count = count;
+        const int blocks = (int)std::min<uint64_t>(div_up(count, 4), (uint64_t)ctx->sm_count * 8);
+        kernel<<<blocks, 128, smem, ctx->stream>>>(p);
+        return check_launch(ctx, "mass_source_kernel");
+    };
+    if (WHAT != 2 && scatter_mode == FB200_SCATTER_COLORED) {
+        if (!ctx->has_colors) return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
+        p.plain = 1;
+        for (size_t c = 0; c + 1 < ctx->h_color_off.size(); ++c)
+            FB200_TRY(run(ctx->d_color_elems + ctx->h_color_off[c], ctx->h_color_off[c + 1] - ctx->h_color_off[c]));
+        return FB200_OK;
+    }
+    if (WHAT != 2 && scatter_mode != FB200_SCATTER_ATOMIC)
+        return fail(ctx, FB200_ERR_UNSUPPORTED, "mass matrix / vector assembly support the ATOMIC and COLORED scatter");
+    p.plain = 0;
+    return run(nullptr, WHAT == 2 ? ctx->E : ctx->E_owned);
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" {
+
+fb200_status fb200_assemble_mass_into_csr_device(fb200_ctx* ctx, const fb200_quadrature* q, int32_t scatter_mode, int32_t accumulate) {
+    FB200_TRY(ms_validate(ctx, q));
+    if (!q->data) return fail(ctx, FB200_ERR_SHAPE, "the mass matrix needs a density per quadrature point (Density, mass.rs:23-31)");
+    if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
+    if (ctx->ragged || !ctx->d_blockmap) return fail(ctx, FB200_ERR_UNSUPPORTED, "mass assembly needs a uniform-element space");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB200_TRY(ms_tables(ctx, q, true));
+    if (!accumulate) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = ctx->sdim;
+    p.values = ctx->d_values;
+    return ms_launch<0>(ctx, p, scatter_mode);
+}
+
+fb200_status fb200_assemble_mass_into_csr(fb200_ctx* ctx, const fb200_quadrature* q, int32_t scatter_mode, int32_t accumulate, double* values) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!values) return fail(ctx, FB200_ERR_SHAPE, "null values");
+    if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (accumulate && ctx->nnz)
+        FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_values, values, ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB200_TRY(fb200_assemble_mass_into_csr_device(ctx, q, scatter_mode, accumulate));
+    if (ctx->nnz) FB200_CUDA(ctx, cudaMemcpyAsync(values, ctx->d_values, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return read_errword(ctx);
+}
+
+fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* q, int32_t solution_dim, const double* source_values,
+                                   int32_t per_element, int32_t scatter_mode, int32_t accumulate, double* out) {
+    FB200_TRY(ms_validate(ctx, q));
+    if (solution_dim < 1 || solution_dim > 3) return fail(ctx, FB200_ERR_SHAPE, "solution_dim must be 1..3");
+    if (!source_values || !out) return fail(ctx, FB200_ERR_SHAPE, "null source values / output");
+    if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "vector assembly needs a uniform-element space");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB200_TRY(ms_tables(ctx, q, false));
+    const uint64_t len = (uint64_t)solution_dim * ctx->N;
+    const uint64_t src_len = (uint64_t)q->num_points * solution_dim * (per_element ? ctx->E : 1);
+    if (ctx->vector_capacity < len) {
+        dev_free(ctx->d_vector);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_vector, len));
+        ctx->vector_capacity = len;
+    }
+    if (ctx->source_capacity < src_len) {
+        dev_free(ctx->d_source);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_source, src_len));
+        ctx->source_capacity = src_len;
+    }
+    ctx->vector_len = len;
+    if (accumulate) {
+        if (len) FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_vector, out, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (len) {
+        FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_vector, 0, len * sizeof(double), ctx->stream));
+    }
+    if (src_len) FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_source, source_values, src_len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = solution_dim;
+    p.vector = ctx->d_vector;
+    p.source = ctx->d_source;
+    p.source_per_element = per_element ? 1 : 0;
+    FB200_TRY(ms_launch<1>(ctx, p, scatter_mode));
+    if (len) FB200_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_vector, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return read_errword(ctx);
+}
+
+fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* q, double* out) {
+    FB200_TRY(ms_validate(ctx, q));
+    if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");
+    if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB200_TRY(ms_tables(ctx, q, false));
+    const uint64_t len = ctx->E * (uint64_t)q->num_points * ctx->ei.d;
+    if (len == 0) return FB200_OK;
+    double* d_out = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_out, len));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = 1;
+    p.points_out = d_out;
+    fb200_status st = ms_launch<2>(ctx, p, FB200_SCATTER_ATOMIC);
+    if (st == FB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "D2H physical points");
+    }
+    if (st == FB200_OK) st = read_errword(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    return st;
+}
+
+}  // extern "C"

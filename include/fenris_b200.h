@@ -157,6 +157,24 @@ fb200_status fb200_values_upload(fb200_ctx* ctx, const double* values);
 fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature,
                                     uint64_t first, uint64_t count, double* out);
 
+/* ---- mass matrix, source vector, global vector assembly (the rest of "assemble a linear system", examples/poisson2d.rs:33-86) --- */
+/* ElementMassAssembler through CsrAssembler / CsrParAssembler (src/assembly/local/mass.rs:127-159, 218-286): M_IJ = I_s * sum_q w_q |det J_q|
+ * rho_q phi_I phi_J into the CSR values of the current pattern (s = the pattern's solution_dim).  quadrature->data = density per point
+ * (Density, mass.rs:23-31; [num_points]).  scatter_mode: ATOMIC or COLORED.  accumulate as in fb200_assemble_into_csr. */
+fb200_status fb200_assemble_mass_into_csr_device(fb200_ctx* ctx, const fb200_quadrature* quadrature, int32_t scatter_mode, int32_t accumulate);
+fb200_status fb200_assemble_mass_into_csr(fb200_ctx* ctx, const fb200_quadrature* quadrature, int32_t scatter_mode, int32_t accumulate, double* values);
+/* VectorAssembler / VectorParAssembler::assemble_vector_into with an ElementSourceAssembler (global.rs:569-686, source.rs:217-278):
+ * out[s I + i] (+)= sum over elements and points of w_q |det J_q| phi_I(xi_q) f_i(x_q).  The source function is a caller-side closure in the
+ * reference (SourceFunction::evaluate); here the caller passes its VALUES at the quadrature points: source_values[q * s + i] shared by all
+ * elements (per_element = 0, e.g. gravity) or source_values[(e * num_points + q) * s + i] (per_element = 1; physical points from
+ * fb200_physical_quadrature_points).  out: solution_dim * num_nodes doubles on the host; accumulate != 0 adds to its contents.
+ * quadrature->data is not used.  scatter_mode: ATOMIC or COLORED. */
+fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* quadrature, int32_t solution_dim, const double* source_values,
+                                   int32_t per_element, int32_t scatter_mode, int32_t accumulate, double* out);
+/* x_q = element.map_reference_coords(xi_q) for every element and point (FiniteElement::map_reference_coords; sub-parametric elements map
+ * through their embedded linear element, hexahedron.rs:328-330): out[(e * num_points + q) * d + c]. */
+fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* quadrature, double* out);
+
 /* ---- multi-GPU: element partition + interface-row exchange --------------------------------- */
 #define FB200_UNIQUE_ID_BYTES 128
 fb200_status fb200_comm_unique_id(char id[FB200_UNIQUE_ID_BYTES]);

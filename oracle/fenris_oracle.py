@@ -841,3 +841,152 @@ def jitter_vertices(vertices: np.ndarray, h: float, seed: int = 12345, amp: floa
     """Robustness input of SURVEY 8d: every vertex moved by U(-amp h, amp h) (PCG64)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     return vertices + rng.uniform(-amp * h, amp * h, size=vertices.shape)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rank 1: element mass matrix, source vector and the global vector assembler (test infrastructure, like the rest)
+# ------------------------------------------------------------------------------------------------------------------------
+def basis_values(elem_type: int, xi: Sequence[float]) -> np.ndarray:
+    """Reference basis phi(xi), shape (n,).  Quad4 quadrilateral.rs:79-91, Tet4 tetrahedron.rs:551-558,
+    Tet10 tetrahedron.rs:179-196, Hex8 hexahedron.rs:43-60, Hex27 hexahedron.rs:223-268."""
+    if elem_type == QUAD4:
+        return np.array([_phi_lin(a, xi[0]) * _phi_lin(b, xi[1]) for a, b in _QUAD4_NODES])
+    if elem_type == TET4:
+        return tet4_basis(xi)
+    if elem_type == TET10:
+        psi = tet4_basis(xi)
+        return np.array([psi[i] * (2.0 * psi[i] - 1.0) for i in range(4)] + [4.0 * psi[i] * psi[j] for i, j in _TET10_EDGES])
+    if elem_type == HEX8:
+        return hex8_basis(xi)
+    if elem_type == HEX27:
+        return np.array([_phi_quad(a, xi[0]) * _phi_quad(b, xi[1]) * _phi_quad(c, xi[2]) for a, b, c in _HEX27_NODES])
+    raise NotImplementedError(elem_type)
+
+
+def geometry_basis_values(elem_type: int, xi: Sequence[float]) -> np.ndarray:
+    """Basis of the GEOMETRY map: Hex27 -> embedded Hex8 (hexahedron.rs:318-335), Tet10 -> Tet4 (tetrahedron.rs:226-246)."""
+    if elem_type in (HEX27, HEX20):
+        return basis_values(HEX8, xi)
+    if elem_type == TET10:
+        return basis_values(TET4, xi)
+    return basis_values(elem_type, xi)
+
+
+def map_reference_coords(elem_type: int, X: np.ndarray, xi: Sequence[float]) -> np.ndarray:
+    """x(xi) = sum_a phi_a^geo(xi) X_a (FiniteElement::map_reference_coords, e.g. quadrilateral.rs:117-122); X: (n, d) rows."""
+    _, ng, _ = element_info(elem_type)
+    return geometry_basis_values(elem_type, xi) @ np.asarray(X)[:ng]
+
+
+def element_mass_matrix(elem_type: int, X: np.ndarray, weights, points, density, s: int) -> np.ndarray:
+    """assemble_element_mass_matrix, src/assembly/local/mass.rs:218-286 (literal): per point scale = w |det J| rho, upper
+    triangle of blocks m_IJ I_s with m_IJ += scale * phi_I * phi_J, then clone_upper_to_lower (util.rs:38-50)."""
+    n, _, _ = element_info(elem_type)
+    M = np.zeros((s * n, s * n))
+    for w, xi, rho in zip(weights, points, density):
+        j_det = det_small(reference_jacobian(elem_type, np.asarray(X).T, xi))  # X: (n, d) rows
+        phi = basis_values(elem_type, xi)
+        scale = w * abs(j_det) * rho
+        for I in range(n):
+            for J in range(I, n):
+                m = scale * phi[I] * phi[J]
+                for i in range(s):
+                    M[s * I + i, s * J + i] += m
+    iu = np.triu_indices(s * n, 1)
+    M[(iu[1], iu[0])] = M[iu]
+    return M
+
+
+def element_source_vector(elem_type: int, X: np.ndarray, weights, points, fvals: np.ndarray) -> np.ndarray:
+    """assemble_element_source_vector, src/assembly/local/source.rs:217-278: output (s x n, column = node) += w |det J| f phi^T;
+    fvals[q] = source.evaluate(x_q, data_q) (shape (q, s)).  Returned as the length s*n vector (node-major)."""
+    n, _, _ = element_info(elem_type)
+    fvals = np.asarray(fvals, dtype=np.float64)
+    s = fvals.shape[1]
+    out = np.zeros((s, n))
+    for w, xi, f in zip(weights, points, fvals):
+        phi = basis_values(elem_type, xi)
+        j = reference_jacobian(elem_type, np.asarray(X).T, xi)  # X: (n, d) rows
+        out += (w * abs(det_small(j))) * np.outer(f, phi)
+    return out.T.reshape(-1)
+
+
+def assemble_mass_serial(elem_type: int, vertices, connectivity, weights, points, density, s: int):
+    """CsrAssembler::assemble with an ElementMassAssembler (global.rs:124-182, mass.rs:127-159): (row_offsets, col_indices, values)."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    ro, ci = assemble_pattern(s, len(vertices), conn.tolist())
+    values = np.zeros(len(ci))
+    for e in range(len(conn)):
+        M = element_mass_matrix(elem_type, np.asarray(vertices)[conn[e]], weights, points, density, s)
+        scatter_element(values, ro, ci, s, conn[e].tolist(), M)
+    return ro, ci, values
+
+
+def assemble_mass_fast(elem_type: int, vertices, connectivity, weights, points, density, s: int):
+    """Vectorised variant of assemble_mass_serial (same sums up to fp reassociation); cross-checked against it in the tests."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    E, n = conn.shape
+    X = V[conn]
+    m = np.zeros((E, n, n))
+    for w, xi, rho in zip(weights, points, density):
+        G = geometry_gradients(elem_type, xi)
+        ng = G.shape[1]
+        J = np.einsum("eai,ja->eij", X[:, :ng], G)
+        phi = basis_values(elem_type, xi)
+        m += (w * rho * np.abs(np.linalg.det(J)))[:, None, None] * np.outer(phi, phi)[None]
+    ro, ci = assemble_pattern_fast(s, len(V), conn)
+    rows = (s * conn[:, :, None, None] + np.arange(s)[None, None, None, :]) + 0 * conn[:, None, :, None]
+    cols = (s * conn[:, None, :, None] + np.arange(s)[None, None, None, :]) + 0 * conn[:, :, None, None]
+    vals = np.broadcast_to(m[:, :, :, None], rows.shape)
+    # place the entries on the pattern: (row, col) keys are strictly increasing along the CSR arrays
+    ncols = s * len(V)
+    row_of = np.repeat(np.arange(len(ro) - 1, dtype=np.int64), np.diff(ro.astype(np.int64)))
+    keys = row_of * ncols + ci.astype(np.int64)
+    idx = np.searchsorted(keys, rows.ravel().astype(np.int64) * ncols + cols.ravel().astype(np.int64))
+    assert np.array_equal(keys[idx], rows.ravel() * ncols + cols.ravel())
+    values = np.zeros(len(ci))
+    np.add.at(values, idx, vals.ravel())
+    return ro, ci, values
+
+
+def physical_quadrature_points(elem_type: int, vertices, connectivity, points) -> np.ndarray:
+    """x_q of every element (E, q, d): what an ElementSourceAssembler hands to SourceFunction::evaluate (source.rs:253-255)."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    _, ng, _ = element_info(elem_type)
+    X = np.asarray(vertices, dtype=np.float64)[conn[:, :ng]]
+    N = np.stack([geometry_basis_values(elem_type, xi) for xi in points])  # q, ng
+    return np.einsum("qa,ead->eqd", N, X)
+
+
+def assemble_vector_serial(elem_type: int, vertices, connectivity, weights, points, fvals: np.ndarray) -> np.ndarray:
+    """VectorAssembler::assemble_vector (global.rs:569-617) with an ElementSourceAssembler: fvals (E, q, s) or (q, s) (uniform);
+    add_local_to_global (global.rs:779-796): global[s I + i] += local[s a + i]."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    fvals = np.asarray(fvals, dtype=np.float64)
+    s = fvals.shape[-1]
+    out = np.zeros(s * len(vertices))
+    for e in range(len(conn)):
+        fe = fvals[e] if fvals.ndim == 3 else fvals
+        local = element_source_vector(elem_type, np.asarray(vertices)[conn[e]], weights, points, fe)
+        for a, I in enumerate(conn[e]):
+            out[s * I:s * I + s] += local[s * a:s * a + s]
+    return out
+
+
+def assemble_vector_fast(elem_type: int, vertices, connectivity, weights, points, fvals: np.ndarray) -> np.ndarray:
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    fvals = np.asarray(fvals, dtype=np.float64)
+    s = fvals.shape[-1]
+    E, n = conn.shape
+    X = V[conn]
+    out = np.zeros((len(V), s))
+    for q, (w, xi) in enumerate(zip(weights, points)):
+        G = geometry_gradients(elem_type, xi)
+        J = np.einsum("eai,ja->eij", X[:, :G.shape[1]], G)
+        scale = w * np.abs(np.linalg.det(J))  # E
+        f = fvals[:, q] if fvals.ndim == 3 else np.broadcast_to(fvals[q], (E, s))
+        phi = basis_values(elem_type, xi)
+        np.add.at(out, conn, scale[:, None, None] * phi[None, :, None] * f[:, None, :])
+    return out.reshape(-1)

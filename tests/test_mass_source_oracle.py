@@ -1,0 +1,79 @@
+"""The numpy oracle of the mass matrix / source vector path (oracle/fenris_oracle.py) pinned against the
+reference's own tests: the analytic Quad4 mass matrix (tests/unit_tests/assembly/local.rs:38-69), the quadratic-form identity
+of tests/unit_tests/assembly/local/mass.rs:15-118 and the inner-product identity of local/source.rs:19-160 (restated for the
+elements of this scope), plus literal-vs-vectorised cross checks.  No GPU."""
+import numpy as np
+import pytest
+
+from oracle import fenris_oracle as fo
+
+
+def test_quad4_reference_element_mass_matrix_kat():
+    X = np.array(fo._QUAD4_NODES)
+    w, p = fo.quadrilateral_gauss(3)  # the reference uses total_order::quadrilateral(5): any rule exact for degree 4 per direction
+    M = fo.element_mass_matrix(fo.QUAD4, X, w, p, [3.0] * len(w), 2)
+    expected = np.kron(3.0 / 9.0 * np.array([[4, 2, 1, 2], [2, 4, 2, 1], [1, 2, 4, 2], [2, 1, 2, 4.0]]), np.eye(2))
+    assert np.abs(M - expected).max() < 1e-14
+
+
+@pytest.mark.parametrize("et", [fo.QUAD4, fo.TET4, fo.TET10, fo.HEX8, fo.HEX27])
+def test_basis_is_a_nodal_partition_of_unity(et):
+    n, _, d = fo.element_info(et)
+    rng = np.random.default_rng(0)
+    for xi in rng.uniform(-0.9, -0.1, size=(5, d)):  # inside every reference domain
+        assert abs(fo.basis_values(et, xi).sum() - 1.0) < 1e-14
+    nodes = {fo.QUAD4: fo._QUAD4_NODES, fo.HEX8: fo._HEX8_NODES, fo.HEX27: fo._HEX27_NODES}.get(et)
+    if nodes is not None:  # phi_I(xi_J) = delta_IJ
+        assert np.abs(np.array([fo.basis_values(et, x) for x in nodes]) - np.eye(n)).max() < 1e-14
+
+
+def test_mass_quadratic_form_reproduces_weighted_l2_norm():
+    # mass.rs:15-118 restated for a trilinear hex: with f in the element's space, f_h^T M f_h = int rho f^2; both sides by the same
+    # (exact enough) Gauss rule, rho evaluated at the physical points
+    X = np.array(fo._HEX8_NODES) * [1.0, 0.7, 1.3] + [2.0, 0.0, 1.0]
+    w, p = fo.hexahedron_gauss(4)
+    f = lambda x: 3.0 * x[..., 0] - x[..., 1] * x[..., 2] + 2.0 * x[..., 0] * x[..., 1] * x[..., 2] + 5.0  # trilinear
+    rho = lambda x: (3.0 * x[..., 0] + 2.0 * x[..., 1] - 4.0 * x[..., 2] + 2.0) ** 2
+    xq = np.array([fo.map_reference_coords(fo.HEX8, X, xi) for xi in p])
+    M = fo.element_mass_matrix(fo.HEX8, X, w, p, rho(xq), 1)
+    fh = f(X)
+    detj = np.array([abs(fo.det_small(fo.reference_jacobian(fo.HEX8, X.T, xi))) for xi in p])
+    assert abs(fh @ M @ fh - np.sum(w * detj * rho(xq) * f(xq) ** 2)) < 1e-10 * abs(fh @ M @ fh)
+
+
+def test_source_vector_reproduces_inner_product():
+    # source.rs:19-160: for u in the element's space, int f . u = u_K . f_K  (s = 2, a density-like parameter per point)
+    a, b, c, d = np.array([2.0, 0, 1]), np.array([3.0, 4, 1]), np.array([1.0, 1, 2]), np.array([3.0, 1, 4])
+    X4 = np.stack([a, b, c, d])
+    X = np.concatenate([X4, [(X4[i] + X4[j]) / 2 for i, j in fo._TET10_EDGES]])  # Tet10 vertices (mesh_convert semantics)
+    u = lambda x: np.stack([3 * x[..., 0] ** 2 - 4 * x[..., 0] * x[..., 1] + 3 * x[..., 0] * x[..., 2] - x[..., 2] ** 2 + 5,
+                            3 * x[..., 0] + 3 * x[..., 1] * x[..., 2] - 2 * x[..., 1] + x[..., 2] * x[..., 1] - 3], axis=-1)
+    f = lambda x: np.stack([6 * x[..., 0] ** 2 - 4 * x[..., 0] * x[..., 2] + 3 - x[..., 2] ** 2 - x[..., 0] + x[..., 1] - 3,
+                            2 * x[..., 0] + 3 * x[..., 0] * (x[..., 1] - x[..., 2]) - x[..., 0] * x[..., 1] - 2 * x[..., 2] ** 2 + 5], axis=-1)
+    from tests.mms import duffy_tet_rule
+    w, p = duffy_tet_rule(5)
+    xq = np.array([fo.map_reference_coords(fo.TET10, X, xi) for xi in p])
+    dens = np.sum(xq ** 2, axis=1)  # the reference's artificial density |x|^2 (local.rs:72-78)
+    fK = fo.element_source_vector(fo.TET10, X, w, p, dens[:, None] * f(xq))
+    detj = abs(fo.det_small(fo.reference_jacobian(fo.TET10, X.T, p[0])))  # affine
+    lhs = np.sum(w * detj * dens * np.sum(f(xq) * u(xq), axis=1))
+    assert abs(lhs - u(X).reshape(-1) @ fK) < 1e-10 * abs(lhs)
+
+
+@pytest.mark.parametrize("et,mesh,s", [(fo.QUAD4, lambda: fo.create_unit_square_uniform_quad_mesh_2d(4), 2),
+                                      (fo.HEX8, lambda: fo.create_unit_box_uniform_hex_mesh_3d(2), 3),
+                                      (fo.TET4, lambda: fo.create_unit_box_uniform_tet_mesh_3d(1), 1)])
+def test_vectorised_variants_equal_the_literal_ones(et, mesh, s):
+    v, c = mesh()
+    v = fo.jitter_vertices(v, 0.25, amp=0.15)
+    w, p = fo.quadrilateral_gauss(3) if et == fo.QUAD4 else (fo.hexahedron_gauss(3) if et == fo.HEX8 else fo.tetrahedron_rule(2))
+    rho = np.linspace(1.0, 2.0, len(w))
+    a, b = fo.assemble_mass_serial(et, v, c, w, p, rho, s), fo.assemble_mass_fast(et, v, c, w, p, rho, s)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and fo.rel_frobenius(b[2], a[2]) < 1e-14
+    x = fo.physical_quadrature_points(et, v, c, p)
+    f = np.stack([x[..., 0] ** 2, 1.0 + x[..., -1]], axis=-1)
+    assert np.abs(fo.assemble_vector_serial(et, v, c, w, p, f) - fo.assemble_vector_fast(et, v, c, w, p, f)).max() < 1e-15
+    # mass of the whole mesh: sum of all entries = s * int rho-weighted volume; for rho = 1 on the (jittered) unit domain
+    one = fo.assemble_mass_fast(et, v, c, w, p, np.ones(len(w)), 1)[2].sum()
+    vol = fo.assemble_vector_fast(et, v, c, w, p, np.ones((len(w), 1))).sum()
+    assert abs(one - vol) < 1e-13
