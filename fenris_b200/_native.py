@@ -99,6 +99,7 @@ def lib():
         "fb200_assemble_mass_into_csr": (i32, [vp, C.POINTER(Quadrature), i32, i32, vp]),
         "fb200_assemble_vector": (i32, [vp, C.POINTER(Quadrature), i32, vp, i32, i32, i32, vp]),
         "fb200_physical_quadrature_points": (i32, [vp, C.POINTER(Quadrature), vp]),
+        "fb200_apply_homogeneous_dirichlet_bc_csr": (i32, [vp, u64, vp, pdbl]),
         "fb200_comm_unique_id": (i32, [C.c_char_p]),
         "fb200_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
         "fb200_interface_set": (i32, [vp, u64, vp, vp, u64]),

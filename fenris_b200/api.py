@@ -569,3 +569,33 @@ class CsrParAssembler(CsrAssembler):
     def assemble_into_csr(self, csr: CsrMatrix, colors: Sequence[DisjointSubsets], element_assembler):  # type: ignore[override]
         self._cols = list(colors)
         super().assemble_into_csr(csr, element_assembler)
+
+
+# ----------------------------------------------------------------------------- Dirichlet conditions (global.rs:379-495)
+def apply_homogeneous_dirichlet_bc_csr(matrix: CsrMatrix, nodes, solution_dim: int, assembler: Optional[CsrAssembler] = None) -> float:
+    """src/assembly/global.rs:379-451.  With `assembler` (the CsrAssembler that produced `matrix`) the values still resident on its
+    device context are modified in place there and copied back; otherwise the matrix is uploaded to a temporary context first."""
+    nodes = np.asarray(nodes, dtype=np.uint64)
+    if assembler is not None:
+        ctx, own = assembler.ctx, False
+    else:
+        ctx, own = Context(), True
+        nrows = matrix.nrows()
+        assert nrows % solution_dim == 0
+        ctx.connectivity_upload(nrows // solution_dim, [])
+        ctx.pattern_adopt(solution_dim, matrix.row_offsets, matrix.col_indices)
+    try:
+        ctx.values_upload(matrix.values)
+        scale = ctx.apply_homogeneous_dirichlet_bc_csr(nodes)
+        ctx.values_download(matrix.values)
+        return scale
+    finally:
+        if own:
+            ctx.close()
+
+
+def apply_homogeneous_dirichlet_bc_rhs(rhs: np.ndarray, nodes, solution_dim: int) -> None:
+    """src/assembly/global.rs:479-495 (host loop; the vector lives on the host)."""
+    for node in np.asarray(nodes, dtype=np.int64):
+        rhs[solution_dim * node:solution_dim * node + solution_dim] = 0.0
+

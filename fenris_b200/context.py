@@ -207,6 +207,16 @@ class Context:
         self._check(self._lib.fb200_physical_quadrature_points(self._h, C.byref(q), nat.ptr(out)))
         return out[:num_elements]
 
+    def apply_homogeneous_dirichlet_bc_csr(self, nodes) -> float:
+        """global.rs:379-451 on the device-resident values; returns the diagonal scale that was used."""
+        n = nat.as_u64(nodes)
+        cnt = len(n)
+        if cnt == 0:
+            n = np.zeros(1, dtype=np.uint64)
+        scale = C.c_double(0.0)
+        self._check(self._lib.fb200_apply_homogeneous_dirichlet_bc_csr(self._h, cnt, nat.ptr(n), C.byref(scale)))
+        return float(scale.value)
+
     def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.zeros(max(self.nnz, 1))

@@ -175,6 +175,11 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* quadr
  * through their embedded linear element, hexahedron.rs:328-330): out[(e * num_points + q) * d + c]. */
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* quadrature, double* out);
 
+/* apply_homogeneous_dirichlet_bc_csr (src/assembly/global.rs:379-451) on the device-resident CSR values: rows of the listed nodes' dofs get
+ * scale on the diagonal and 0 elsewhere, the rows coupled to them lose their entries in those columns; scale = |first non-zero diagonal
+ * entry| (1 if none), returned in *scale (may be NULL).  The right-hand side counterpart (global.rs:479-495) is a host loop over s*node+i. */
+fb200_status fb200_apply_homogeneous_dirichlet_bc_csr(fb200_ctx* ctx, uint64_t num_dirichlet_nodes, const uint64_t* nodes, double* scale);
+
 /* ---- multi-GPU: element partition + interface-row exchange --------------------------------- */
 #define FB200_UNIQUE_ID_BYTES 128
 fb200_status fb200_comm_unique_id(char id[FB200_UNIQUE_ID_BYTES]);

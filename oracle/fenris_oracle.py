@@ -990,3 +990,45 @@ def assemble_vector_fast(elem_type: int, vertices, connectivity, weights, points
         phi = basis_values(elem_type, xi)
         np.add.at(out, conn, scale[:, None, None] * phi[None, :, None] * f[:, None, :])
     return out.reshape(-1)
+
+
+def apply_homogeneous_dirichlet_bc_csr(row_offsets, col_indices, values, nodes, solution_dim: int) -> float:
+    """Literal restatement of apply_homogeneous_dirichlet_bc_csr (src/assembly/global.rs:379-451); modifies `values` in place and
+    returns the diagonal scale.  (The reference sizes its two flag vectors d * nrows, :410-411 - more than needed; nrows here.)"""
+    ro = np.asarray(row_offsets, dtype=np.int64)
+    ci = np.asarray(col_indices, dtype=np.int64)
+    d = solution_dim
+    nrows = len(ro) - 1
+    scale = 1.0
+    for i in range(nrows):  # triplet_iter is row-major: the first non-zero DIAGONAL entry (:388-397)
+        hit = False
+        for k in range(ro[i], ro[i + 1]):
+            if ci[k] == i and values[k] != 0.0:
+                scale, hit = abs(values[k]), True
+                break
+        if hit:
+            break
+    member = np.zeros(nrows, dtype=bool)
+    visit = np.zeros(nrows, dtype=bool)
+    for node in nodes:
+        for i in range(d):
+            r = d * int(node) + i
+            member[r] = True
+            for k in range(ro[r], ro[r + 1]):
+                if ci[k] == r:
+                    values[k] = scale
+                else:
+                    values[k] = 0.0
+                    visit[ci[k]] = True
+    for r in np.nonzero(visit)[0]:
+        if not member[r]:
+            for k in range(ro[r], ro[r + 1]):
+                if member[ci[k]]:
+                    values[k] = 0.0
+    return scale
+
+
+def apply_homogeneous_dirichlet_bc_rhs(rhs, nodes, solution_dim: int) -> None:
+    """src/assembly/global.rs:479-495."""
+    for node in nodes:
+        rhs[solution_dim * int(node):solution_dim * int(node) + solution_dim] = 0.0

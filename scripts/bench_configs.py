@@ -15,6 +15,38 @@ import fenris_b200 as fb  # noqa: E402
 MODES = {"atomic": 0, "colored": 1, "gather": 2}
 
 
+def measure_mass_or_vector(what, steps, peak):
+    from oracle import fenris_oracle as fo  # quadrature rule tables only (host side)
+    mesh = fb.create_unit_box_uniform_hex_mesh_3d(126)
+    E, N = mesh.num_elements(), mesh.num_nodes()
+    with fb.Context(0) as ctx:
+        ctx.space_upload(mesh.element_type, mesh.vertices(), mesh.connectivity())
+        if what == "mass":
+            w, p = fo.hexahedron_gauss(3)
+            nrows, nnz = ctx.assemble_pattern(3)
+            fn = lambda: ctx.assemble_mass_into_csr_device(w, p, 1000.0, accumulate=False)
+            b_algo = 4 * 8 * E + 8 * 3 * N + 4 * 64 * E + 16 * nnz
+            name = "Hex8 mass matrix (s = 3, Gauss 3^3) on the C3 mesh, device-resident CSR"
+        else:
+            w, p = fo.hexahedron_gauss(2)
+            nnz = 0
+            out = np.zeros(3 * N)
+            g = np.tile([0.0, -9.81, 0.0], (len(w), 1))
+            fn = lambda: ctx.assemble_vector(w, p, g, N, out=out)
+            b_algo = 4 * 8 * E + 8 * 3 * N + 16 * 3 * N
+            name = "Hex8 source vector (uniform body force, s = 3) on the C3 mesh, host output (D2H of 3 N doubles inside the step)"
+        for _ in range(3):
+            fn()
+        ctx.synchronize()
+        ctx.timer_begin()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_end() / steps
+        ctx.synchronize()
+        print(json.dumps({"config": name, "scatter": "atomic", "elements": E, "nnz": nnz, "ms_per_step": ms, "elements_per_s": E / (ms * 1e-3),
+                          "algorithmic_GBps": b_algo / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": b_algo / (ms * 1e-3) / 1e9 / peak}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c4,c5")
@@ -36,6 +68,9 @@ def main():
             mesh, op, data, sdim, name = fb.create_unit_box_uniform_tet_mesh_3d(80), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C5 share: Tet4 elasticity 80^3 cells (1/8 of 161^3)"
         elif cfg == "c3":
             mesh, op, data, sdim, name = fb.create_unit_box_uniform_hex_mesh_3d(126), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C3 Hex8 elasticity 126^3"
+        elif cfg in ("mass", "vector"):  # SURVEY 8f rank 1 on the C3 mesh: mass matrix (s = 3, Gauss 3^3) / source vector (Gauss 2^3)
+            measure_mass_or_vector(cfg, args.steps, peak)
+            continue
         else:
             continue
         w, p = fb.canonical_stiffness_quadrature(mesh.element_type)

@@ -160,3 +160,47 @@ def test_reference_api_mass_and_vector_assemblers():
     ref = fo.assemble_vector_fast(fo.QUAD4, m.vertices(), m.connectivity(), w, p, 2.0 * x[..., :1] ** 2)
     assert np.abs(b - ref).max() < 1e-13 and np.abs(b_par - ref).max() < 1e-13
     assert abs(b.sum() - 2.0 / 3.0) < 1e-12  # int 2 x^2 over the unit square
+
+
+@pytest.mark.parametrize("kind,n,s", [("quad4", 6, 1), ("hex8", 4, 3), ("tet4", 3, 3), ("hex27", 2, 1)])
+def test_dirichlet_bc_csr_equals_reference_semantics(ctx, kind, n, s):
+    # apply_homogeneous_dirichlet_bc_csr (global.rs:379-451) on the device-resident stiffness matrix vs the literal restatement
+    et, v, c = _mesh(kind, n, 0.0)
+    op = fo.LAPLACE if s == 1 else fo.LINEAR_ELASTIC
+    prob = fo.Problem(et, v, c.astype(np.int64), op, params=() if s == 1 else fo.lame_from_young_poisson(1e6, 0.2))
+    ctx.space_upload(et, v, c)
+    ctx.assemble_pattern(s)
+    ctx.assemble_into_csr_device(op, prob.weights, prob.points, None if s == 1 else fo.lame_from_young_poisson(1e6, 0.2))
+    ctx.synchronize()
+    ro, ci = ctx.pattern_download()
+    ref = ctx.values_download().copy()
+    boundary = np.nonzero(np.abs(v - 0.5).max(axis=1) > 0.4999)[0]  # the unit-domain boundary, as poisson_mms_common.rs:126-134
+    scale = ctx.apply_homogeneous_dirichlet_bc_csr(boundary)
+    oscale = fo.apply_homogeneous_dirichlet_bc_csr(ro, ci, ref, boundary, s)
+    assert scale == oscale
+    assert np.array_equal(ctx.values_download(), ref)  # only copies, zeros and one scale value: bit-exact
+    # no Dirichlet nodes: nothing changes
+    before = ctx.values_download().copy()
+    ctx.apply_homogeneous_dirichlet_bc_csr(np.zeros(0, dtype=np.uint64))
+    assert np.array_equal(ctx.values_download(), before)
+
+
+def test_poisson_system_end_to_end_on_the_reference_api():
+    # examples/poisson2d.rs:33-86: stiffness + source vector + homogeneous Dirichlet, then solve; u = sin(pi x) sin(pi y)
+    import scipy.sparse.linalg as spla
+    m = fb.create_unit_square_uniform_quad_mesh_2d(24)
+    w, p = fo.quadrilateral_gauss(2)
+    qt = fb.UniformQuadratureTable.from_points_and_weights(p, w)
+    stiffness = fb.ElementEllipticAssemblerBuilder().with_finite_element_space(m).with_operator(fb.LaplaceOperator()).with_quadrature_table(qt) \
+        .with_u(np.zeros(m.num_nodes())).build()
+    asm = fb.CsrAssembler()
+    A = asm.assemble(stiffness)
+    f = lambda x, _data: 2.0 * np.pi ** 2 * np.sin(np.pi * x[..., :1]) * np.sin(np.pi * x[..., 1:2])
+    b = fb.VectorAssembler().assemble_vector(fb.ElementSourceAssembler(m, qt, f, 1))
+    v = m.vertices()
+    boundary = np.nonzero(np.abs(v - 0.5).max(axis=1) > 0.4999)[0]
+    fb.apply_homogeneous_dirichlet_bc_csr(A, boundary, 1)
+    fb.apply_homogeneous_dirichlet_bc_rhs(b, boundary, 1)
+    u = spla.spsolve(A.to_scipy().tocsc(), b)
+    exact = np.sin(np.pi * v[:, 0]) * np.sin(np.pi * v[:, 1])
+    assert np.abs(u - exact).max() < 5e-3  # O(h^2) with h = 1/24

@@ -77,3 +77,18 @@ def test_vectorised_variants_equal_the_literal_ones(et, mesh, s):
     one = fo.assemble_mass_fast(et, v, c, w, p, np.ones(len(w)), 1)[2].sum()
     vol = fo.assemble_vector_fast(et, v, c, w, p, np.ones((len(w), 1))).sum()
     assert abs(one - vol) < 1e-13
+
+
+def test_dirichlet_oracle_small_known_answer():
+    # 1-D chain of 4 nodes, s = 1, tridiagonal [2 -1; -1 2 -1; ...]; Dirichlet at node 0: row 0 -> (scale, 0), entry (1, 0) -> 0
+    ro = np.array([0, 2, 5, 8, 10])
+    ci = np.array([0, 1, 0, 1, 2, 1, 2, 3, 2, 3])
+    vals = np.array([2.0, -1, -1, 2, -1, -1, 2, -1, -1, 2])
+    scale = fo.apply_homogeneous_dirichlet_bc_csr(ro, ci, vals, [0], 1)
+    assert scale == 2.0 and vals.tolist() == [2.0, 0, 0, 2, -1, -1, 2, -1, -1, 2]
+    # first diagonal entry zero -> the next non-zero one gives the scale (skip_while, global.rs:393)
+    vals = np.array([0.0, -1, -1, -3, -1, -1, 2, -1, -1, 2])
+    assert fo.apply_homogeneous_dirichlet_bc_csr(ro, ci, vals, [3], 1) == 3.0 and vals.tolist() == [0.0, -1, -1, -3, -1, -1, 2, 0, 0, 3.0]
+    rhs = np.arange(8.0)
+    fo.apply_homogeneous_dirichlet_bc_rhs(rhs, [1, 3], 2)
+    assert rhs.tolist() == [0, 1, 0, 0, 4, 5, 0, 0]
