@@ -32,17 +32,18 @@ struct MsParams {
     double* points_out;        // physical points [E][nq][d]
 };
 
-__device__ __forceinline__ double det_small_dev(const double* J, int d) {
-    if (d == 2) return J[0] * J[3] - J[2] * J[1];
+template <int d>
+__device__ __forceinline__ double det_small_dev(const double (&J)[d * d]) {
+    if constexpr (d == 2) return J[0] * J[3] - J[2] * J[1];
     // first-row cofactor expansion, as nalgebra's determinant()
     const double c00 = J[4] * J[8] - J[7] * J[5], c01 = J[3] * J[8] - J[6] * J[5], c02 = J[3] * J[7] - J[6] * J[4];
     return J[0] * c00 - J[1] * c01 + J[2] * c02;
 }
 
-template <int WHAT>  // 0 mass matrix, 1 source vector, 2 physical points
+template <int WHAT, int n, int ng, int d>  // WHAT: 0 mass matrix, 1 source vector, 2 physical points; element shape at compile time
 __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     extern __shared__ double sm[];
-    const int nq = p.nq, n = p.n, ng = p.ng, d = p.d, s = p.s;
+    const int nq = p.nq, s = p.s;
     const int tab_len = nq * (2 + ng * d + ng + n);
     for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sm[i] = p.tab[i];
     const double* t_w = sm;
@@ -81,14 +82,16 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
             }
         }
         for (int q = lane; WHAT != 2 && q < nq; q += 32) {  // scale_q = w |det J_q| rho_q  (mass.rs:262-267, source.rs:254-267)
-            double J[9];
-            for (int i = 0; i < d; ++i)
-                for (int j = 0; j < d; ++j) {
-                    double acc = 0.0;
-                    for (int a = 0; a < ng; ++a) acc = fma(w_X[a * d + i], t_ggeo[(q * ng + a) * d + j], acc);
-                    J[i * d + j] = acc;
-                }
-            w_scale[q] = t_w[q] * fabs(det_small_dev(J, d)) * (WHAT == 0 ? t_rho[q] : 1.0);
+            double J[d * d];
+#pragma unroll
+            for (int i = 0; i < d * d; ++i) J[i] = 0.0;
+#pragma unroll
+            for (int a = 0; a < ng; ++a)
+#pragma unroll
+                for (int i = 0; i < d; ++i)
+#pragma unroll
+                    for (int j = 0; j < d; ++j) J[i * d + j] = fma(w_X[a * d + i], t_ggeo[(q * ng + a) * d + j], J[i * d + j]);
+            w_scale[q] = t_w[q] * fabs(det_small_dev<d>(J)) * (WHAT == 0 ? t_rho[q] : 1.0);
         }
         __syncwarp();
         if constexpr (WHAT == 0) {
@@ -160,20 +163,20 @@ static fb200_status ms_tables(fb200_ctx* ctx, const fb200_quadrature* q, bool wi
     return FB200_OK;
 }
 
-template <int WHAT>
-static fb200_status ms_launch(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
+template <int WHAT, int N, int NG, int D>
+static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
     p.vertices = ctx->d_vertices;
     p.conn = ctx->d_conn;
     p.blk_off = ctx->d_blk_off;
     p.blockmap = ctx->d_blockmap;
     p.tab = ctx->d_ms_tab;
-    p.n = ctx->ei.n;
-    p.ng = ctx->ei.ng;
-    p.d = ctx->ei.d;
-    const int tab_len = p.nq * (2 + p.ng * p.d + p.ng + p.n);
-    const int warp_doubles = p.ng * p.d + p.nq + 2 * p.n + (p.n & 1);
+    p.n = N;
+    p.ng = NG;
+    p.d = D;
+    const int tab_len = p.nq * (2 + NG * D + NG + N);
+    const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1);
     const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + 4 * warp_doubles);
-    auto kernel = mass_source_kernel<WHAT>;
+    auto kernel = mass_source_kernel<WHAT, N, NG, D>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     auto run = [&](const int32_t* list, uint64_t count) -> fb200_status {
         if (count == 0) return FB200_OK;
@@ -193,7 +196,23 @@ static fb200_status ms_launch(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
     if (WHAT != 2 && scatter_mode != FB200_SCATTER_ATOMIC)
         return fail(ctx, FB200_ERR_UNSUPPORTED, "mass matrix / vector assembly support the ATOMIC and COLORED scatter");
     p.plain = 0;
-    return run(nullptr, WHAT == 2 ? ctx->E : ctx->E_owned);
+    if (WHAT == 2) return run(nullptr, ctx->E);
+    // visit the elements in the Morton order of the space (as the stiffness path): all contributions to a CSR row / vector
+    // entry arrive while its lines are still in L2
+    const bool ordered = ctx->d_order && ctx->order_count == ctx->E_owned;
+    return run(ordered ? ctx->d_order : nullptr, ctx->E_owned);
+}
+
+template <int WHAT>
+static fb200_status ms_launch(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
+    switch (ctx->elem_type) {
+        case FB200_QUAD4: return ms_launch_t<WHAT, 4, 4, 2>(ctx, p, scatter_mode);
+        case FB200_TET4: return ms_launch_t<WHAT, 4, 4, 3>(ctx, p, scatter_mode);
+        case FB200_HEX8: return ms_launch_t<WHAT, 8, 8, 3>(ctx, p, scatter_mode);
+        case FB200_HEX27: return ms_launch_t<WHAT, 27, 8, 3>(ctx, p, scatter_mode);
+        case FB200_TET10: return ms_launch_t<WHAT, 10, 4, 3>(ctx, p, scatter_mode);
+        default: return fail(ctx, FB200_ERR_UNSUPPORTED, "element type has no device specialisation (no CPU fallback)");
+    }
 }
 
 }  // namespace fb200
