@@ -3,7 +3,8 @@ CsrAssembler / CsrParAssembler hot path.  See DESIGN.md, INTEGRATION.md and incl
 
 The numerical path is libfenris_b200.so (hand-written CUDA); there is no CPU fallback.
 """
-from ._native import (ERR_COLORING, ERR_COLUMN_NOT_IN_PATTERN, ERR_CUDA, ERR_INDEX_OOB, ERR_NCCL, ERR_SHAPE,  # noqa: F401
+from ._native import (ERR_COLORING, ERR_COLUMN_NOT_IN_PATTERN, ERR_CUDA, ERR_INDEFINITE, ERR_INDEX_OOB, ERR_NCCL,  # noqa: F401
+                      ERR_NOT_CONVERGED, ERR_SHAPE,
                       ERR_SINGULAR_JACOBIAN, ERR_STATE, ERR_UNSUPPORTED, HEX8, HEX27, LAPLACE, LINEAR_ELASTIC, OK, QUAD4,
                       SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER, TET4, TET10, Fb200Error, SingularJacobianError)
 from .api import (CsrAssembler, CsrMatrix, CsrParAssembler, Density, DisjointSubsets, ElementConnectivityAssembler,  # noqa: F401

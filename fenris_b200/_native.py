@@ -23,6 +23,7 @@ SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
 OK = 0
 ERR_SINGULAR_JACOBIAN, ERR_SHAPE, ERR_INDEX_OOB, ERR_COLUMN_NOT_IN_PATTERN = 1, 2, 3, 4
 ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_COLORING = 5, 6, 7, 8, 9
+ERR_NOT_CONVERGED, ERR_INDEFINITE = 10, 11
 
 
 class Fb200Error(RuntimeError):
@@ -100,6 +101,8 @@ def lib():
         "fb200_assemble_vector": (i32, [vp, C.POINTER(Quadrature), i32, vp, i32, i32, i32, vp]),
         "fb200_physical_quadrature_points": (i32, [vp, C.POINTER(Quadrature), vp]),
         "fb200_apply_homogeneous_dirichlet_bc_csr": (i32, [vp, u64, vp, pdbl]),
+        "fb200_spmv": (i32, [vp, vp, vp]),
+        "fb200_cg_solve": (i32, [vp, vp, vp, dbl, u64, i32, pu64, pdbl]),
         "fb200_comm_unique_id": (i32, [C.c_char_p]),
         "fb200_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
         "fb200_interface_set": (i32, [vp, u64, vp, vp, u64]),

@@ -217,6 +217,22 @@ class Context:
         self._check(self._lib.fb200_apply_homogeneous_dirichlet_bc_csr(self._h, cnt, nat.ptr(n), C.byref(scale)))
         return float(scale.value)
 
+    def spmv(self, x: np.ndarray) -> np.ndarray:
+        """y = A x with the device-resident matrix."""
+        xv = nat.as_f64(x)
+        y = np.zeros_like(xv)
+        self._check(self._lib.fb200_spmv(self._h, nat.ptr(xv), nat.ptr(y)))
+        return y
+
+    def cg_solve(self, b: np.ndarray, x0: Optional[np.ndarray] = None, rel_tol: float = 1e-8, max_iter: int = 0, jacobi: bool = True):
+        """ConjugateGradient::solve_with_guess (fenris-sparse/src/cg.rs:364-480) on the device-resident matrix.
+        Returns (x, iterations, relative residual); raises Fb200Error(ERR_NOT_CONVERGED | ERR_INDEFINITE)."""
+        bv = nat.as_f64(b)
+        x = np.zeros_like(bv) if x0 is None else nat.as_f64(x0).copy()
+        it, res = C.c_uint64(0), C.c_double(0.0)
+        self._check(self._lib.fb200_cg_solve(self._h, nat.ptr(bv), nat.ptr(x), float(rel_tol), int(max_iter), int(jacobi), C.byref(it), C.byref(res)))
+        return x, int(it.value), float(res.value)
+
     def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.zeros(max(self.nnz, 1))

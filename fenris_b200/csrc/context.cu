@@ -194,6 +194,8 @@ const char* fb200_status_string(fb200_status s) {
         case FB200_ERR_NCCL: return "NCCL error";
         case FB200_ERR_STATE: return "invalid call order";
         case FB200_ERR_COLORING: return "colours are not disjoint";
+        case FB200_ERR_NOT_CONVERGED: return "maximum number of iterations reached";
+        case FB200_ERR_INDEFINITE: return "indefinite operator or preconditioner";
         default: return "unknown status";
     }
 }

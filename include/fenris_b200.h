@@ -42,7 +42,9 @@ enum {
     FB200_ERR_CUDA = 6,
     FB200_ERR_NCCL = 7,
     FB200_ERR_STATE = 8,               /* call order violated (e.g. assemble before a pattern exists) */
-    FB200_ERR_COLORING = 9             /* adopted colours are not disjoint (DisjointSubsets::try_from..., fenris-paradis/src/lib.rs:184-220) */
+    FB200_ERR_COLORING = 9,            /* adopted colours are not disjoint (DisjointSubsets::try_from..., fenris-paradis/src/lib.rs:184-220) */
+    FB200_ERR_NOT_CONVERGED = 10,      /* SolveErrorKind::MaxIterationsReached (fenris-sparse/src/cg.rs:278-286) */
+    FB200_ERR_INDEFINITE = 11          /* SolveErrorKind::IndefiniteOperator / IndefinitePreconditioner */
 };
 
 /* Element types = the reference's connectivity newtypes (src/connectivity.rs:182,523,607,667,912). */
@@ -179,6 +181,16 @@ fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadra
  * scale on the diagonal and 0 elsewhere, the rows coupled to them lose their entries in those columns; scale = |first non-zero diagonal
  * entry| (1 if none), returned in *scale (may be NULL).  The right-hand side counterpart (global.rs:479-495) is a host loop over s*node+i. */
 fb200_status fb200_apply_homogeneous_dirichlet_bc_csr(fb200_ctx* ctx, uint64_t num_dirichlet_nodes, const uint64_t* nodes, double* scale);
+
+/* ---- the consumer of the assembled matrix, on the device-resident CSR (no D2H of the matrix) ------------------------------- */
+/* y = A x (host vectors of solution_dim * num_nodes doubles). */
+fb200_status fb200_spmv(fb200_ctx* ctx, const double* x, double* y);
+/* ConjugateGradient::solve_with_guess (fenris-sparse/src/cg.rs:364-480) with RelativeResidualCriterion(rel_tol) (cg.rs:85-124):
+ * x holds the initial guess on entry and the solution on return; jacobi != 0 preconditions with the inverse diagonal, else identity;
+ * max_iter = 0: unbounded.  Returns FB200_OK, FB200_ERR_NOT_CONVERGED (x = last iterate) or FB200_ERR_INDEFINITE.
+ * *iterations = number of updates of x, *rel_residual = ||r|| / ||b|| (recursive residual) at exit. */
+fb200_status fb200_cg_solve(fb200_ctx* ctx, const double* b, double* x, double rel_tol, uint64_t max_iter, int32_t jacobi, uint64_t* iterations,
+                            double* rel_residual);
 
 /* ---- multi-GPU: element partition + interface-row exchange --------------------------------- */
 #define FB200_UNIQUE_ID_BYTES 128

@@ -1032,3 +1032,39 @@ def apply_homogeneous_dirichlet_bc_rhs(rhs, nodes, solution_dim: int) -> None:
     """src/assembly/global.rs:479-495."""
     for node in nodes:
         rhs[solution_dim * int(node):solution_dim * int(node) + solution_dim] = 0.0
+
+
+def conjugate_gradient(apply_a, b, x0=None, rel_tol: float = 1e-8, max_iter: int = 0, apply_p=None):
+    """Literal restatement of ConjugateGradient::solve_with_guess (fenris-sparse/src/cg.rs:364-480) with
+    RelativeResidualCriterion (cg.rs:85-124).  apply_a / apply_p: callables y = A x / z = P r (identity if None).
+    Returns (x, iterations, status) with status in {"ok", "max_iter", "indefinite_operator", "indefinite_preconditioner"}."""
+    b = np.asarray(b, dtype=np.float64)
+    x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=np.float64)
+    apply_p = apply_p or (lambda r: r.copy())
+    r = b - apply_a(x)
+    z = apply_p(r)
+    p = z.copy()
+    zTr = float(z @ r)
+    b_norm = float(np.linalg.norm(b))
+    if b_norm == 0.0:
+        return np.zeros_like(b), 0, "ok"
+    it = 0
+    while True:
+        if np.linalg.norm(r) <= rel_tol * b_norm:
+            return x, it, "ok"
+        if max_iter and it >= max_iter:
+            return x, it, "max_iter"
+        Ap = apply_a(p)
+        pAp = float(p @ Ap)
+        if pAp <= 0.0:
+            return x, it, "indefinite_operator"
+        if zTr <= 0.0:
+            return x, it, "indefinite_preconditioner"
+        alpha = zTr / pAp
+        x = x + alpha * p
+        r = r - alpha * Ap
+        it += 1
+        z = apply_p(r)
+        zTr_next = float(z @ r)
+        p = p * (zTr_next / zTr) + z
+        zTr = zTr_next

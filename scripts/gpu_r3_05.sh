@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/*.log
-timeout 600 python -m pytest tests/test_mass_source_gpu.py -m gpu -q --maxfail=6 > gpurun_out/pytest_ms.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_ms.log
+timeout 600 python -m pytest tests/test_mass_source_gpu.py tests/test_solve_gpu.py -m gpu -q --maxfail=6 > gpurun_out/pytest_ms.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_ms.log
 tail -n 40 gpurun_out/pytest_ms.log | cut -c1-220

@@ -92,3 +92,19 @@ def test_dirichlet_oracle_small_known_answer():
     rhs = np.arange(8.0)
     fo.apply_homogeneous_dirichlet_bc_rhs(rhs, [1, 3], 2)
     assert rhs.tolist() == [0, 1, 0, 0, 4, 5, 0, 0]
+
+
+def test_conjugate_gradient_restatement():
+    # the literal restatement of fenris-sparse/src/cg.rs:364-480 used as the checker of the device CG
+    import scipy.sparse as sp
+    n = 40
+    A = sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(n, n)).tocsr()
+    b = np.linspace(1.0, 2.0, n)
+    x, its, status = fo.conjugate_gradient(lambda q: A @ q, b, rel_tol=1e-12)
+    assert status == "ok" and its <= n and np.abs(A @ x - b).max() < 1e-10
+    d = A.diagonal()
+    xj, itsj, _ = fo.conjugate_gradient(lambda q: A @ q, b, rel_tol=1e-12, apply_p=lambda r: r / d)
+    assert np.abs(xj - x).max() < 1e-10
+    assert fo.conjugate_gradient(lambda q: A @ q, np.zeros(n), x0=np.ones(n))[1:] == (0, "ok")
+    assert fo.conjugate_gradient(lambda q: A @ q, b, rel_tol=1e-14, max_iter=2)[2] == "max_iter"
+    assert fo.conjugate_gradient(lambda q: -(A @ q), b)[2] == "indefinite_operator"
