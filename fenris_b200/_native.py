@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfenris_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fenris_b200.h")
 
 # element / operator / scatter ids (include/fenris_b200.h)
-QUAD4, TET4, HEX8, HEX27, TET10 = 1, 2, 3, 4, 5
+QUAD4, TET4, HEX8, HEX27, TET10, HEX20 = 1, 2, 3, 4, 5, 6
 LAPLACE, LINEAR_ELASTIC = 1, 2
 SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
 
@@ -112,6 +112,7 @@ def lib():
         "fb200_gen_tet_mesh": (i32, [u64, u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_gen_quad_mesh": (i32, [u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_hex27_from_hex8": (i32, [u64, vp, u64, vp, pu64, vp, vp]),
+        "fb200_hex20_from_hex8": (i32, [u64, vp, u64, vp, pu64, vp, vp]),
         "fb200_canonical_quadrature": (i32, [i32, pi32, vp, vp]),
         "fb200_lame_from_young_poisson": (None, [dbl, dbl, pdbl, pdbl]),
         "fb200_tile_lists_selftest": (i32, [u64, vp, u64, vp, u64, pu64, pi32]),

@@ -27,8 +27,8 @@ from . import _native as nat
 from ._native import Fb200Error, SingularJacobianError  # noqa: F401
 from .context import Context
 
-_NODES = {nat.QUAD4: 4, nat.TET4: 4, nat.HEX8: 8, nat.HEX27: 27, nat.TET10: 10}
-_DIM = {nat.QUAD4: 2, nat.TET4: 3, nat.HEX8: 3, nat.HEX27: 3, nat.TET10: 3}
+_NODES = {nat.QUAD4: 4, nat.TET4: 4, nat.HEX8: 8, nat.HEX27: 27, nat.TET10: 10, nat.HEX20: 20}
+_DIM = {nat.QUAD4: 2, nat.TET4: 3, nat.HEX8: 3, nat.HEX27: 3, nat.TET10: 3, nat.HEX20: 3}
 
 
 # ----------------------------------------------------------------------------- meshes
@@ -133,6 +133,23 @@ def hex27_mesh_from(hex8_mesh: Mesh) -> Mesh:
     if st != nat.OK:
         raise Fb200Error(st, "hex27 conversion failed")
     return Mesh(v27, c27, nat.HEX27)
+
+
+def hex20_mesh_from(hex8_mesh: Mesh) -> Mesh:
+    """Hex20Mesh::from(&hex8_mesh), src/mesh_convert.rs:168-217,481-488"""
+    assert hex8_mesh.element_type == nat.HEX8
+    L = nat.lib()
+    v, c = hex8_mesh.vertices_, hex8_mesh.connectivity_
+    n20 = C.c_uint64(0)
+    st = L.fb200_hex20_from_hex8(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n20), None, None)
+    if st != nat.OK:
+        raise Fb200Error(st, "hex20 conversion failed")
+    v20 = np.zeros((n20.value, 3))
+    c20 = np.zeros((len(c), 20), dtype=np.uint64)
+    st = L.fb200_hex20_from_hex8(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n20), nat.ptr(v20), nat.ptr(c20))
+    if st != nat.OK:
+        raise Fb200Error(st, "hex20 conversion failed")
+    return Mesh(v20, c20, nat.HEX20)
 
 
 # ----------------------------------------------------------------------------- quadrature tables / operators

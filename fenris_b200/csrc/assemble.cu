@@ -1023,6 +1023,7 @@ static fb200_status dispatch(fb200_ctx* ctx, AssembleParams& p, int op, int mode
         case FB200_HEX8: return dispatch_op<8, 8, 3>(ctx, p, op, mode);
         case FB200_HEX27: return dispatch_op<27, 8, 3>(ctx, p, op, mode);
         case FB200_TET10: return dispatch_op<10, 4, 3>(ctx, p, op, mode);
+        case FB200_HEX20: return dispatch_op<20, 8, 3>(ctx, p, op, mode);
         default: return fail(ctx, FB200_ERR_UNSUPPORTED, "element type has no device specialisation (no CPU fallback)");
     }
 }

@@ -21,12 +21,13 @@ bool element_info(int t, ElementInfo* out) {
         case FB200_HEX8: *out = {8, 8, 3}; return true;
         case FB200_HEX27: *out = {27, 8, 3}; return true;
         case FB200_TET10: *out = {10, 4, 3}; return true;
+        case FB200_HEX20: *out = {20, 8, 3}; return true;
         default: return false;
     }
 }
 
 int geometry_type(int t) {
-    if (t == FB200_HEX27) return FB200_HEX8;
+    if (t == FB200_HEX27 || t == FB200_HEX20) return FB200_HEX8;
     if (t == FB200_TET10) return FB200_TET4;
     return t;
 }
@@ -97,6 +98,28 @@ void reference_gradients(int t, const double* xi, double* g) {
                 g[3 * k + 2] = quad(a, xi[0]) * quad(b, xi[1]) * dquad(c, xi[2]);
             }
             break;
+        case FB200_HEX20:  // serendipity hexahedron, hexahedron.rs:467-545: corners phi = f g / 8, edges phi = h g / 4
+            for (int k = 0; k < 20; ++k) {
+                const double al = kHex[k][0], be = kHex[k][1], ga = kHex[k][2];
+                const double x0 = xi[0], x1 = xi[1], x2 = xi[2];
+                const double gg = (1.0 + al * x0) * (1.0 + be * x1) * (1.0 + ga * x2);
+                if (k < 8) {
+                    const double f = al * x0 + be * x1 + ga * x2 - 2.0, s = 1.0 / 8.0;
+                    g[3 * k + 0] = s * (al * gg + f * al * (1.0 + be * x1) * (1.0 + ga * x2));
+                    g[3 * k + 1] = s * (be * gg + f * be * (1.0 + al * x0) * (1.0 + ga * x2));
+                    g[3 * k + 2] = s * (ga * gg + f * ga * (1.0 + al * x0) * (1.0 + be * x1));
+                } else {
+                    const double a2 = al * al, b2 = be * be, c2 = ga * ga, s = 1.0 / 4.0;
+                    const double h = (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - b2) * x1 * x1) * (1.0 - (1.0 - c2) * x2 * x2);
+                    const double dh0 = -2.0 * (1.0 - a2) * x0 * (1.0 - (1.0 - b2) * x1 * x1) * (1.0 - (1.0 - c2) * x2 * x2);
+                    const double dh1 = -2.0 * (1.0 - b2) * x1 * (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - c2) * x2 * x2);
+                    const double dh2 = -2.0 * (1.0 - c2) * x2 * (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - b2) * x1 * x1);
+                    g[3 * k + 0] = s * (dh0 * gg + h * al * (1.0 + be * x1) * (1.0 + ga * x2));
+                    g[3 * k + 1] = s * (dh1 * gg + h * be * (1.0 + al * x0) * (1.0 + ga * x2));
+                    g[3 * k + 2] = s * (dh2 * gg + h * ga * (1.0 + al * x0) * (1.0 + be * x1));
+                }
+            }
+            break;
         default: break;
     }
 }
@@ -125,6 +148,17 @@ void reference_basis(int t, const double* xi, double* phi) {
             break;
         case FB200_HEX27:
             for (int k = 0; k < 27; ++k) phi[k] = quad(kHex[k][0], xi[0]) * quad(kHex[k][1], xi[1]) * quad(kHex[k][2], xi[2]);
+            break;
+        case FB200_HEX20:  // hexahedron.rs:414-465
+            for (int k = 0; k < 20; ++k) {
+                const double al = kHex[k][0], be = kHex[k][1], ga = kHex[k][2];
+                const double gg = (1.0 + al * xi[0]) * (1.0 + be * xi[1]) * (1.0 + ga * xi[2]);
+                if (k < 8)
+                    phi[k] = (1.0 / 8.0) * gg * (al * xi[0] + be * xi[1] + ga * xi[2] - 2.0);
+                else
+                    phi[k] = (1.0 / 4.0) * (1.0 - (1.0 - al * al) * xi[0] * xi[0]) * (1.0 - (1.0 - be * be) * xi[1] * xi[1]) *
+                             (1.0 - (1.0 - ga * ga) * xi[2] * xi[2]) * gg;
+            }
             break;
         default: break;
     }
@@ -207,7 +241,8 @@ fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_point
             return FB200_OK;
         }
         case FB200_HEX8:
-        case FB200_HEX27: {  // tensor.rs:36-58, x outer / z inner
+        case FB200_HEX20:
+        case FB200_HEX27: {  // tensor.rs:36-58, x outer / z inner; canonical.rs:102-112: Gauss 2^3 for Hex8, 3^3 for Hex20 / Hex27
             const int n = element_type == FB200_HEX8 ? 2 : 3;
             gauss(n, w1, x1);
             *num_points = n * n * n;
@@ -393,8 +428,19 @@ fb200_status fb200_gen_tet_mesh(uint64_t cx, uint64_t cy, uint64_t cz, double h,
 }
 
 // ---------------------------------------------------------------- Hex8 -> Hex27 (src/mesh_convert.rs:85-166,227-330)
+static fb200_status hex_refine(int nodes_out, uint64_t nv, const double* v, uint64_t ne, const uint64_t* hex8, uint64_t* nv27, double* v27,
+                               uint64_t* hex27);
 fb200_status fb200_hex27_from_hex8(uint64_t nv, const double* v, uint64_t ne, const uint64_t* hex8, uint64_t* nv27, double* v27,
                                    uint64_t* hex27) {
+    return hex_refine(27, nv, v, ne, hex8, nv27, v27, hex27);
+}
+// Hex20: the vertices and the 12 edge midpoints only (src/mesh_convert.rs:168-217)
+fb200_status fb200_hex20_from_hex8(uint64_t nv, const double* v, uint64_t ne, const uint64_t* hex8, uint64_t* nv20, double* v20,
+                                   uint64_t* hex20) {
+    return hex_refine(20, nv, v, ne, hex8, nv20, v20, hex20);
+}
+static fb200_status hex_refine(int nodes_out, uint64_t nv, const double* v, uint64_t ne, const uint64_t* hex8, uint64_t* nv27, double* v27,
+                               uint64_t* hex27) {
     static const int edges[12][2] = {{0, 1}, {0, 3}, {0, 4}, {1, 2}, {1, 5}, {2, 3}, {2, 6}, {3, 7}, {4, 5}, {4, 7}, {5, 6}, {6, 7}};
     static const int faces[6][4] = {{0, 1, 2, 3}, {0, 1, 4, 5}, {0, 3, 4, 7}, {1, 2, 5, 6}, {2, 3, 6, 7}, {4, 5, 6, 7}};
     static const double face_ref[6][3] = {{0, 0, -1}, {0, -1, 0}, {-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -412,7 +458,7 @@ fb200_status fb200_hex27_from_hex8(uint64_t nv, const double* v, uint64_t ne, co
             if (g[a] >= nv) return FB200_ERR_INDEX_OOB;
             for (int i = 0; i < 3; ++i) X[a][i] = v[3 * g[a] + i];
         }
-        for (int l = 0; l < 27; ++l) {
+        for (int l = 0; l < nodes_out; ++l) {
             Key key;
             std::fill(key.k, key.k + 8, ~0ull);
             double pos[3] = {0, 0, 0};
@@ -449,7 +495,7 @@ fb200_status fb200_hex27_from_hex8(uint64_t nv, const double* v, uint64_t ne, co
             } else {
                 id = it->second;
             }
-            if (write) hex27[27 * e + l] = id;
+            if (write) hex27[(uint64_t)nodes_out * e + l] = id;
         }
     }
     if (nv27) *nv27 = label.size();

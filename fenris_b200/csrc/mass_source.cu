@@ -211,6 +211,7 @@ static fb200_status ms_launch(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
         case FB200_HEX8: return ms_launch_t<WHAT, 8, 8, 3>(ctx, p, scatter_mode);
         case FB200_HEX27: return ms_launch_t<WHAT, 27, 8, 3>(ctx, p, scatter_mode);
         case FB200_TET10: return ms_launch_t<WHAT, 10, 4, 3>(ctx, p, scatter_mode);
+        case FB200_HEX20: return ms_launch_t<WHAT, 20, 8, 3>(ctx, p, scatter_mode);
         default: return fail(ctx, FB200_ERR_UNSUPPORTED, "element type has no device specialisation (no CPU fallback)");
     }
 }

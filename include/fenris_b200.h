@@ -53,7 +53,8 @@ enum {
     FB200_TET4 = 2,   /* Tet4Connectivity     */
     FB200_HEX8 = 3,   /* Hex8Connectivity     */
     FB200_HEX27 = 4,  /* Hex27Connectivity (geometry from the first 8 vertices, hexahedron.rs:318-335) */
-    FB200_TET10 = 5   /* Tet10Connectivity (geometry from the first 4 vertices, tetrahedron.rs:226-246) */
+    FB200_TET10 = 5,  /* Tet10Connectivity (geometry from the first 4 vertices, tetrahedron.rs:226-246) */
+    FB200_HEX20 = 6   /* Hex20Connectivity, the serendipity hexahedron (hexahedron.rs:369-563; geometry from the first 8 vertices) */
 };
 
 /* Operators = EllipticContraction implementors on the path. */
@@ -226,6 +227,9 @@ fb200_status fb200_hex27_from_hex8(uint64_t num_vertices, const double* vertices
                                    uint64_t* num_vertices27, double* vertices27, uint64_t* hex27);
 /* Canonical stiffness quadrature of an element type (src/quadrature/canonical.rs:95,102-104,110-112):
  * query num_points with weights == NULL. points are point-major [num_points * dim]. */
+/* Hex20Mesh::from(&hex8_mesh) (src/mesh_convert.rs:168-217, 481-488): same calling convention as fb200_hex27_from_hex8. */
+fb200_status fb200_hex20_from_hex8(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* hex8,
+                                   uint64_t* num_vertices_out, double* vertices_out, uint64_t* hex20);
 fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_points, double* weights, double* points);
 /* LameParameters::from(YoungPoisson) (fenris-solid/src/materials.rs:31-43). */
 void fb200_lame_from_young_poisson(double young, double poisson, double* mu, double* lambda);

@@ -248,6 +248,28 @@ def reference_gradients(elem_type: int, xi: Sequence[float]) -> np.ndarray:
             g[1, k] = _phi_quad(a, xi[0]) * _dphi_quad(b, xi[1]) * _phi_quad(c, xi[2])
             g[2, k] = _phi_quad(a, xi[0]) * _phi_quad(b, xi[1]) * _dphi_quad(c, xi[2])
         return g
+    if elem_type == HEX20:  # serendipity hexahedron, hexahedron.rs:467-545 (corner / edge formulas kept as written there)
+        g = np.empty((3, 20))
+        x0, x1, x2 = xi
+        for k, (al, be, ga) in enumerate(_HEX27_NODES[:20]):
+            gg = (1.0 + al * x0) * (1.0 + be * x1) * (1.0 + ga * x2)
+            if k < 8:
+                f = al * x0 + be * x1 + ga * x2 - 2.0
+                s = 1.0 / 8.0
+                g[0, k] = s * (al * gg + f * al * (1.0 + be * x1) * (1.0 + ga * x2))
+                g[1, k] = s * (be * gg + f * be * (1.0 + al * x0) * (1.0 + ga * x2))
+                g[2, k] = s * (ga * gg + f * ga * (1.0 + al * x0) * (1.0 + be * x1))
+            else:
+                a2, b2, c2 = al * al, be * be, ga * ga
+                h = (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - b2) * x1 * x1) * (1.0 - (1.0 - c2) * x2 * x2)
+                s = 1.0 / 4.0
+                dh0 = -2.0 * (1.0 - a2) * x0 * (1.0 - (1.0 - b2) * x1 * x1) * (1.0 - (1.0 - c2) * x2 * x2)
+                dh1 = -2.0 * (1.0 - b2) * x1 * (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - c2) * x2 * x2)
+                dh2 = -2.0 * (1.0 - c2) * x2 * (1.0 - (1.0 - a2) * x0 * x0) * (1.0 - (1.0 - b2) * x1 * x1)
+                g[0, k] = s * (dh0 * gg + h * al * (1.0 + be * x1) * (1.0 + ga * x2))
+                g[1, k] = s * (dh1 * gg + h * be * (1.0 + al * x0) * (1.0 + ga * x2))
+                g[2, k] = s * (dh2 * gg + h * ga * (1.0 + al * x0) * (1.0 + be * x1))
+        return g
     raise NotImplementedError(elem_type)
 
 
@@ -816,6 +838,18 @@ def hex27_mesh_from_hex8(vertices: np.ndarray, hex8: np.ndarray):
     return _relabel(out, None)
 
 
+def hex20_mesh_from_hex8(vertices: np.ndarray, hex8: np.ndarray):
+    """Hex20Mesh::from(&hex8_mesh).  src/mesh_convert.rs:168-217 + :227-330 (vertices, then the 12 edge midpoints)."""
+    out = []
+    for nodes in hex8.tolist():
+        Xe = vertices[nodes]
+        elem = [((g,), Xe[l].copy()) for l, g in enumerate(nodes)]
+        for a, b in _HEX_EDGES:
+            elem.append(((nodes[a], nodes[b]), 0.5 * Xe[b] + 0.5 * Xe[a]))
+        out.append(elem)
+    return _relabel(out, None)
+
+
 def tet10_mesh_from_tet4(vertices: np.ndarray, tet4: np.ndarray):
     """Tet10Mesh::from(&tet4_mesh).  src/mesh_convert.rs:42-83 + :227-330."""
     out = []
@@ -860,6 +894,16 @@ def basis_values(elem_type: int, xi: Sequence[float]) -> np.ndarray:
         return hex8_basis(xi)
     if elem_type == HEX27:
         return np.array([_phi_quad(a, xi[0]) * _phi_quad(b, xi[1]) * _phi_quad(c, xi[2]) for a, b, c in _HEX27_NODES])
+    if elem_type == HEX20:  # hexahedron.rs:414-465
+        x0, x1, x2 = xi
+        out = []
+        for k, (al, be, ga) in enumerate(_HEX27_NODES[:20]):
+            if k < 8:
+                out.append((1.0 / 8.0) * (1.0 + al * x0) * (1.0 + be * x1) * (1.0 + ga * x2) * (al * x0 + be * x1 + ga * x2 - 2.0))
+            else:
+                out.append((1.0 / 4.0) * (1.0 - (1.0 - al * al) * x0 * x0) * (1.0 - (1.0 - be * be) * x1 * x1) * (1.0 - (1.0 - ga * ga) * x2 * x2)
+                           * (1.0 + al * x0) * (1.0 + be * x1) * (1.0 + ga * x2))
+        return np.array(out)
     raise NotImplementedError(elem_type)
 
 

@@ -108,3 +108,26 @@ def test_conjugate_gradient_restatement():
     assert fo.conjugate_gradient(lambda q: A @ q, np.zeros(n), x0=np.ones(n))[1:] == (0, "ok")
     assert fo.conjugate_gradient(lambda q: A @ q, b, rel_tol=1e-14, max_iter=2)[2] == "max_iter"
     assert fo.conjugate_gradient(lambda q: -(A @ q), b)[2] == "indefinite_operator"
+
+
+def test_hex20_serendipity_element_restatement():
+    # hexahedron.rs:369-563: nodal basis (delta property, partition of unity), gradients = derivative of the basis, and the mesh
+    # converter of mesh_convert.rs:168-217 (vertices + 12 edge midpoints, shared nodes merged)
+    nodes = np.array(fo._HEX27_NODES[:20])
+    assert np.abs(np.array([fo.basis_values(fo.HEX20, x) for x in nodes]) - np.eye(20)).max() == 0.0
+    rng = np.random.default_rng(1)
+    for xi in rng.uniform(-1, 1, size=(4, 3)):
+        G = fo.reference_gradients(fo.HEX20, xi)
+        h = 1e-6
+        fd = np.stack([(fo.basis_values(fo.HEX20, xi + h * e) - fo.basis_values(fo.HEX20, xi - h * e)) / (2 * h) for e in np.eye(3)])
+        assert abs(fo.basis_values(fo.HEX20, xi).sum() - 1.0) < 1e-14 and np.abs(G.sum(axis=1)).max() < 1e-14 and np.abs(G - fd).max() < 1e-8
+    v, c = fo.create_unit_box_uniform_hex_mesh_3d(3)
+    v20, c20 = fo.hex20_mesh_from_hex8(v, c)
+    assert c20.shape == (27, 20) and len(v20) == 4 ** 3 + 3 * 3 * 4 * 4  # vertices + one node per edge of the 3^3 grid
+    assert np.array_equal(v20[c20[:, :8]], v[c])  # the first 8 nodes are the Hex8 vertices (the geometry, hexahedron.rs:552-554)
+    # a quadratic field is reproduced exactly by the serendipity space: K u = 0 for u linear (stiffness annihilates constants + linears' curl-free part)
+    prob = fo.Problem(fo.HEX20, v20, c20, fo.LAPLACE)
+    ro, ci, vals = fo.assemble_fast(prob)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals, ci.astype(np.int64), ro.astype(np.int64)), shape=(len(v20),) * 2)
+    assert np.abs(A @ np.ones(len(v20))).max() < 1e-12 and abs(v20[:, 0] @ (A @ v20[:, 0]) - 1.0) < 1e-12  # int |grad x|^2 = 1
