@@ -7,7 +7,7 @@ from ._native import (ERR_COLORING, ERR_COLUMN_NOT_IN_PATTERN, ERR_CUDA, ERR_IND
                       ERR_NOT_CONVERGED, ERR_SHAPE,
                       ERR_SINGULAR_JACOBIAN, ERR_STATE, ERR_UNSUPPORTED, HEX8, HEX20, HEX27, LAPLACE, LINEAR_ELASTIC, OK, QUAD4,
                       SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER, TET4, TET10, Fb200Error, SingularJacobianError)
-from .api import (CsrAssembler, CsrMatrix, CsrParAssembler, Density, DisjointSubsets, ElementConnectivityAssembler,  # noqa: F401
+from .api import (CompactQuadratureTable, CsrAssembler, CsrMatrix, CsrParAssembler, Density, GeneralQuadratureTable, DisjointSubsets, ElementConnectivityAssembler,  # noqa: F401
                   ElementEllipticAssembler, ElementEllipticAssemblerBuilder, ElementMassAssembler, ElementSourceAssembler, LameParameters, LaplaceOperator,
                   LinearElasticMaterial, MaterialEllipticOperator, Mesh, SparsityPattern, UniformQuadratureTable, VectorAssembler, VectorParAssembler, YoungPoisson,
                   apply_homogeneous_dirichlet_bc_csr, apply_homogeneous_dirichlet_bc_rhs, canonical_stiffness_quadrature, color_nodes, create_rectangular_uniform_hex_mesh,

@@ -92,6 +92,7 @@ def lib():
         "fb200_colors_adopt": (i32, [vp, u64, vp, vp]),
         "fb200_assemble_into_csr_device": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), vp, i32, i32]),
         "fb200_assemble_into_csr": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), vp, i32, i32, vp]),
+        "fb200_assemble_into_csr_table_device": (i32, [vp, C.POINTER(Operator), C.c_uint32, C.POINTER(Quadrature), vp, vp, i32, i32]),
         "fb200_values_device": (i32, [vp, C.POINTER(vp), pu64]),
         "fb200_values_download": (i32, [vp, vp]),
         "fb200_values_upload": (i32, [vp, vp]),

@@ -209,6 +209,56 @@ class UniformQuadratureTable:
         return UniformQuadratureTable(self.points, self.weights, [data] * len(self.weights))
 
 
+class CompactQuadratureTable:
+    """src/assembly/local/quadrature_table.rs:312-439: a set of rules and a map element -> rule."""
+
+    def __init__(self, points, weights, data, element_to_rule_map):
+        assert len(points) == len(weights), "Quadrature point and weight tables must have the same number of rules."
+        self.points = [np.ascontiguousarray(p, dtype=np.float64) for p in points]
+        self.weights = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
+        self.data = [None] * len(weights) if data is None else list(data)
+        assert len(self.data) == len(self.weights), "Quadrature point and data tables must have the same number of rules."
+        for r, (p, w, d) in enumerate(zip(self.points, self.weights, self.data)):
+            assert len(p) == len(w) and (d is None or len(d) == len(w)), f"rule {r} has mismatched numbers of points, weights and data"
+        self.element_to_rule_map = np.ascontiguousarray(element_to_rule_map, dtype=np.uint32)
+        assert self.element_to_rule_map.size == 0 or int(self.element_to_rule_map.max()) < len(self.weights), \
+            "element to rule map contains out-of-bounds rule indices"  # quadrature_table.rs:361-366
+
+    @staticmethod
+    def from_points_weights_and_map(points, weights, element_to_rule_map):
+        return CompactQuadratureTable(points, weights, None, element_to_rule_map)
+
+    @staticmethod
+    def from_quadrature_rules_and_map(points, weights, data, element_to_rule_map):
+        return CompactQuadratureTable(points, weights, data, element_to_rule_map)
+
+
+class GeneralQuadratureTable(CompactQuadratureTable):
+    """src/assembly/local/quadrature_table.rs:57-210: one rule per element (identical rules are merged before they reach the device)."""
+
+    def __init__(self, points, weights, data=None):
+        data = [None] * len(weights) if data is None else list(data)
+        keys, rules, emap = {}, [], []
+        for p, w, d in zip(points, weights, data):
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            dk = None if d is None else tuple((x.mu, x.lambda_) if hasattr(x, "mu") else float(x) for x in d)
+            key = (p.tobytes(), w.tobytes(), dk)
+            if key not in keys:
+                keys[key] = len(rules)
+                rules.append((p, w, d))
+            emap.append(keys[key])
+        super().__init__([r[0] for r in rules], [r[1] for r in rules], [r[2] for r in rules], emap)
+
+    @staticmethod
+    def from_points_and_weights(points, weights):
+        return GeneralQuadratureTable(points, weights, None)
+
+    @staticmethod
+    def from_points_weights_and_data(points, weights, data):
+        return GeneralQuadratureTable(points, weights, data)
+
+
 class LaplaceOperator:
     kind = nat.LAPLACE
 
@@ -281,6 +331,18 @@ class ElementEllipticAssembler:
         if self.qtable.data is None:
             raise Fb200Error(nat.ERR_SHAPE, "quadrature table carries no LameParameters")
         return np.array([[d.mu, d.lambda_] for d in self.qtable.data], dtype=np.float64)
+
+    def _rules(self):
+        """(weights, points, data) per rule of a Compact / General table."""
+        out = []
+        for p, w, d in zip(self.qtable.points, self.qtable.weights, self.qtable.data):
+            if self.op.kind == nat.LAPLACE:
+                out.append((w, p, None))
+            else:
+                if d is None:
+                    raise Fb200Error(nat.ERR_SHAPE, "quadrature table carries no LameParameters")
+                out.append((w, p, np.array([[x.mu, x.lambda_] for x in d], dtype=np.float64)))
+        return out
 
     # ElementMatrixAssembler::assemble_element_matrix (local.rs:77-103)
     def assemble_element_matrix(self, element_index: int, ctx: Optional[Context] = None) -> np.ndarray:
@@ -560,6 +622,14 @@ class CsrAssembler:
             self.ctx.colors_adopt(offs, elems)
             mode = nat.SCATTER_COLORED
         if len(csr.values) == 0:
+            return
+        if isinstance(getattr(ea, "qtable", None), CompactQuadratureTable):  # a rule per element (quadrature_table.rs:57-210, 312-439)
+            if mode == nat.SCATTER_GATHER:
+                mode = nat.SCATTER_ATOMIC
+            self.ctx.values_upload(csr.values)
+            self.ctx.assemble_into_csr_table_device(ea.op.kind, ea._rules(), ea.qtable.element_to_rule_map, scatter_mode=mode, accumulate=True)
+            self.ctx.synchronize()
+            self.ctx.values_download(csr.values)
             return
         if isinstance(ea, ElementMassAssembler):
             if mode == nat.SCATTER_GATHER:

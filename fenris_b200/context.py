@@ -233,6 +233,18 @@ class Context:
         self._check(self._lib.fb200_cg_solve(self._h, nat.ptr(bv), nat.ptr(x), float(rel_tol), int(max_iter), int(jacobi), C.byref(it), C.byref(res)))
         return x, int(it.value), float(res.value)
 
+    def assemble_into_csr_table_device(self, op_kind: int, rules, element_rule, scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False):
+        """rules: sequence of (weights, points, data) - a CompactQuadratureTable; element_rule: rule index per element."""
+        keep, qs = [], (nat.Quadrature * len(rules))()
+        for r, (weights, points, data) in enumerate(rules):
+            _, q = self._structs(op_kind, weights, points, data)
+            keep.append(self._keep)
+            qs[r] = q
+        er = np.ascontiguousarray(element_rule, dtype=np.uint32)
+        op = nat.Operator(op_kind)
+        self._keep = keep
+        self._check(self._lib.fb200_assemble_into_csr_table_device(self._h, C.byref(op), len(rules), qs, nat.ptr(er), None, scatter_mode, int(accumulate)))
+
     def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.zeros(max(self.nnz, 1))

@@ -29,7 +29,7 @@
 
 namespace fb200 {
 
-enum { MODE_ATOMIC = 0, MODE_COLORED = 1, MODE_DUMP = 3 };
+enum { MODE_ATOMIC = 0, MODE_COLORED = 1, MODE_DUMP = 3, MODE_COLORED_LIST = 4 /* dispatch only: coloured launch over p.elem_list */ };
 
 struct AssembleParams {
     const double* vertices;
@@ -69,6 +69,7 @@ struct AssembleParams {
     uint64_t num_owned;
     int accumulate;
     int debug;                  // measurement knobs of the Hex8 DMMA kernel (FB200_DEBUG)
+    int generic_only;           // elem_list is an arbitrary subset (quadrature-table groups): generic element kernel only
     // chunk-local scatter lists (chunks.cpp); num_chunks above
     const int64_t* slot_off;
     const uint16_t* contrib;
@@ -889,6 +890,7 @@ static fb200_status launch_hex27_mma(fb200_ctx* ctx, AssembleParams& p) {
 // element-parallel launch: the Hex8 warp kernel when it applies, the generic kernel otherwise
 template <int N, int NG, int D, int OP, int MODE>
 static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
+    if (p.generic_only) return launch_elements<N, NG, D, OP, MODE>(ctx, p);
     if constexpr (N == 8 && NG == 8 && D == 3) {
         static const bool force_v1 = std::getenv("FB200_HEX8_V1") != nullptr;
         if (p.uniform && !force_v1) {
@@ -987,6 +989,7 @@ static fb200_status dispatch_mode(fb200_ctx* ctx, AssembleParams& p, int mode) {
             // elements are visited in a locality-preserving (Morton) order so that all contributions to a CSR row
             // arrive while the row is still resident in L2; the sum does not depend on the order (up to fp rounding)
             static const bool no_order = std::getenv("FB200_NO_ORDER") != nullptr;
+            if (p.generic_only) return launch_element_parallel<N, NG, D, OP, MODE_ATOMIC>(ctx, p);
             if (ctx->d_order && !no_order && ctx->order_count == p.count) p.elem_list = ctx->d_order;
             if constexpr (N == 4 && NG == 4 && D == 3) {
                 static const bool tet_v1 = std::getenv("FB200_TET4_V1") != nullptr;
@@ -996,6 +999,7 @@ static fb200_status dispatch_mode(fb200_ctx* ctx, AssembleParams& p, int mode) {
         }
         case FB200_SCATTER_GATHER: return launch_gather<N, NG, D, OP>(ctx, p);
         case MODE_DUMP: return launch_element_parallel<N, NG, D, OP, MODE_DUMP>(ctx, p);
+        case MODE_COLORED_LIST: return launch_element_parallel<N, NG, D, OP, MODE_COLORED>(ctx, p);
         case FB200_SCATTER_COLORED: {
             const uint64_t ncol = ctx->h_color_off.size() - 1;
             for (uint64_t c = 0; c < ncol; ++c) {
@@ -1115,6 +1119,71 @@ fb200_status fb200_assemble_into_csr(fb200_ctx* ctx, const fb200_operator* op, c
     FB200_TRY(fb200_assemble_into_csr_device(ctx, op, q, u, scatter_mode, accumulate));
     if (ctx->nnz) FB200_CUDA(ctx, cudaMemcpyAsync(values, ctx->d_values, ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return read_errword(ctx);
+}
+
+// CompactQuadratureTable / GeneralQuadratureTable (quadrature_table.rs:57-210, 312-439): a rule per element.  Elements are grouped by
+// rule on the host; every group runs the uniform-table element kernel over its own element list with accumulate semantics.
+fb200_status fb200_assemble_into_csr_table_device(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                                  const uint32_t* element_rule, const double* u, int32_t scatter_mode, int32_t accumulate) {
+    (void)u;
+    if (!ctx) return FB200_ERR_STATE;
+    if (!op || !rules || !element_rule || num_rules == 0) return fail(ctx, FB200_ERR_SHAPE, "null operator / rules / element map");
+    for (uint32_t r = 0; r < num_rules; ++r) FB200_TRY(validate(ctx, op, &rules[r]));
+    if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
+    const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;
+    if (s != ctx->sdim) return fail(ctx, FB200_ERR_SHAPE, "pattern solution_dim does not match the operator");
+    if (scatter_mode != FB200_SCATTER_ATOMIC && scatter_mode != FB200_SCATTER_COLORED)
+        return fail(ctx, FB200_ERR_UNSUPPORTED, "quadrature tables with a rule per element support the ATOMIC and COLORED scatter");
+    if (scatter_mode == FB200_SCATTER_COLORED && !ctx->has_colors)
+        return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    // element lists per (colour, rule) - one pseudo colour holding all owned elements for the ATOMIC scatter
+    std::vector<uint64_t> col_off{0, ctx->E_owned};
+    const bool colored = scatter_mode == FB200_SCATTER_COLORED;
+    if (colored) col_off = ctx->h_color_off;
+    std::vector<std::vector<int32_t>> lists((col_off.size() - 1) * (size_t)num_rules);
+    for (size_t c = 0; c + 1 < col_off.size(); ++c)
+        for (uint64_t k = col_off[c]; k < col_off[c + 1]; ++k) {
+            const uint64_t e = colored ? ctx->h_color_elems[k] : k;
+            if (e >= ctx->E_owned) continue;  // ghost elements of a partition are not assembled
+            const uint32_t r = element_rule[e];
+            if (r >= num_rules) return fail(ctx, FB200_ERR_INDEX_OOB, "element_to_rule_map entry out of bounds (quadrature_table.rs:361-366)", (int64_t)e);
+            lists[c * num_rules + r].push_back((int32_t)e);
+        }
+    std::vector<int32_t> flat;
+    std::vector<uint64_t> off(lists.size() + 1, 0);
+    for (size_t i = 0; i < lists.size(); ++i) {
+        off[i + 1] = off[i] + lists[i].size();
+        flat.insert(flat.end(), lists[i].begin(), lists[i].end());
+    }
+    int32_t* d_lists = nullptr;
+    FB200_TRY(upload_vec(ctx, &d_lists, flat));
+    fb200_status st = FB200_OK;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "memset values");
+    }
+    for (uint32_t r = 0; r < num_rules && st == FB200_OK; ++r) {
+        bool any = false;
+        for (size_t c = 0; c + 1 < col_off.size(); ++c) any |= off[c * num_rules + r + 1] > off[c * num_rules + r];
+        if (!any) continue;
+        st = upload_tables(ctx, op, &rules[r]);
+        for (size_t c = 0; c + 1 < col_off.size() && st == FB200_OK; ++c) {
+            const size_t i = c * num_rules + r;
+            if (off[i + 1] == off[i]) continue;
+            AssembleParams p;
+            fill_params(ctx, p);
+            p.accumulate = 1;
+            p.generic_only = 1;
+            p.elem_list = d_lists + off[i];
+            p.count = off[i + 1] - off[i];
+            // COLORED: one launch per (colour, rule), plain read-modify-write inside a colour
+            st = dispatch(ctx, p, op->kind, colored ? (int)MODE_COLORED_LIST : (int)FB200_SCATTER_ATOMIC);
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_lists);
+    return st;
 }
 
 fb200_status fb200_values_device(fb200_ctx* ctx, double** device_ptr, uint64_t* nnz) {

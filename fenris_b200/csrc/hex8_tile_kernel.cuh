@@ -43,6 +43,11 @@ __device__ __forceinline__ void tile_accumulate(double* __restrict__ a, const do
         for (int j = 0; j < S; ++j) a[i * S + j] = v[i * S + j] + K[i][j];
 }
 
+__device__ __forceinline__ void dmma_m8n8k4_zero(double& d0, double& d1, double a, double b) {
+    const double z = 0.0;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(z));
+}
+
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -403,13 +408,10 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
 #pragma unroll
                     for (int m = 0; m < D; ++m)
 #pragma unroll
-                        for (int n = 0; n < D; ++n) { M0[m][n] = 0.0; M1[m][n] = 0.0; }
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                        for (int m = 0; m < D; ++m)
-#pragma unroll
-                            for (int n = 0; n < D; ++n) dmma_m8n8k4(M0[m][n], M1[m][n], ga[ks][m], ga[ks][n]);
+                        for (int n = 0; n < D; ++n) {  // first k-step from a shared zero accumulator (no 18 register clears)
+                            dmma_m8n8k4_zero(M0[m][n], M1[m][n], ga[0][m], ga[0][n]);
+                            dmma_m8n8k4(M0[m][n], M1[m][n], ga[1][m], ga[1][n]);
+                        }
                     const double tr0 = M0[0][0] + M0[1][1] + M0[2][2], tr1 = M1[0][0] + M1[1][1] + M1[2][2];
 #pragma unroll
                     for (int i = 0; i < D; ++i)

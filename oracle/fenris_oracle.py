@@ -1112,3 +1112,20 @@ def conjugate_gradient(apply_a, b, x0=None, rel_tol: float = 1e-8, max_iter: int
         zTr_next = float(z @ r)
         p = p * (zTr_next / zTr) + z
         zTr = zTr_next
+
+
+def assemble_with_quadrature_table(elem_type: int, vertices, connectivity, op: int, rules, element_to_rule):
+    """CsrAssembler::assemble with an ElementEllipticAssembler whose QuadratureTable has a rule per element
+    (CompactQuadratureTable / GeneralQuadratureTable, quadrature_table.rs:57-210, 312-439; the element loop of elliptic.rs:299-340 calls
+    populate_element_quadrature_from_table per element).  rules[r] = (weights, points, params_per_point)."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    n, _, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    ro, ci = assemble_pattern(s, len(V), conn.tolist())
+    values = np.zeros(len(ci))
+    for e in range(len(conn)):
+        w, p, params = rules[int(element_to_rule[e])]
+        K = element_matrix(elem_type, V[conn[e]], op, w, p, params)
+        scatter_element(values, ro, ci, s, conn[e].tolist(), K)
+    return ro, ci, values
