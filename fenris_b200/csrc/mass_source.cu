@@ -53,7 +53,20 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     const double* t_phi = t_pgeo + nq * ng;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const int warp_doubles = ng * d + nq + 2 * n + (n & 1);  // X | scale | base (int64) | ids + row lengths (int32)
-    double* w_X = sm + ((tab_len + 1) & ~1) + warp * warp_doubles;
+    // mass matrix of small elements: the products phi_I(q) phi_J(q) do not depend on the element - tabulated once per CTA as
+    // pp[q][I n + J] (lane-contiguous: conflict-free), so that M_IJ = sum_q scale_q pp[q][IJ] costs one shared load per term
+    constexpr bool kProducts = WHAT == 0 && n * n <= 128;
+    const int pp_len = kProducts ? nq * n * n : 0;
+    double* t_pp = sm + ((tab_len + 1) & ~1);
+    if constexpr (kProducts) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pp_len; i += blockDim.x) {
+            const int q = i / (n * n), t = i - q * (n * n);
+            const int a = t / n, b = t - a * n;
+            t_pp[i] = sm[nq * (2 + ng * d + ng) + q * n + (a < b ? a : b)] * sm[nq * (2 + ng * d + ng) + q * n + (a < b ? b : a)];
+        }
+    }
+    double* w_X = sm + ((tab_len + 1) & ~1) + ((pp_len + 1) & ~1) + warp * warp_doubles;
     double* w_scale = w_X + ng * d;
     long long* w_base = reinterpret_cast<long long*>(w_scale + nq);
     int* w_ids = reinterpret_cast<int*>(w_base + n);
@@ -95,13 +108,17 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
         }
         __syncwarp();
         if constexpr (WHAT == 0) {
-            // M_IJ = I_s sum_q scale_q phi_I phi_J; both triangles with the factors in (min, max) order: bitwise the
-            // reference's upper-triangle-then-mirror result (mass.rs:270-283)
+            // M_IJ = I_s sum_q scale_q phi_I phi_J; both triangles from the same (min, max)-ordered products: exactly symmetric,
+            // like the reference's upper-triangle-then-mirror result (mass.rs:270-283)
             for (int t = lane; t < n * n; t += 32) {
                 const int a = t / n, b = t - a * n;
                 const int lo = a < b ? a : b, hi = a < b ? b : a;
                 double m = 0.0;
-                for (int q = 0; q < nq; ++q) m += w_scale[q] * t_phi[q * n + lo] * t_phi[q * n + hi];
+                if constexpr (kProducts) {
+                    for (int q = 0; q < nq; ++q) m = fma(w_scale[q], t_pp[q * (n * n) + t], m);
+                } else {
+                    for (int q = 0; q < nq; ++q) m += w_scale[q] * t_phi[q * n + lo] * t_phi[q * n + hi];
+                }
                 const int kk = p.blockmap[e * (uint64_t)(n * n) + t];
                 double* row = p.values + (w_base[a] + (long long)(s * kk));
                 for (int i = 0; i < s; ++i) {
@@ -175,7 +192,8 @@ static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
     p.d = D;
     const int tab_len = p.nq * (2 + NG * D + NG + N);
     const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1);
-    const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + 4 * warp_doubles);
+    const int pp_len = (WHAT == 0 && N * N <= 128) ? p.nq * N * N : 0;  // products phi_I phi_J per point (see the kernel)
+    const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + ((pp_len + 1) & ~1) + 4 * warp_doubles);
     auto kernel = mass_source_kernel<WHAT, N, NG, D>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     auto run = [&](const int32_t* list, uint64_t count) -> fb200_status {
