@@ -486,13 +486,18 @@ class VectorAssembler:
             ctx.colors_adopt(offs, elems)
             mode = nat.SCATTER_COLORED
         qt = ea.qtable
+        if isinstance(ea, ElementEllipticAssembler):  # elliptic.rs:342-359: the operator's vector at ea.u
+            assert ea.u is not None and len(ea.u) == s * n, "u has the wrong length"
+            ctx.assemble_elliptic_vector(ea.op.kind, qt.weights, qt.points, ea._data(), np.asarray(ea.u, dtype=np.float64), out=output,
+                                         scatter_mode=mode, accumulate=True)
+            return output
         x = ctx.physical_quadrature_points(qt.weights, qt.points, ea.num_elements())
         data = qt.data if qt.data is not None else [None] * len(qt.weights)
         f = np.stack([np.asarray(ea.source(x[:, q], data[q]), dtype=np.float64).reshape(ea.num_elements(), s) for q in range(len(qt.weights))], axis=1)
         ctx.assemble_vector(qt.weights, qt.points, np.ascontiguousarray(f), n, out=output, scatter_mode=mode, accumulate=True)
         return output
 
-    def assemble_vector(self, ea: ElementSourceAssembler) -> np.ndarray:
+    def assemble_vector(self, ea) -> np.ndarray:
         return self.assemble_vector_into(np.zeros(ea.solution_dim() * ea.num_nodes()), ea)
 
 
@@ -656,6 +661,18 @@ class CsrParAssembler(CsrAssembler):
     def assemble_into_csr(self, csr: CsrMatrix, colors: Sequence[DisjointSubsets], element_assembler):  # type: ignore[override]
         self._cols = list(colors)
         super().assemble_into_csr(csr, element_assembler)
+
+
+def assemble_scalar(ea: ElementEllipticAssembler, ctx: Optional[Context] = None) -> float:
+    """src/assembly/global.rs:697-722 over an ElementEllipticAssembler (ElementScalarAssembler, elliptic.rs:352-359): the elliptic energy of ea.u."""
+    own = ctx is None
+    ctx = ctx or Context()
+    try:
+        ctx.space_upload(ea.space.element_type, ea.space.vertices_, ea.space.connectivity_)
+        return ctx.assemble_elliptic_scalar(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), np.asarray(ea.u, dtype=np.float64))
+    finally:
+        if own:
+            ctx.close()
 
 
 # ----------------------------------------------------------------------------- Dirichlet conditions (global.rs:379-495)

@@ -200,6 +200,25 @@ class Context:
         self._check(self._lib.fb200_assemble_vector(self._h, C.byref(q), s, nat.ptr(f), int(f.ndim == 3), scatter_mode, int(accumulate), nat.ptr(out)))
         return out
 
+    def assemble_elliptic_vector(self, op_kind: int, weights, points, data, u: np.ndarray, out: Optional[np.ndarray] = None,
+                                 scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False) -> np.ndarray:
+        """elliptic.rs:456-526 through VectorAssembler (global.rs:569-686): internal-force-like vector of the elliptic operator at u."""
+        uv = nat.as_f64(u)
+        if out is None:
+            out = np.zeros_like(uv)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == uv.size
+        op, q = self._structs(op_kind, weights, points, data)
+        self._check(self._lib.fb200_assemble_elliptic_vector(self._h, C.byref(op), C.byref(q), nat.ptr(uv), scatter_mode, int(accumulate), nat.ptr(out)))
+        return out
+
+    def assemble_elliptic_scalar(self, op_kind: int, weights, points, data, u: np.ndarray) -> float:
+        """elliptic.rs:545-605 through assemble_scalar (global.rs:697-722): the elliptic energy of u."""
+        uv = nat.as_f64(u)
+        op, q = self._structs(op_kind, weights, points, data)
+        e = C.c_double(0.0)
+        self._check(self._lib.fb200_assemble_elliptic_scalar(self._h, C.byref(op), C.byref(q), nat.ptr(uv), C.byref(e)))
+        return float(e.value)
+
     def physical_quadrature_points(self, weights, points, num_elements: int) -> np.ndarray:
         q = self._quad_only(weights, points)
         d = q.dim

@@ -22,7 +22,7 @@ struct MsParams {
     const uint16_t* blockmap;
     const int32_t* elem_list;  // colour list or nullptr
     uint64_t count;
-    const double* tab;         // w[nq] | rho[nq] | ggeo[nq*ng*d] | phigeo[nq*ng] | phi[nq*n]
+    const double* tab;         // w[nq] | rho[nq] | ggeo[nq*ng*d] | phigeo[nq*ng] | phi[nq*n] | mu[nq] | lam[nq] | gref[nq*n*d]
     int nq, n, ng, d, s;
     int plain;                 // COLORED: plain read-modify-write
     double* values;            // CSR values (mass)
@@ -30,6 +30,11 @@ struct MsParams {
     const double* source;      // [count_all or 1][nq][s]
     int source_per_element;
     double* points_out;        // physical points [E][nq][d]
+    // elliptic vector / energy (elliptic.rs:440-605): operator kind, nodal solution u [N][s], per-element energies, error word
+    int op;
+    const double* u;
+    double* energies;
+    unsigned long long* errword;
 };
 
 template <int d>
@@ -40,19 +45,24 @@ __device__ __forceinline__ double det_small_dev(const double (&J)[d * d]) {
     return J[0] * c00 - J[1] * c01 + J[2] * c02;
 }
 
-template <int WHAT, int n, int ng, int d>  // WHAT: 0 mass matrix, 1 source vector, 2 physical points; element shape at compile time
+template <int WHAT, int n, int ng, int d>  // WHAT: 0 mass matrix, 1 source vector, 2 physical points, 3 elliptic vector, 4 elliptic energy
 __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     extern __shared__ double sm[];
     const int nq = p.nq, s = p.s;
-    const int tab_len = nq * (2 + ng * d + ng + n);
+    constexpr bool kElliptic = WHAT >= 3;
+    const int tab_len = nq * (2 + ng * d + ng + n) + (kElliptic ? nq * (2 + n * d) : 0);
     for (int i = threadIdx.x; i < tab_len; i += blockDim.x) sm[i] = p.tab[i];
     const double* t_w = sm;
     const double* t_rho = t_w + nq;
     const double* t_ggeo = t_rho + nq;
     const double* t_pgeo = t_ggeo + nq * ng * d;
     const double* t_phi = t_pgeo + nq * ng;
+    const double* t_mu = t_phi + nq * n;     // (elliptic only)
+    const double* t_lam = t_mu + nq;
+    const double* t_gref = t_lam + nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-    const int warp_doubles = ng * d + nq + 2 * n + (n & 1);  // X | scale | base (int64) | ids + row lengths (int32)
+    // per warp: X | scale | base (int64) | ids + row lengths (int32) | elliptic: u_e[n][s], A[nq][s][d]
+    const int warp_doubles = ng * d + nq + 2 * n + (n & 1) + (kElliptic ? n * s + nq * s * d : 0);
     // mass matrix of small elements: the products phi_I(q) phi_J(q) do not depend on the element - tabulated once per CTA as
     // pp[q][I n + J] (lane-contiguous: conflict-free), so that M_IJ = sum_q scale_q pp[q][IJ] costs one shared load per term
     constexpr bool kProducts = WHAT == 0 && n * n <= 128;
@@ -71,6 +81,8 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     long long* w_base = reinterpret_cast<long long*>(w_scale + nq);
     int* w_ids = reinterpret_cast<int*>(w_base + n);
     int* w_len = w_ids + n;
+    double* w_u = w_X + ng * d + nq + 2 * n + (n & 1);
+    double* w_A = w_u + n * s;
     __syncthreads();
     for (uint64_t k = (uint64_t)blockIdx.x * warps + warp; k < p.count; k += (uint64_t)gridDim.x * warps) {
         const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[k] : k;
@@ -94,7 +106,114 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                 p.points_out[(e * nq + q) * d + c] = x;
             }
         }
-        for (int q = lane; WHAT != 2 && q < nq; q += 32) {  // scale_q = w |det J_q| rho_q  (mass.rs:262-267, source.rs:254-267)
+        if constexpr (kElliptic) {
+            // ---- elliptic vector f_I = sum_q w |det J| g^T grad phi_I and energy sum_q w |det J| psi(grad u)  (elliptic.rs:456-605)
+            for (int t = lane; t < n * s; t += 32) w_u[t] = p.u[(uint64_t)w_ids[t / s] * s + (t % s)];
+            __syncwarp();
+            double energy = 0.0;
+            for (int q = lane; q < nq; q += 32) {
+                double J[d * d], Ji[d * d];
+#pragma unroll
+                for (int i = 0; i < d * d; ++i) J[i] = 0.0;
+#pragma unroll
+                for (int a = 0; a < ng; ++a)
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) J[i * d + j] = fma(w_X[a * d + i], t_ggeo[(q * ng + a) * d + j], J[i * d + j]);
+                const double det = det_small_dev<d>(J);
+                if (det == 0.0) {  // "Singular element Jacobian encountered" (elliptic.rs:493-497)
+                    atomicMin(p.errword, ((unsigned long long)e << 8) | (unsigned long long)FB200_ERR_SINGULAR_JACOBIAN);
+                    for (int t = 0; t < s * d; ++t) w_A[q * s * d + t] = 0.0;
+                    continue;
+                }
+                if constexpr (d == 2) {
+                    Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
+                } else {
+                    Ji[0] = (J[4] * J[8] - J[7] * J[5]) / det; Ji[1] = (J[2] * J[7] - J[8] * J[1]) / det; Ji[2] = (J[1] * J[5] - J[4] * J[2]) / det;
+                    Ji[3] = -(J[3] * J[8] - J[6] * J[5]) / det; Ji[4] = (J[0] * J[8] - J[6] * J[2]) / det; Ji[5] = (J[2] * J[3] - J[5] * J[0]) / det;
+                    Ji[6] = (J[3] * J[7] - J[6] * J[4]) / det; Ji[7] = (J[1] * J[6] - J[7] * J[0]) / det; Ji[8] = (J[0] * J[4] - J[3] * J[1]) / det;
+                }
+                // grad u = J^{-T} sum_I grad_ref phi_I (x) u_I   (d x s, compute_volume_u_grad, elliptic.rs:25-59)
+                double H[d * 3], GU[d * 3];  // s <= 3
+#pragma unroll
+                for (int i = 0; i < d * 3; ++i) H[i] = 0.0;
+                for (int a = 0; a < n; ++a)
+#pragma unroll
+                    for (int k = 0; k < d; ++k)
+                        for (int i = 0; i < s; ++i) H[k * 3 + i] = fma(t_gref[(q * n + a) * d + k], w_u[a * s + i], H[k * 3 + i]);
+#pragma unroll
+                for (int k = 0; k < d; ++k)
+                    for (int i = 0; i < s; ++i) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < d; ++m) acc = fma(Ji[m * d + k], H[m * 3 + i], acc);  // (J^{-T})_{km} = Ji[m][k]
+                        GU[k * 3 + i] = acc;
+                    }
+                // g^T (s x d) and psi
+                double GT[3 * d], psi;
+                if (p.op == FB200_LAPLACE) {  // g = grad u, psi = |grad u|^2 / 2  (operators/laplace.rs:33-51)
+                    psi = 0.0;
+#pragma unroll
+                    for (int k = 0; k < d; ++k) {
+                        GT[k] = GU[k * 3];
+                        psi = fma(GU[k * 3], GU[k * 3], psi);
+                    }
+                    psi *= 0.5;
+                } else {
+                    // LinearElasticMaterial through F = I + (grad u)^T, eps = sym(F) - I  (fenris-solid lib.rs:20-29, materials.rs:72-95)
+                    double eps[d * d];
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            const double Fij = (i == j ? 1.0 : 0.0) + GU[j * 3 + i], Fji = (i == j ? 1.0 : 0.0) + GU[i * 3 + j];
+                            eps[i * d + j] = 0.5 * (Fij + Fji) - (i == j ? 1.0 : 0.0);
+                        }
+                    double tr = 0.0, ee = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; ++i) tr += eps[i * d + i];
+#pragma unroll
+                    for (int i = 0; i < d * d; ++i) ee = fma(eps[i], eps[i], ee);
+                    const double mu = t_mu[q], lam = t_lam[q];
+                    psi = mu * ee + 0.5 * lam * tr * tr;
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) GT[i * d + j] = eps[i * d + j] * 2.0 * mu + (i == j ? lam * tr : 0.0);  // P = g^T
+                }
+                const double alpha = t_w[q] * fabs(det);
+                energy = fma(alpha, psi, energy);
+                // A_q = alpha g^T J^{-T}  (s x d): f_I += A_q grad_ref phi_I   (elliptic.rs:520-524)
+                for (int i = 0; i < s; ++i)
+#pragma unroll
+                    for (int k = 0; k < d; ++k) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int m = 0; m < d; ++m) acc = fma(GT[i * d + m], Ji[k * d + m], acc);  // (J^{-T})_{mk} = Ji[k][m]
+                        w_A[(q * s + i) * d + k] = alpha * acc;
+                    }
+            }
+            __syncwarp();
+            if constexpr (WHAT == 3) {
+                for (int t = lane; t < n * s; t += 32) {
+                    const int a = t / s, i = t - a * s;
+                    double f = 0.0;
+                    for (int q = 0; q < nq; ++q)
+#pragma unroll
+                        for (int k = 0; k < d; ++k) f = fma(w_A[(q * s + i) * d + k], t_gref[(q * n + a) * d + k], f);
+                    double* dst = p.vector + (uint64_t)w_ids[a] * s + i;
+                    if (p.plain) *dst += f;
+                    else atomicAdd(dst, f);
+                }
+            } else {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, o);
+                if (lane == 0) p.energies[k] = energy;
+            }
+            __syncwarp();
+        }
+        for (int q = lane; WHAT < 2 && q < nq; q += 32) {  // scale_q = w |det J_q| rho_q  (mass.rs:262-267, source.rs:254-267)
             double J[d * d];
 #pragma unroll
             for (int i = 0; i < d * d; ++i) J[i] = 0.0;
@@ -153,17 +272,25 @@ static fb200_status ms_validate(fb200_ctx* ctx, const fb200_quadrature* q) {
     return FB200_OK;
 }
 
-static fb200_status ms_tables(fb200_ctx* ctx, const fb200_quadrature* q, bool with_density) {
+static fb200_status ms_tables(fb200_ctx* ctx, const fb200_quadrature* q, int with_density /* 0 none, 1 density, 2 Lame pairs */) {
     const int nq = q->num_points, n = ctx->ei.n, ng = ctx->ei.ng, d = ctx->ei.d;
-    std::vector<double> h((size_t)nq * (2 + ng * d + ng + n), 0.0);
+    std::vector<double> h((size_t)nq * (2 + ng * d + ng + n) + (size_t)nq * (2 + n * d), 0.0);
     double* w = h.data();
     double* rho = w + nq;
     double* ggeo = rho + nq;
     double* pgeo = ggeo + (size_t)nq * ng * d;
     double* phi = pgeo + (size_t)nq * ng;
+    double* mu = phi + (size_t)nq * n;
+    double* lam = mu + nq;
+    double* gref = lam + nq;
     for (int k = 0; k < nq; ++k) {
         w[k] = q->weights[k];
-        rho[k] = with_density ? q->data[k] : 1.0;
+        rho[k] = with_density == 1 ? q->data[k] : 1.0;
+        if (with_density == 2) {  // Lame parameters per point (elliptic vector / energy of the linear elastic operator)
+            mu[k] = q->data[2 * k];
+            lam[k] = q->data[2 * k + 1];
+        }
+        reference_gradients(ctx->elem_type, q->points + (size_t)k * d, gref + (size_t)k * n * d);
         reference_gradients(geometry_type(ctx->elem_type), q->points + (size_t)k * d, ggeo + (size_t)k * ng * d);
         reference_basis(geometry_type(ctx->elem_type), q->points + (size_t)k * d, pgeo + (size_t)k * ng);
         reference_basis(ctx->elem_type, q->points + (size_t)k * d, phi + (size_t)k * n);
@@ -190,8 +317,8 @@ static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
     p.n = N;
     p.ng = NG;
     p.d = D;
-    const int tab_len = p.nq * (2 + NG * D + NG + N);
-    const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1);
+    const int tab_len = p.nq * (2 + NG * D + NG + N) + (WHAT >= 3 ? p.nq * (2 + N * D) : 0);
+    const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1) + (WHAT >= 3 ? N * p.s + p.nq * p.s * D : 0);
     const int pp_len = (WHAT == 0 && N * N <= 128) ? p.nq * N * N : 0;  // products phi_I phi_J per point (see the kernel)
     const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + ((pp_len + 1) & ~1) + 4 * warp_doubles);
     auto kernel = mass_source_kernel<WHAT, N, NG, D>;
@@ -204,6 +331,10 @@ static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
         kernel<<<blocks, 128, smem, ctx->stream>>>(p);
         return check_launch(ctx, "mass_source_kernel");
     };
+    if (WHAT == 4) {  // energies: every owned element once, no scatter
+        p.plain = 0;
+        return run(nullptr, ctx->E_owned);
+    }
     if (WHAT != 2 && scatter_mode == FB200_SCATTER_COLORED) {
         if (!ctx->has_colors) return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
         p.plain = 1;
@@ -246,7 +377,7 @@ fb200_status fb200_assemble_mass_into_csr_device(fb200_ctx* ctx, const fb200_qua
     if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
     if (ctx->ragged || !ctx->d_blockmap) return fail(ctx, FB200_ERR_UNSUPPORTED, "mass assembly needs a uniform-element space");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    FB200_TRY(ms_tables(ctx, q, true));
+    FB200_TRY(ms_tables(ctx, q, 1));
     if (!accumulate) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
     MsParams p;
     std::memset(&p, 0, sizeof(p));
@@ -275,7 +406,7 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* q, in
     if (!source_values || !out) return fail(ctx, FB200_ERR_SHAPE, "null source values / output");
     if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "vector assembly needs a uniform-element space");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    FB200_TRY(ms_tables(ctx, q, false));
+    FB200_TRY(ms_tables(ctx, q, 0));
     const uint64_t len = (uint64_t)solution_dim * ctx->N;
     const uint64_t src_len = (uint64_t)q->num_points * solution_dim * (per_element ? ctx->E : 1);
     if (ctx->vector_capacity < len) {
@@ -307,12 +438,111 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* q, in
     return read_errword(ctx);
 }
 
+// ElementEllipticAssembler as ElementVectorAssembler / ElementScalarAssembler (elliptic.rs:342-359, 440-605) through VectorAssembler
+// (global.rs:569-686) / assemble_scalar (global.rs:697-722)
+static fb200_status elliptic_common(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int* s_out) {
+    FB200_TRY(ms_validate(ctx, q));
+    if (!op || (op->kind != FB200_LAPLACE && op->kind != FB200_LINEAR_ELASTIC))
+        return fail(ctx, FB200_ERR_UNSUPPORTED, "operator has no device specialisation (no CPU fallback)");
+    if (op->kind == FB200_LINEAR_ELASTIC && !q->data) return fail(ctx, FB200_ERR_SHAPE, "linear elasticity needs Lame data per point");
+    if (!u) return fail(ctx, FB200_ERR_SHAPE, "null u");
+    if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB200_TRY(ms_tables(ctx, q, op->kind == FB200_LINEAR_ELASTIC ? 2 : 0));
+    const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;
+    const uint64_t len = (uint64_t)s * ctx->N;
+    if (ctx->source_capacity < len) {
+        dev_free(ctx->d_source);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_source, len));
+        ctx->source_capacity = len;
+    }
+    if (len) FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_source, u, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    *s_out = s;
+    return FB200_OK;
+}
+
+fb200_status fb200_assemble_elliptic_vector(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
+                                            int32_t scatter_mode, int32_t accumulate, double* out) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");
+    int s = 0;
+    FB200_TRY(elliptic_common(ctx, op, q, u, &s));
+    const uint64_t len = (uint64_t)s * ctx->N;
+    if (ctx->vector_capacity < len) {
+        dev_free(ctx->d_vector);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_vector, len));
+        ctx->vector_capacity = len;
+    }
+    ctx->vector_len = len;
+    if (accumulate) {
+        if (len) FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_vector, out, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (len) {
+        FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_vector, 0, len * sizeof(double), ctx->stream));
+    }
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = s;
+    p.op = op->kind;
+    p.u = ctx->d_source;
+    p.vector = ctx->d_vector;
+    p.errword = ctx->d_errword;
+    FB200_TRY(ms_launch<3>(ctx, p, scatter_mode));
+    if (len) FB200_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_vector, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return read_errword(ctx);
+}
+
+__global__ void sum_energies_kernel(const double* __restrict__ e, uint64_t n, double* out) {  // one block, fixed order
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (uint64_t i = threadIdx.x; i < n; i += 256) s += e[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+fb200_status fb200_assemble_elliptic_scalar(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, double* energy) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!energy) return fail(ctx, FB200_ERR_SHAPE, "null output");
+    int s = 0;
+    FB200_TRY(elliptic_common(ctx, op, q, u, &s));
+    *energy = 0.0;
+    if (ctx->E_owned == 0) return FB200_OK;
+    double* d_e = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_e, ctx->E_owned + 1));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = s;
+    p.op = op->kind;
+    p.u = ctx->d_source;
+    p.energies = d_e;
+    p.errword = ctx->d_errword;
+    fb200_status st = ms_launch<4>(ctx, p, FB200_SCATTER_ATOMIC);
+    if (st == FB200_OK) {
+        sum_energies_kernel<<<1, 256, 0, ctx->stream>>>(d_e, ctx->E_owned, d_e + ctx->E_owned);
+        st = check_launch(ctx, "sum_energies_kernel");
+    }
+    if (st == FB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(energy, d_e + ctx->E_owned, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "D2H energy");
+    }
+    if (st == FB200_OK) st = read_errword(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_e);
+    return st;
+}
+
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* q, double* out) {
     FB200_TRY(ms_validate(ctx, q));
     if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");
     if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    FB200_TRY(ms_tables(ctx, q, false));
+    FB200_TRY(ms_tables(ctx, q, 0));
     const uint64_t len = ctx->E * (uint64_t)q->num_points * ctx->ei.d;
     if (len == 0) return FB200_OK;
     double* d_out = nullptr;

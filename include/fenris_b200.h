@@ -180,6 +180,16 @@ fb200_status fb200_assemble_mass_into_csr(fb200_ctx* ctx, const fb200_quadrature
  * quadrature->data is not used.  scatter_mode: ATOMIC or COLORED. */
 fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* quadrature, int32_t solution_dim, const double* source_values,
                                    int32_t per_element, int32_t scatter_mode, int32_t accumulate, double* out);
+/* ElementEllipticAssembler as ElementVectorAssembler / ElementScalarAssembler (src/assembly/local/elliptic.rs:342-359, 440-605): with
+ * grad u = J^-T sum_I grad_ref phi_I (x) u_I (compute_volume_u_grad, :25-59) per quadrature point,
+ *   vector  out[s I + i] (+)= sum w |det J| (g^T grad phi_I)_i      g = grad u (Laplace) | g^T = P(grad u) (LinearElasticMaterial stress)
+ *   scalar  *energy = sum over elements and points of w |det J| psi(grad u)    psi = |grad u|^2 / 2 | mu eps:eps + lambda tr(eps)^2 / 2
+ * u: solution_dim * num_nodes doubles on the host.  Vector: VectorAssembler / VectorParAssembler semantics (ATOMIC | COLORED, accumulate);
+ * scalar: assemble_scalar (global.rs:697-722).  Errors: FB200_ERR_SINGULAR_JACOBIAN with the element index. */
+fb200_status fb200_assemble_elliptic_vector(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature, const double* u,
+                                            int32_t scatter_mode, int32_t accumulate, double* out);
+fb200_status fb200_assemble_elliptic_scalar(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature, const double* u,
+                                            double* energy);
 /* x_q = element.map_reference_coords(xi_q) for every element and point (FiniteElement::map_reference_coords; sub-parametric elements map
  * through their embedded linear element, hexahedron.rs:328-330): out[(e * num_points + q) * d + c]. */
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* quadrature, double* out);

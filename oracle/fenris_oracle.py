@@ -1129,3 +1129,100 @@ def assemble_with_quadrature_table(elem_type: int, vertices, connectivity, op: i
         K = element_matrix(elem_type, V[conn[e]], op, w, p, params)
         scatter_element(values, ro, ci, s, conn[e].tolist(), K)
     return ro, ci, values
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# ElementEllipticAssembler as vector / scalar assembler (elliptic.rs:342-359, 440-605) - row a7 of SURVEY 8 (grad u) in use
+# ------------------------------------------------------------------------------------------------------------------------
+def volume_u_grad(j_inv_t: np.ndarray, G_ref: np.ndarray, U: np.ndarray) -> np.ndarray:
+    """compute_volume_u_grad (elliptic.rs:25-59): grad u = J^{-T} sum_I grad_ref phi_I (x) u_I, shape (d, s).
+    G_ref: (d, n) reference gradients as columns, U: (s, n) nodal values as columns."""
+    d, s = G_ref.shape[0], U.shape[0]
+    acc = np.zeros((d, s))
+    for I in range(G_ref.shape[1]):
+        acc += np.outer(G_ref[:, I], U[:, I])  # ger, node by node
+    return j_inv_t @ acc
+
+
+def elliptic_operator_transpose(op: int, u_grad: np.ndarray, params) -> np.ndarray:
+    """g^T (s x d).  Laplace: g = grad u (laplace.rs:44-51).  MaterialEllipticOperator<LinearElasticMaterial>: g^T = P(F) with
+    F = I + (grad u)^T (compute_stress_tensor_du, fenris-solid lib.rs:20-29, 98-104, 460-468; materials.rs:86-95)."""
+    if op == LAPLACE:
+        return u_grad.T.copy()
+    mu, lam = params
+    d = u_grad.shape[0]
+    return linear_elastic_stress(np.eye(d) + u_grad.T, mu, lam)
+
+
+def elliptic_energy_density(op: int, u_grad: np.ndarray, params) -> float:
+    """psi(grad u): Laplace 0.5 grad u . grad u (laplace.rs:33-35); LinearElastic through F = I + (grad u)^T (lib.rs:78-84, 438-440)."""
+    if op == LAPLACE:
+        return 0.5 * float(np.sum(u_grad * u_grad))
+    mu, lam = params
+    d = u_grad.shape[0]
+    return linear_elastic_energy_density(np.eye(d) + u_grad.T, mu, lam)
+
+
+def element_elliptic_vector(elem_type: int, X_elem: np.ndarray, op: int, u_element: np.ndarray, weights, points, params_per_point) -> np.ndarray:
+    """assemble_element_elliptic_vector (elliptic.rs:456-526): output (s x n) += w |det J| (g^T J^{-T}) G_ref; returned node-major."""
+    n, ng, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    X = np.asarray(X_elem, dtype=np.float64)[:ng].T
+    U = np.asarray(u_element, dtype=np.float64).reshape(n, s).T  # s x n
+    out = np.zeros((s, n))
+    for w, xi, par in zip(weights, points, params_per_point):
+        J = reference_jacobian(elem_type, X, xi)
+        det = det_small(J)
+        inv = try_inverse_small(J)
+        if inv is None:
+            raise SingularJacobian()
+        j_inv_t = inv.T
+        G_ref = reference_gradients(elem_type, xi)
+        u_grad = volume_u_grad(j_inv_t, G_ref, U)
+        g_t = elliptic_operator_transpose(op, u_grad, par)
+        out += (w * abs(det)) * ((g_t @ j_inv_t) @ G_ref)
+    return out.T.reshape(-1)
+
+
+def element_elliptic_energy(elem_type: int, X_elem: np.ndarray, op: int, u_element: np.ndarray, weights, points, params_per_point) -> float:
+    """compute_element_elliptic_energy (elliptic.rs:545-605)."""
+    n, ng, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    X = np.asarray(X_elem, dtype=np.float64)[:ng].T
+    U = np.asarray(u_element, dtype=np.float64).reshape(n, s).T
+    integral = 0.0
+    for w, xi, par in zip(weights, points, params_per_point):
+        J = reference_jacobian(elem_type, X, xi)
+        det = det_small(J)
+        inv = try_inverse_small(J)
+        if inv is None:
+            raise SingularJacobian()
+        u_grad = volume_u_grad(inv.T, reference_gradients(elem_type, xi), U)
+        integral += w * abs(det) * elliptic_energy_density(op, u_grad, par)
+    return integral
+
+
+def assemble_elliptic_vector_serial(problem: "Problem", u: np.ndarray) -> np.ndarray:
+    """VectorAssembler::assemble_vector (global.rs:569-617) over an ElementEllipticAssembler."""
+    s = problem.sdim
+    U = np.asarray(u, dtype=np.float64).reshape(-1, s)
+    out = np.zeros(s * len(problem.vertices))
+    for e in range(len(problem.connectivity)):
+        nodes = problem.connectivity[e]
+        local = element_elliptic_vector(problem.elem_type, problem.vertices[nodes], problem.op, U[nodes].reshape(-1), problem.weights,
+                                        problem.points, problem.params_per_point)
+        for a, I in enumerate(nodes):
+            out[s * I:s * I + s] += local[s * a:s * a + s]
+    return out
+
+
+def assemble_elliptic_scalar(problem: "Problem", u: np.ndarray) -> float:
+    """assemble_scalar (global.rs:697-722): the element energies summed in element order."""
+    s = problem.sdim
+    U = np.asarray(u, dtype=np.float64).reshape(-1, s)
+    total = 0.0
+    for e in range(len(problem.connectivity)):
+        nodes = problem.connectivity[e]
+        total += element_elliptic_energy(problem.elem_type, problem.vertices[nodes], problem.op, U[nodes].reshape(-1), problem.weights,
+                                         problem.points, problem.params_per_point)
+    return total

@@ -131,3 +131,24 @@ def test_hex20_serendipity_element_restatement():
     import scipy.sparse as sp
     A = sp.csr_matrix((vals, ci.astype(np.int64), ro.astype(np.int64)), shape=(len(v20),) * 2)
     assert np.abs(A @ np.ones(len(v20))).max() < 1e-12 and abs(v20[:, 0] @ (A @ v20[:, 0]) - 1.0) < 1e-12  # int |grad x|^2 = 1
+
+
+def test_elliptic_vector_and_energy_restatement_tie_to_the_stiffness_matrix():
+    # elliptic.rs:440-605 restated; for the linear operators f(u) = K u and psi(u) = u.K u / 2 with the K of elliptic.rs:361-439
+    import scipy.sparse as sp
+    mu, lam = fo.lame_from_young_poisson(1e6, 0.2)
+    for et, mesh, op in [(fo.HEX8, fo.create_unit_box_uniform_hex_mesh_3d(2), fo.LINEAR_ELASTIC),
+                         (fo.QUAD4, fo.create_unit_square_uniform_quad_mesh_2d(3), fo.LAPLACE),
+                         (fo.TET4, fo.create_unit_box_uniform_tet_mesh_3d(1), fo.LINEAR_ELASTIC)]:
+        v, c = mesh
+        v = fo.jitter_vertices(v, 0.3, amp=0.1)
+        prob = fo.Problem(et, v, c.astype(np.int64), op, params=() if op == fo.LAPLACE else (mu, lam))
+        ro, ci, vals = fo.assemble_fast(prob)
+        n = len(ro) - 1
+        A = sp.csr_matrix((vals, ci.astype(np.int64), ro.astype(np.int64)), shape=(n, n))
+        u = np.random.default_rng(0).normal(size=n)
+        f, e = fo.assemble_elliptic_vector_serial(prob, u), fo.assemble_elliptic_scalar(prob, u)
+        assert np.abs(f - A @ u).max() < 1e-13 * np.abs(f).max() and abs(e - 0.5 * u @ (A @ u)) < 1e-13 * abs(e)
+    # the reference's energy known answers at a fixed deformation gradient (fenris-solid tests; materials KAT of tests/golden)
+    F = np.array([[1.0, 2.0], [3.0, 4.0]])
+    assert abs(fo.elliptic_energy_density(fo.LINEAR_ELASTIC, (F - np.eye(2)).T, (384.0, 577.0)) - fo.linear_elastic_energy_density(F, 384.0, 577.0)) < 1e-9
