@@ -270,14 +270,21 @@ class LinearElasticMaterial:
     pass
 
 
+class StVKMaterial:
+    """fenris-solid/src/materials.rs:355-469 (state-dependent: the assembler's u enters through F = I + (grad u)^T)."""
+
+
 class MaterialEllipticOperator:
     """Wraps a hyperelastic material as an elliptic operator (fenris-solid/src/lib.rs:412-508).
-    Only LinearElasticMaterial has a device specialisation; anything else raises (no CPU fallback)."""
+    LinearElasticMaterial and StVKMaterial have device specialisations; anything else raises (no CPU fallback)."""
 
     def __init__(self, material):
-        if not isinstance(material, LinearElasticMaterial) and material is not LinearElasticMaterial:
-            raise Fb200Error(nat.ERR_UNSUPPORTED, "only LinearElasticMaterial is specialised on the device (no CPU fallback)")
-        self.kind = nat.LINEAR_ELASTIC
+        if isinstance(material, LinearElasticMaterial) or material is LinearElasticMaterial:
+            self.kind = nat.LINEAR_ELASTIC
+        elif isinstance(material, StVKMaterial) or material is StVKMaterial:
+            self.kind = nat.STVK
+        else:
+            raise Fb200Error(nat.ERR_UNSUPPORTED, "only LinearElasticMaterial and StVKMaterial are specialised on the device (no CPU fallback)")
 
     def solution_dim(self, geometry_dim):
         return geometry_dim
@@ -641,7 +648,12 @@ class CsrAssembler:
                 mode = nat.SCATTER_ATOMIC
             self.ctx.assemble_mass_into_csr(ea.qtable.weights, ea.qtable.points, ea._density(), csr.values, scatter_mode=mode, accumulate=True)
             return
-        self.ctx.assemble_into_csr(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), csr.values, scatter_mode=mode, accumulate=True)
+        u = None
+        if ea.op.kind == nat.STVK:  # the state enters the contraction (elliptic.rs:393-399)
+            if mode == nat.SCATTER_GATHER:
+                mode = nat.SCATTER_ATOMIC
+            u = None if ea.u is None else np.asarray(ea.u, dtype=np.float64)
+        self.ctx.assemble_into_csr(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), csr.values, scatter_mode=mode, accumulate=True, u=u)
 
 
 class CsrParAssembler(CsrAssembler):

@@ -151,15 +151,20 @@ class Context:
         return nat.Operator(op_kind), q
 
     def assemble_into_csr_device(self, op_kind: int, weights, points, data=None, scatter_mode: int = nat.SCATTER_ATOMIC,
-                                 accumulate: bool = False):
+                                 accumulate: bool = False, u: Optional[np.ndarray] = None):
+        """u: the state of a non-linear operator (STVK; elliptic.rs:361-439 with u_grad), ignored by the linear ones."""
         op, q = self._structs(op_kind, weights, points, data)
-        self._check(self._lib.fb200_assemble_into_csr_device(self._h, C.byref(op), C.byref(q), None, scatter_mode, int(accumulate)))
+        uv = None if u is None else nat.as_f64(u).reshape(-1)
+        self._check(self._lib.fb200_assemble_into_csr_device(self._h, C.byref(op), C.byref(q), None if uv is None else nat.ptr(uv), scatter_mode,
+                                                             int(accumulate)))
 
     def assemble_into_csr(self, op_kind: int, weights, points, data, values: np.ndarray, scatter_mode: int = nat.SCATTER_ATOMIC,
-                          accumulate: bool = True):
+                          accumulate: bool = True, u: Optional[np.ndarray] = None):
         assert values.dtype == np.float64 and values.flags["C_CONTIGUOUS"] and values.size >= self.nnz
         op, q = self._structs(op_kind, weights, points, data)
-        self._check(self._lib.fb200_assemble_into_csr(self._h, C.byref(op), C.byref(q), None, scatter_mode, int(accumulate), nat.ptr(values)))
+        uv = None if u is None else nat.as_f64(u).reshape(-1)
+        self._check(self._lib.fb200_assemble_into_csr(self._h, C.byref(op), C.byref(q), None if uv is None else nat.ptr(uv), scatter_mode,
+                                                      int(accumulate), nat.ptr(values)))
         return values
 
     # -- mass matrix / source vector / physical points (SURVEY 8f rank 1)

@@ -262,6 +262,10 @@ void free_ordered(fb200_ctx* ctx);
 fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q);
 fb200_status read_errword(fb200_ctx* ctx);  // sync + translate deferred device errors
 
+// mass_source.cu: CSR assembly of a state-dependent operator (FB200_STVK) at the host vector u (NULL = zeros)
+fb200_status assemble_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int scatter_mode,
+                                      int accumulate);
+
 inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace fb200

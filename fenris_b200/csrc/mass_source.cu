@@ -45,7 +45,8 @@ __device__ __forceinline__ double det_small_dev(const double (&J)[d * d]) {
     return J[0] * c00 - J[1] * c01 + J[2] * c02;
 }
 
-template <int WHAT, int n, int ng, int d>  // WHAT: 0 mass matrix, 1 source vector, 2 physical points, 3 elliptic vector, 4 elliptic energy
+// WHAT: 0 mass matrix, 1 source vector, 2 physical points, 3 elliptic vector, 4 elliptic energy, 5 state-dependent elliptic matrix (StVK)
+template <int WHAT, int n, int ng, int d>
 __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     extern __shared__ double sm[];
     const int nq = p.nq, s = p.s;
@@ -62,12 +63,21 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     const double* t_gref = t_lam + nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     // per warp: X | scale | base (int64) | ids + row lengths (int32) | elliptic: u_e[n][s], A[nq][s][d]
-    const int warp_doubles = ng * d + nq + 2 * n + (n & 1) + (kElliptic ? n * s + nq * s * d : 0);
+    constexpr int kRec = 4 * d * d + 4;  // WHAT 5, per point: J^-1 | F | E | F F^T | alpha, mu, lambda, tr E
+    constexpr int kPairs = n * (n + 1) / 2;
+    const int warp_doubles = ng * d + nq + 2 * n + (n & 1) + (kElliptic ? n * s + nq * (WHAT == 5 ? kRec : s * d) : 0);
     // mass matrix of small elements: the products phi_I(q) phi_J(q) do not depend on the element - tabulated once per CTA as
     // pp[q][I n + J] (lane-contiguous: conflict-free), so that M_IJ = sum_q scale_q pp[q][IJ] costs one shared load per term
     constexpr bool kProducts = WHAT == 0 && n * n <= 128;
-    const int pp_len = kProducts ? nq * n * n : 0;
+    const int pp_len = kProducts ? nq * n * n : (WHAT == 5 ? (kPairs + 1) / 2 : 0);
     double* t_pp = sm + ((tab_len + 1) & ~1);
+    if constexpr (WHAT == 5) {  // node pairs I <= J of the upper block triangle (elliptic.rs:417-431), a | b << 8
+        int* pairs = reinterpret_cast<int*>(t_pp);
+        for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+            const int a = i / n, b = i - a * n;
+            if (a <= b) pairs[a * n - a * (a - 1) / 2 + (b - a)] = a | (b << 8);
+        }
+    }
     if constexpr (kProducts) {
         __syncthreads();
         for (int i = threadIdx.x; i < pp_len; i += blockDim.x) {
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
         for (int a = lane; a < n; a += 32) {
             const int id = p.conn[e * n + a];
             w_ids[a] = id;
-            if (WHAT == 0) {
+            if (WHAT == 0 || WHAT == 5) {
                 const long long o0 = p.blk_off[id], o1 = p.blk_off[id + 1];
                 w_base[a] = (long long)(s * s) * o0;
                 w_len[a] = (int)(o1 - o0) * s;
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                 const double det = det_small_dev<d>(J);
                 if (det == 0.0) {  // "Singular element Jacobian encountered" (elliptic.rs:493-497)
                     atomicMin(p.errword, ((unsigned long long)e << 8) | (unsigned long long)FB200_ERR_SINGULAR_JACOBIAN);
-                    for (int t = 0; t < s * d; ++t) w_A[q * s * d + t] = 0.0;
+                    for (int t = 0; t < (WHAT == 5 ? kRec : s * d); ++t) w_A[q * (WHAT == 5 ? kRec : s * d) + t] = 0.0;
                     continue;
                 }
                 if constexpr (d == 2) {
@@ -150,6 +160,38 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                         for (int m = 0; m < d; ++m) acc = fma(Ji[m * d + k], H[m * 3 + i], acc);  // (J^{-T})_{km} = Ji[m][k]
                         GU[k * 3 + i] = acc;
                     }
+                if constexpr (WHAT == 5) {
+                    // StVK state of the point (materials.rs:379-388): F = I + (grad u)^T, E = (F^T F - I) / 2, F F^T
+                    double* R = w_A + q * kRec;
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            R[i * d + j] = Ji[i * d + j];
+                            R[d * d + i * d + j] = (i == j ? 1.0 : 0.0) + GU[j * 3 + i];
+                        }
+                    double trE = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            double c = 0.0, b = 0.0;
+#pragma unroll
+                            for (int m = 0; m < d; ++m) {
+                                c = fma(R[d * d + m * d + i], R[d * d + m * d + j], c);
+                                b = fma(R[d * d + i * d + m], R[d * d + j * d + m], b);
+                            }
+                            const double Eij = 0.5 * (c - (i == j ? 1.0 : 0.0));
+                            R[2 * d * d + i * d + j] = Eij;
+                            R[3 * d * d + i * d + j] = b;
+                            if (i == j) trE += Eij;
+                        }
+                    R[4 * d * d] = t_w[q] * fabs(det);
+                    R[4 * d * d + 1] = t_mu[q];
+                    R[4 * d * d + 2] = t_lam[q];
+                    R[4 * d * d + 3] = trE;
+                    continue;
+                }
                 // g^T (s x d) and psi
                 double GT[3 * d], psi;
                 if (p.op == FB200_LAPLACE) {  // g = grad u, psi = |grad u|^2 / 2  (operators/laplace.rs:33-51)
@@ -160,6 +202,36 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                         psi = fma(GU[k * 3], GU[k * 3], psi);
                     }
                     psi *= 0.5;
+                } else if (p.op == FB200_STVK) {
+                    // StVKMaterial (materials.rs:400-415): psi = mu E:E + lambda tr(E)^2 / 2, P = F (2 mu E + lambda tr(E) I)
+                    double F[d * d], E[d * d];
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) F[i * d + j] = (i == j ? 1.0 : 0.0) + GU[j * 3 + i];
+                    double tr = 0.0, ee = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            double c = 0.0;
+#pragma unroll
+                            for (int m = 0; m < d; ++m) c = fma(F[m * d + i], F[m * d + j], c);
+                            E[i * d + j] = 0.5 * (c - (i == j ? 1.0 : 0.0));
+                            ee = fma(E[i * d + j], E[i * d + j], ee);
+                            if (i == j) tr += E[i * d + j];
+                        }
+                    const double mu = t_mu[q], lam = t_lam[q];
+                    psi = mu * ee + 0.5 * lam * tr * tr;
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            double c = 0.0;
+#pragma unroll
+                            for (int m = 0; m < d; ++m) c = fma(F[i * d + m], E[m * d + j], c);
+                            GT[i * d + j] = 2.0 * mu * c + lam * tr * F[i * d + j];
+                        }
                 } else {
                     // LinearElasticMaterial through F = I + (grad u)^T, eps = sym(F) - I  (fenris-solid lib.rs:20-29, materials.rs:72-95)
                     double eps[d * d];
@@ -206,10 +278,84 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                     if (p.plain) *dst += f;
                     else atomicAdd(dst, f);
                 }
-            } else {
+            } else if constexpr (WHAT == 4) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, o);
                 if (lane == 0) p.energies[k] = energy;
+            } else {
+                // K_IJ = sum_q alpha C(F_q; grad phi_I, grad phi_J) for I <= J (operators.rs:176-188 with the contraction of
+                // materials.rs:417-437), block (J, I) = K_IJ^T (clone_upper_to_lower, util.rs:38-50); one node pair per lane
+                const int* pairs = reinterpret_cast<const int*>(t_pp);
+                for (int t = lane; t < kPairs; t += 32) {
+                    const int a = pairs[t] & 0xff, b = pairs[t] >> 8;
+                    double C[d * d];
+#pragma unroll
+                    for (int i = 0; i < d * d; ++i) C[i] = 0.0;
+                    for (int q = 0; q < nq; ++q) {
+                        const double* R = w_A + q * kRec;
+                        double ga[d], gb[d], Fa[d], Fb[d], Eb[d];
+#pragma unroll
+                        for (int c = 0; c < d; ++c) {
+                            double xa = 0.0, xb = 0.0;
+#pragma unroll
+                            for (int m = 0; m < d; ++m) {  // grad phi = J^-T grad_ref phi
+                                xa = fma(R[m * d + c], t_gref[(q * n + a) * d + m], xa);
+                                xb = fma(R[m * d + c], t_gref[(q * n + b) * d + m], xb);
+                            }
+                            ga[c] = xa;
+                            gb[c] = xb;
+                        }
+                        double ab = 0.0, aEb = 0.0;
+#pragma unroll
+                        for (int i = 0; i < d; ++i) {
+                            double fa = 0.0, fb = 0.0, eb = 0.0;
+#pragma unroll
+                            for (int m = 0; m < d; ++m) {
+                                fa = fma(R[d * d + i * d + m], ga[m], fa);
+                                fb = fma(R[d * d + i * d + m], gb[m], fb);
+                                eb = fma(R[2 * d * d + i * d + m], gb[m], eb);
+                            }
+                            Fa[i] = fa;
+                            Fb[i] = fb;
+                            Eb[i] = eb;
+                            ab = fma(ga[i], gb[i], ab);
+                        }
+#pragma unroll
+                        for (int i = 0; i < d; ++i) aEb = fma(ga[i], Eb[i], aEb);
+                        const double alpha = R[4 * d * d], mu = R[4 * d * d + 1], lam = R[4 * d * d + 2], trE = R[4 * d * d + 3];
+                        const double diag = 2.0 * mu * aEb + lam * trE * ab;
+#pragma unroll
+                        for (int i = 0; i < d; ++i)
+#pragma unroll
+                            for (int j = 0; j < d; ++j) {
+                                const double c = (i == j ? diag : 0.0) + mu * Fb[i] * Fa[j] + lam * Fa[i] * Fb[j] + mu * ab * R[3 * d * d + i * d + j];
+                                C[i * d + j] = fma(alpha, c, C[i * d + j]);
+                            }
+                    }
+                    if (a == b) {  // diagonal block: the scalar upper triangle mirrored (clone_upper_to_lower, util.rs:38-50)
+#pragma unroll
+                        for (int i = 0; i < d; ++i)
+#pragma unroll
+                            for (int j = 0; j < i; ++j) C[i * d + j] = C[j * d + i];
+                    }
+                    const int kab = p.blockmap[e * (uint64_t)(n * n) + a * n + b], kba = p.blockmap[e * (uint64_t)(n * n) + b * n + a];
+                    double* rab = p.values + (w_base[a] + (long long)(d * kab));
+                    double* rba = p.values + (w_base[b] + (long long)(d * kba));
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            double* d0 = rab + (long long)i * w_len[a] + j;
+                            double* d1 = rba + (long long)j * w_len[b] + i;
+                            if (p.plain) {
+                                *d0 += C[i * d + j];
+                                if (a != b) *d1 += C[i * d + j];
+                            } else {
+                                atomicAdd(d0, C[i * d + j]);
+                                if (a != b) atomicAdd(d1, C[i * d + j]);
+                            }
+                        }
+                }
             }
             __syncwarp();
         }
@@ -318,8 +464,9 @@ static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
     p.ng = NG;
     p.d = D;
     const int tab_len = p.nq * (2 + NG * D + NG + N) + (WHAT >= 3 ? p.nq * (2 + N * D) : 0);
-    const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1) + (WHAT >= 3 ? N * p.s + p.nq * p.s * D : 0);
-    const int pp_len = (WHAT == 0 && N * N <= 128) ? p.nq * N * N : 0;  // products phi_I phi_J per point (see the kernel)
+    const int warp_doubles = NG * D + p.nq + 2 * N + (N & 1) + (WHAT >= 3 ? N * p.s + p.nq * (WHAT == 5 ? 4 * D * D + 4 : p.s * D) : 0);
+    // products phi_I phi_J per point (mass) / node pair list (state-dependent matrix): see the kernel
+    const int pp_len = (WHAT == 0 && N * N <= 128) ? p.nq * N * N : (WHAT == 5 ? (N * (N + 1) / 2 + 1) / 2 : 0);
     const size_t smem = sizeof(double) * (size_t)(((tab_len + 1) & ~1) + ((pp_len + 1) & ~1) + 4 * warp_doubles);
     auto kernel = mass_source_kernel<WHAT, N, NG, D>;
     if (smem > 48 * 1024) FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -442,13 +589,13 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* q, in
 // (global.rs:569-686) / assemble_scalar (global.rs:697-722)
 static fb200_status elliptic_common(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int* s_out) {
     FB200_TRY(ms_validate(ctx, q));
-    if (!op || (op->kind != FB200_LAPLACE && op->kind != FB200_LINEAR_ELASTIC))
+    if (!op || (op->kind != FB200_LAPLACE && op->kind != FB200_LINEAR_ELASTIC && op->kind != FB200_STVK))
         return fail(ctx, FB200_ERR_UNSUPPORTED, "operator has no device specialisation (no CPU fallback)");
-    if (op->kind == FB200_LINEAR_ELASTIC && !q->data) return fail(ctx, FB200_ERR_SHAPE, "linear elasticity needs Lame data per point");
+    if (op->kind != FB200_LAPLACE && !q->data) return fail(ctx, FB200_ERR_SHAPE, "elastic materials need Lame data per point");
     if (!u) return fail(ctx, FB200_ERR_SHAPE, "null u");
     if (ctx->ragged) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    FB200_TRY(ms_tables(ctx, q, op->kind == FB200_LINEAR_ELASTIC ? 2 : 0));
+    FB200_TRY(ms_tables(ctx, q, op->kind != FB200_LAPLACE ? 2 : 0));
     const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;
     const uint64_t len = (uint64_t)s * ctx->N;
     if (ctx->source_capacity < len) {
@@ -536,6 +683,37 @@ fb200_status fb200_assemble_elliptic_scalar(fb200_ctx* ctx, const fb200_operator
     cudaFree(d_e);
     return st;
 }
+
+}  // extern "C"
+
+// ElementEllipticAssembler as ElementMatrixAssembler with a state-dependent contraction (elliptic.rs:361-439 with u_grad, operators.rs:
+// 176-188): the tangent stiffness of StVKMaterial at u.  Called by fb200_assemble_into_csr_device for FB200_STVK.
+fb200_status fb200::assemble_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
+                                             int scatter_mode, int accumulate) {
+    if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
+    if (ctx->ragged || !ctx->d_blockmap) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
+    if (ctx->ei.d != ctx->sdim) return fail(ctx, FB200_ERR_SHAPE, "pattern solution_dim does not match the operator");
+    std::vector<double> zeros;
+    if (!u) {  // NULL = zeros (fb200_assemble_into_csr): the tangent at the undeformed state
+        zeros.assign((size_t)ctx->sdim * ctx->N + 1, 0.0);
+        u = zeros.data();
+    }
+    int s = 0;
+    FB200_TRY(elliptic_common(ctx, op, q, u, &s));
+    if (!zeros.empty()) FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the copy reads pageable memory that dies here
+    if (!accumulate) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = s;
+    p.op = op->kind;
+    p.u = ctx->d_source;
+    p.values = ctx->d_values;
+    p.errword = ctx->d_errword;
+    return ms_launch<5>(ctx, p, scatter_mode);
+}
+
+extern "C" {
 
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* q, double* out) {
     FB200_TRY(ms_validate(ctx, q));

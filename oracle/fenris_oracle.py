@@ -1226,3 +1226,102 @@ def assemble_elliptic_scalar(problem: "Problem", u: np.ndarray) -> float:
         total += element_elliptic_energy(problem.elem_type, problem.vertices[nodes], problem.op, U[nodes].reshape(-1), problem.weights,
                                          problem.points, problem.params_per_point)
     return total
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a non-linear material - St. Venant-Kirchhoff (fenris-solid/src/materials.rs:355-469) with u != 0
+# ------------------------------------------------------------------------------------------------------------------------
+STVK = 3
+
+
+def _green_strain(F: np.ndarray) -> np.ndarray:
+    """materials.rs:379-388: E = (F^T F - I) / 2."""
+    return (F.T @ F - np.eye(F.shape[0])) * 0.5
+
+
+def stvk_energy_density(F: np.ndarray, mu: float, lam: float) -> float:
+    """materials.rs:400-404."""
+    E = _green_strain(F)
+    return mu * float(np.sum(E * E)) + 0.5 * lam * float(np.trace(E)) ** 2
+
+
+def stvk_stress(F: np.ndarray, mu: float, lam: float) -> np.ndarray:
+    """materials.rs:406-415: P = 2 mu F E + lambda tr(E) F."""
+    E = _green_strain(F)
+    return F @ E * 2.0 * mu + F * lam * np.trace(E)
+
+
+def stvk_contraction(F: np.ndarray, a: np.ndarray, b: np.ndarray, mu: float, lam: float) -> np.ndarray:
+    """materials.rs:417-437: C = I (2 mu a.E b + lambda tr(E) a.b) + mu Fb Fa^T + lambda Fa Fb^T + mu (a.b) F F^T."""
+    d = F.shape[0]
+    E = _green_strain(F)
+    a_dot_b = float(a @ b)
+    Fa, Fb, Eb = F @ a, F @ b, E @ b
+    return (np.eye(d) * (2.0 * mu * float(a @ Eb) + lam * np.trace(E) * a_dot_b) + np.outer(Fb, Fa) * mu + np.outer(Fa, Fb) * lam
+            + F @ F.T * mu * a_dot_b)
+
+
+_elliptic_operator_transpose_linear = elliptic_operator_transpose
+_elliptic_energy_density_linear = elliptic_energy_density
+
+
+def elliptic_operator_transpose(op: int, u_grad: np.ndarray, params) -> np.ndarray:  # noqa: F811 (extends the linear version with STVK)
+    if op == STVK:
+        return stvk_stress(np.eye(u_grad.shape[0]) + u_grad.T, params[0], params[1])
+    return _elliptic_operator_transpose_linear(op, u_grad, params)
+
+
+def elliptic_energy_density(op: int, u_grad: np.ndarray, params) -> float:  # noqa: F811
+    if op == STVK:
+        return stvk_energy_density(np.eye(u_grad.shape[0]) + u_grad.T, params[0], params[1])
+    return _elliptic_energy_density_linear(op, u_grad, params)
+
+
+def contract_u(op: int, u_grad: np.ndarray, a: np.ndarray, b: np.ndarray, params) -> np.ndarray:
+    """EllipticContraction::contract with the state: MaterialEllipticOperator::contract = compute_stress_contraction_du
+    (fenris-solid lib.rs:480-489, 140-151: F = I + (grad u)^T); the linear operators ignore u."""
+    if op == STVK:
+        return stvk_contraction(np.eye(u_grad.shape[0]) + u_grad.T, a, b, params[0], params[1])
+    return contract(op, a, b, params)
+
+
+def element_matrix_u(elem_type: int, X_elem: np.ndarray, op: int, u_element: np.ndarray, weights, points, params_per_point) -> np.ndarray:
+    """assemble_element_elliptic_matrix (elliptic.rs:361-439) INCLUDING the state: grad u per point (compute_volume_u_grad), upper
+    blocks I <= J of K += scale * contract(grad u, grad phi_I, grad phi_J) (operators.rs:176-188), then clone_upper_to_lower."""
+    n, ng, d = element_info(elem_type)
+    s = d if op in (LINEAR_ELASTIC, STVK) else 1
+    X = np.asarray(X_elem, dtype=np.float64)[:ng].T
+    U = np.asarray(u_element, dtype=np.float64).reshape(n, s).T
+    K = np.zeros((s * n, s * n))
+    for w, xi, par in zip(weights, points, params_per_point):
+        J = reference_jacobian(elem_type, X, xi)
+        det = det_small(J)
+        inv = try_inverse_small(J)
+        if inv is None:
+            raise SingularJacobian()
+        j_inv_t = inv.T
+        G_ref = reference_gradients(elem_type, xi)
+        u_grad = volume_u_grad(j_inv_t, G_ref, U)
+        G = j_inv_t @ G_ref
+        scale = w * abs(det)
+        for I in range(n):
+            for Jn in range(I, n):
+                K[s * I:s * I + s, s * Jn:s * Jn + s] += scale * contract_u(op, u_grad, G[:, I], G[:, Jn], par)
+    iu = np.triu_indices(s * n, 1)
+    K[(iu[1], iu[0])] = K[iu]
+    return K
+
+
+def assemble_matrix_u_serial(elem_type: int, vertices, connectivity, op: int, u: np.ndarray, weights, points, params_per_point):
+    """CsrAssembler::assemble (global.rs:124-182) with a state-dependent operator."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    _, _, d = element_info(elem_type)
+    s = d if op in (LINEAR_ELASTIC, STVK) else 1
+    Uall = np.asarray(u, dtype=np.float64).reshape(-1, s)
+    ro, ci = assemble_pattern(s, len(V), conn.tolist())
+    values = np.zeros(len(ci))
+    for e in range(len(conn)):
+        K = element_matrix_u(elem_type, V[conn[e]], op, Uall[conn[e]].reshape(-1), weights, points, params_per_point)
+        scatter_element(values, ro, ci, s, conn[e].tolist(), K)
+    return ro, ci, values

@@ -27,6 +27,13 @@ def measure_mass_or_vector(what, steps, peak):
             fn = lambda: ctx.assemble_mass_into_csr_device(w, p, 1000.0, accumulate=False)
             b_algo = 4 * 8 * E + 8 * 3 * N + 4 * 64 * E + 16 * nnz
             name = "Hex8 mass matrix (s = 3, Gauss 3^3) on the C3 mesh, device-resident CSR"
+        elif what == "stvk":  # tangent stiffness of StVKMaterial at u (u is copied host -> device inside the step)
+            w, p = fo.hexahedron_gauss(2)
+            nrows, nnz = ctx.assemble_pattern(3)
+            u = 0.01 * np.random.default_rng(0).normal(size=3 * N)
+            fn = lambda: ctx.assemble_into_csr_device(fb.STVK, w, p, (3.0e5, 2.0e5), accumulate=False, u=u)
+            b_algo = 4 * 8 * E + 8 * 3 * N + 8 * 3 * N + 4 * 64 * E + 16 * nnz
+            name = "Hex8 StVK tangent stiffness at u (Gauss 2^3) on the C3 mesh, device-resident CSR"
         else:
             w, p = fo.hexahedron_gauss(2)
             nnz = 0
@@ -104,7 +111,7 @@ def main():
         elif cfg == "cg":  # Jacobi-PCG iterations on the device-resident C3 elasticity matrix
             measure_cg(peak)
             continue
-        elif cfg in ("mass", "vector"):  # SURVEY 8f rank 1 on the C3 mesh: mass matrix (s = 3, Gauss 3^3) / source vector (Gauss 2^3)
+        elif cfg in ("mass", "vector", "stvk"):  # SURVEY 8f rank 1 on the C3 mesh: mass matrix (s = 3, Gauss 3^3) / source vector (Gauss 2^3)
             measure_mass_or_vector(cfg, args.steps, peak)
             continue
         else:

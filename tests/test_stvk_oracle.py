@@ -1,0 +1,86 @@
+"""Pins the StVK restatement (oracle/fenris_oracle.py, SURVEY 8(f) rank 4 - a non-linear material) to the reference's own tests:
+golden energies of fenris-solid/tests/unit_tests/materials.rs:299-315 (fixtures of tests/unit_tests/mod.rs:11-29), stress = dpsi/dF and
+contraction = a.dP/dF.b by central differences (materials.rs:10-120, 317-330), and the assembled tangent K(u) = df/du."""
+import numpy as np
+import pytest
+
+from oracle import fenris_oracle as fo
+
+MU, LAM = 384.0, 577.0  # lame_parameters(), mod.rs:11-16
+F2 = np.array([[2.0, 1.0], [3.0, 4.0]])  # deformation_gradient_2d, mod.rs:18-22
+F3 = np.array([[2.0, 1.0, 3.0], [4.0, 6.0, 5.0], [2.0, 8.0, 9.0]])  # deformation_gradient_3d, mod.rs:24-29
+
+
+def test_stvk_golden_strain_energies():
+    assert fo.stvk_energy_density(F2, MU, LAM) == 132578.0  # materials.rs:300-306
+    assert fo.stvk_energy_density(F3, MU, LAM) == 9136789.125  # materials.rs:309-315
+
+
+@pytest.mark.parametrize("F", [F2, F3])
+def test_stvk_stress_and_contraction_by_finite_differences(F):
+    d, h = F.shape[0], 1e-5
+    P = fo.stvk_stress(F, MU, LAM)
+    Pfd = np.zeros((d, d))
+    for i in range(d):
+        for j in range(d):
+            D = np.zeros((d, d))
+            D[i, j] = h
+            Pfd[i, j] = (fo.stvk_energy_density(F + D, MU, LAM) - fo.stvk_energy_density(F - D, MU, LAM)) / (2 * h)
+    assert np.abs(P - Pfd).max() < 1e-6 * np.abs(P).max()
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=d), rng.normal(size=d)
+    # contraction C_ij = a_k dP_ik / dF_jm b_m  (HyperelasticMaterial::compute_stress_contraction, fenris-solid lib.rs)
+    Cfd = np.zeros((d, d))
+    for j in range(d):
+        for m in range(d):
+            D = np.zeros((d, d))
+            D[j, m] = h
+            dP = (fo.stvk_stress(F + D, MU, LAM) - fo.stvk_stress(F - D, MU, LAM)) / (2 * h)
+            Cfd[:, j] += (dP @ a) * b[m]
+    C = fo.stvk_contraction(F, a, b, MU, LAM)
+    assert np.abs(C - Cfd).max() < 1e-6 * np.abs(C).max()
+    # contraction(b, a) = contraction(a, b)^T: what clone_upper_to_lower relies on (elliptic.rs:433-436)
+    assert np.abs(fo.stvk_contraction(F, b, a, MU, LAM) - C.T).max() < 1e-12 * np.abs(C).max()
+
+
+def test_stvk_at_the_reference_state_is_linear_elasticity():
+    rng = np.random.default_rng(5)
+    for d in (2, 3):
+        a, b = rng.normal(size=d), rng.normal(size=d)
+        assert np.allclose(fo.stvk_contraction(np.eye(d), a, b, MU, LAM), fo.contract(fo.LINEAR_ELASTIC, a, b, (MU, LAM)), rtol=1e-14, atol=1e-12)
+    v, c = fo.create_unit_square_uniform_quad_mesh_2d(3)
+    prob = fo.Problem(fo.QUAD4, v, c, fo.STVK, params=(MU, LAM))
+    lin = fo.Problem(fo.QUAD4, v, c, fo.LINEAR_ELASTIC, params=(MU, LAM))
+    _, _, k0 = fo.assemble_matrix_u_serial(fo.QUAD4, v, c, fo.STVK, np.zeros(2 * len(v)), prob.weights, prob.points, prob.params_per_point)
+    _, _, kl = fo.assemble_serial(lin)
+    assert fo.rel_frobenius(k0, kl) < 1e-14
+
+
+@pytest.mark.parametrize("et,mesh", [(fo.QUAD4, "quad"), (fo.HEX8, "hex"), (fo.TET4, "tet")])
+def test_stvk_tangent_is_the_derivative_of_the_element_vector(et, mesh):
+    # the commented-out reference tests (tests/unit_tests/assembly.rs:385-470) check exactly this with h = 1e-6
+    v, c = {"quad": fo.create_unit_square_uniform_quad_mesh_2d, "hex": fo.create_unit_box_uniform_hex_mesh_3d,
+            "tet": fo.create_unit_box_uniform_tet_mesh_3d}[mesh](1)
+    prob = fo.Problem(et, v, c, fo.STVK, params=(2.0, 3.0))
+    n, _, d = fo.element_info(et)
+    u = 0.2 * np.random.default_rng(9).normal(size=n * d)
+    X = v[c[0]]
+    K = fo.element_matrix_u(et, X, fo.STVK, u, prob.weights, prob.points, prob.params_per_point)
+    Kfd = np.zeros_like(K)
+    h = 1e-6
+    for k in range(n * d):
+        D = np.zeros(n * d)
+        D[k] = h
+        Kfd[:, k] = (fo.element_elliptic_vector(et, X, fo.STVK, u + D, prob.weights, prob.points, prob.params_per_point)
+                     - fo.element_elliptic_vector(et, X, fo.STVK, u - D, prob.weights, prob.points, prob.params_per_point)) / (2 * h)
+    assert np.abs(K - Kfd).max() < 1e-7 * np.abs(K).max()
+    assert np.array_equal(K, K.T)
+    # the element vector is the derivative of the element energy
+    f = fo.element_elliptic_vector(et, X, fo.STVK, u, prob.weights, prob.points, prob.params_per_point)
+    ffd = np.zeros_like(f)
+    for k in range(n * d):
+        D = np.zeros(n * d)
+        D[k] = h
+        ffd[k] = (fo.element_elliptic_energy(et, X, fo.STVK, u + D, prob.weights, prob.points, prob.params_per_point)
+                  - fo.element_elliptic_energy(et, X, fo.STVK, u - D, prob.weights, prob.points, prob.params_per_point)) / (2 * h)
+    assert np.abs(f - ffd).max() < 1e-7 * np.abs(f).max()
