@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fenris_b200.h")
 
 # element / operator / scatter ids (include/fenris_b200.h)
 QUAD4, TET4, HEX8, HEX27, TET10, HEX20 = 1, 2, 3, 4, 5, 6
-LAPLACE, LINEAR_ELASTIC, STVK = 1, 2, 3
+LAPLACE, LINEAR_ELASTIC, STVK, NEO_HOOKEAN = 1, 2, 3, 4
 SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
 
 OK = 0

@@ -274,17 +274,23 @@ class StVKMaterial:
     """fenris-solid/src/materials.rs:355-469 (state-dependent: the assembler's u enters through F = I + (grad u)^T)."""
 
 
+class NeoHookeanMaterial:
+    """fenris-solid/src/materials.rs:232-353 (state-dependent; det F <= 0 gives NaN / +inf as in the reference)."""
+
+
 class MaterialEllipticOperator:
     """Wraps a hyperelastic material as an elliptic operator (fenris-solid/src/lib.rs:412-508).
-    LinearElasticMaterial and StVKMaterial have device specialisations; anything else raises (no CPU fallback)."""
+    LinearElasticMaterial, StVKMaterial and NeoHookeanMaterial have device specialisations; anything else raises (no CPU fallback)."""
 
     def __init__(self, material):
         if isinstance(material, LinearElasticMaterial) or material is LinearElasticMaterial:
             self.kind = nat.LINEAR_ELASTIC
         elif isinstance(material, StVKMaterial) or material is StVKMaterial:
             self.kind = nat.STVK
+        elif isinstance(material, NeoHookeanMaterial) or material is NeoHookeanMaterial:
+            self.kind = nat.NEO_HOOKEAN
         else:
-            raise Fb200Error(nat.ERR_UNSUPPORTED, "only LinearElasticMaterial and StVKMaterial are specialised on the device (no CPU fallback)")
+            raise Fb200Error(nat.ERR_UNSUPPORTED, "material has no device specialisation (no CPU fallback)")
 
     def solution_dim(self, geometry_dim):
         return geometry_dim
@@ -649,7 +655,7 @@ class CsrAssembler:
             self.ctx.assemble_mass_into_csr(ea.qtable.weights, ea.qtable.points, ea._density(), csr.values, scatter_mode=mode, accumulate=True)
             return
         u = None
-        if ea.op.kind == nat.STVK:  # the state enters the contraction (elliptic.rs:393-399)
+        if ea.op.kind in (nat.STVK, nat.NEO_HOOKEAN):  # the state enters the contraction (elliptic.rs:393-399)
             if mode == nat.SCATTER_GATHER:
                 mode = nat.SCATTER_ATOMIC
             u = None if ea.u is None else np.asarray(ea.u, dtype=np.float64)

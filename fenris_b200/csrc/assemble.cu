@@ -1078,8 +1078,8 @@ extern "C" {
 
 fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
                                             int32_t scatter_mode, int32_t accumulate) {
-    // linear operators: K does not depend on u (laplace.rs:62, materials.rs:110); StVK: tangent stiffness at u (mass_source.cu)
-    if (ctx && op && op->kind == FB200_STVK) return assemble_state_dependent(ctx, op, q, u, scatter_mode, accumulate);
+    // linear operators: K does not depend on u (laplace.rs:62, materials.rs:110); StVK / NeoHookean: tangent stiffness at u (mass_source.cu)
+    if (ctx && op && (op->kind == FB200_STVK || op->kind == FB200_NEO_HOOKEAN)) return assemble_state_dependent(ctx, op, q, u, scatter_mode, accumulate);
     FB200_TRY(validate(ctx, op, q));
     if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
     const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;

@@ -45,7 +45,37 @@ __device__ __forceinline__ double det_small_dev(const double (&J)[d * d]) {
     return J[0] * c00 - J[1] * c01 + J[2] * c02;
 }
 
-// WHAT: 0 mass matrix, 1 source vector, 2 physical points, 3 elliptic vector, 4 elliptic energy, 5 state-dependent elliptic matrix (StVK)
+// inverse from the cofactors and the determinant (nalgebra try_inverse, 2 x 2 and 3 x 3 closed forms)
+template <int d>
+__device__ __forceinline__ void inverse_small_dev(const double (&J)[d * d], double det, double (&Ji)[d * d]) {
+    if constexpr (d == 2) {
+        Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
+    } else {
+        Ji[0] = (J[4] * J[8] - J[7] * J[5]) / det; Ji[1] = (J[2] * J[7] - J[8] * J[1]) / det; Ji[2] = (J[1] * J[5] - J[4] * J[2]) / det;
+        Ji[3] = -(J[3] * J[8] - J[6] * J[5]) / det; Ji[4] = (J[0] * J[8] - J[6] * J[2]) / det; Ji[5] = (J[2] * J[3] - J[5] * J[0]) / det;
+        Ji[6] = (J[3] * J[7] - J[6] * J[4]) / det; Ji[7] = (J[1] * J[6] - J[7] * J[0]) / det; Ji[8] = (J[0] * J[4] - J[3] * J[1]) / det;
+    }
+}
+
+// NeoHookeanMaterial (fenris-solid/src/materials.rs:267-318): F^-T and alpha = -mu + lambda log J; NaN for J <= 0 as the reference returns
+template <int d>
+__device__ __forceinline__ double neo_hookean_state(const double (&F)[d * d], double mu, double lam, double (&FinvT)[d * d]) {
+    const double Jd = det_small_dev<d>(F);
+    if (!(Jd > 0.0)) {
+#pragma unroll
+        for (int i = 0; i < d * d; ++i) FinvT[i] = __longlong_as_double(0x7ff8000000000000ll);
+        return __longlong_as_double(0x7ff8000000000000ll);
+    }
+    double Fi[d * d];
+    inverse_small_dev<d>(F, Jd, Fi);
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+#pragma unroll
+        for (int j = 0; j < d; ++j) FinvT[i * d + j] = Fi[j * d + i];
+    return -mu + lam * log(Jd);
+}
+
+// WHAT: 0 mass matrix, 1 source vector, 2 physical points, 3 elliptic vector, 4 elliptic energy, 5 state-dependent elliptic matrix (StVK, NeoHookean)
 template <int WHAT, int n, int ng, int d>
 __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     extern __shared__ double sm[];
@@ -137,13 +167,7 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                     for (int t = 0; t < (WHAT == 5 ? kRec : s * d); ++t) w_A[q * (WHAT == 5 ? kRec : s * d) + t] = 0.0;
                     continue;
                 }
-                if constexpr (d == 2) {
-                    Ji[0] = J[3] / det; Ji[1] = -J[1] / det; Ji[2] = -J[2] / det; Ji[3] = J[0] / det;
-                } else {
-                    Ji[0] = (J[4] * J[8] - J[7] * J[5]) / det; Ji[1] = (J[2] * J[7] - J[8] * J[1]) / det; Ji[2] = (J[1] * J[5] - J[4] * J[2]) / det;
-                    Ji[3] = -(J[3] * J[8] - J[6] * J[5]) / det; Ji[4] = (J[0] * J[8] - J[6] * J[2]) / det; Ji[5] = (J[2] * J[3] - J[5] * J[0]) / det;
-                    Ji[6] = (J[3] * J[7] - J[6] * J[4]) / det; Ji[7] = (J[1] * J[6] - J[7] * J[0]) / det; Ji[8] = (J[0] * J[4] - J[3] * J[1]) / det;
-                }
+                inverse_small_dev<d>(J, det, Ji);
                 // grad u = J^{-T} sum_I grad_ref phi_I (x) u_I   (d x s, compute_volume_u_grad, elliptic.rs:25-59)
                 double H[d * 3], GU[d * 3];  // s <= 3
 #pragma unroll
@@ -170,6 +194,18 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                             R[i * d + j] = Ji[i * d + j];
                             R[d * d + i * d + j] = (i == j ? 1.0 : 0.0) + GU[j * 3 + i];
                         }
+                    R[4 * d * d] = t_w[q] * fabs(det);
+                    R[4 * d * d + 1] = t_mu[q];
+                    R[4 * d * d + 2] = t_lam[q];
+                    if (p.op == FB200_NEO_HOOKEAN) {  // F^-T replaces E, alpha_nh replaces tr E
+                        double F[d * d], T[d * d];
+#pragma unroll
+                        for (int i = 0; i < d * d; ++i) F[i] = R[d * d + i];
+                        R[4 * d * d + 3] = neo_hookean_state<d>(F, t_mu[q], t_lam[q], T);
+#pragma unroll
+                        for (int i = 0; i < d * d; ++i) R[2 * d * d + i] = T[i];
+                        continue;
+                    }
                     double trE = 0.0;
 #pragma unroll
                     for (int i = 0; i < d; ++i)
@@ -186,9 +222,6 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                             R[3 * d * d + i * d + j] = b;
                             if (i == j) trE += Eij;
                         }
-                    R[4 * d * d] = t_w[q] * fabs(det);
-                    R[4 * d * d + 1] = t_mu[q];
-                    R[4 * d * d + 2] = t_lam[q];
                     R[4 * d * d + 3] = trE;
                     continue;
                 }
@@ -232,6 +265,39 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                             for (int m = 0; m < d; ++m) c = fma(F[i * d + m], E[m * d + j], c);
                             GT[i * d + j] = 2.0 * mu * c + lam * tr * F[i * d + j];
                         }
+                } else if (p.op == FB200_NEO_HOOKEAN) {
+                    // NeoHookeanMaterial: psi = mu tr(E) - mu log J + lambda (log J)^2 / 2 with log J = log1p(gamma) (materials.rs:251-265,
+                    // logdet.rs:37-86; +inf when det F <= 0), P = F^-T (-mu + lambda log J) + mu F (materials.rs:267-289)
+                    double F[d * d], T[d * d], U[d * d];
+#pragma unroll
+                    for (int i = 0; i < d; ++i)
+#pragma unroll
+                        for (int j = 0; j < d; ++j) {
+                            U[i * d + j] = GU[j * 3 + i];
+                            F[i * d + j] = (i == j ? 1.0 : 0.0) + GU[j * 3 + i];
+                        }
+                    double gamma, trU = 0.0, uu = 0.0;
+                    if constexpr (d == 2) {
+                        gamma = U[0] * U[3] + U[0] + U[3] - U[1] * U[2];
+                    } else {
+                        const double u11 = U[0], u22 = U[4], u33 = U[8], a = 1.0 + u11, e = 1.0 + u22, ii = 1.0 + u33;
+                        gamma = u11 * u22 * u33 + u11 * u22 + u11 * u33 + u22 * u33 + u11 + u22 + u33 + U[1] * U[5] * U[6] + U[2] * U[3] * U[7] -
+                                U[2] * e * U[6] - U[1] * U[3] * ii - a * U[5] * U[7];
+                    }
+#pragma unroll
+                    for (int i = 0; i < d; ++i) trU += U[i * d + i];
+#pragma unroll
+                    for (int i = 0; i < d * d; ++i) uu = fma(U[i], U[i], uu);
+                    const double mu = t_mu[q], lam = t_lam[q];
+                    if (gamma > -1.0) {
+                        const double logJ = log1p(gamma);
+                        psi = mu * (trU + 0.5 * uu) - mu * logJ + 0.5 * lam * logJ * logJ;
+                    } else {
+                        psi = __longlong_as_double(0x7ff0000000000000ll);
+                    }
+                    const double anh = neo_hookean_state<d>(F, mu, lam, T);
+#pragma unroll
+                    for (int i = 0; i < d * d; ++i) GT[i] = T[i] * anh + F[i] * mu;
                 } else {
                     // LinearElasticMaterial through F = I + (grad u)^T, eps = sym(F) - I  (fenris-solid lib.rs:20-29, materials.rs:72-95)
                     double eps[d * d];
@@ -305,6 +371,31 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                             ga[c] = xa;
                             gb[c] = xb;
                         }
+                        const double alpha = R[4 * d * d], mu = R[4 * d * d + 1], lam = R[4 * d * d + 2], trE = R[4 * d * d + 3];
+                        if (p.op == FB200_NEO_HOOKEAN) {
+                            // C = lambda (F^-T a)(F^-T b)^T - alpha_nh (F^-T b)(F^-T a)^T + mu (a.b) I   (materials.rs:291-318)
+                            double Ta[d], Tb[d], dot = 0.0;
+#pragma unroll
+                            for (int i = 0; i < d; ++i) {
+                                double ta = 0.0, tb = 0.0;
+#pragma unroll
+                                for (int m = 0; m < d; ++m) {
+                                    ta = fma(R[2 * d * d + i * d + m], ga[m], ta);
+                                    tb = fma(R[2 * d * d + i * d + m], gb[m], tb);
+                                }
+                                Ta[i] = ta;
+                                Tb[i] = tb;
+                                dot = fma(ga[i], gb[i], dot);
+                            }
+#pragma unroll
+                            for (int i = 0; i < d; ++i)
+#pragma unroll
+                                for (int j = 0; j < d; ++j) {
+                                    const double c = lam * Ta[i] * Tb[j] - trE * Tb[i] * Ta[j] + (i == j ? mu * dot : 0.0);
+                                    C[i * d + j] = fma(alpha, c, C[i * d + j]);
+                                }
+                            continue;
+                        }
                         double ab = 0.0, aEb = 0.0;
 #pragma unroll
                         for (int i = 0; i < d; ++i) {
@@ -322,7 +413,6 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                         }
 #pragma unroll
                         for (int i = 0; i < d; ++i) aEb = fma(ga[i], Eb[i], aEb);
-                        const double alpha = R[4 * d * d], mu = R[4 * d * d + 1], lam = R[4 * d * d + 2], trE = R[4 * d * d + 3];
                         const double diag = 2.0 * mu * aEb + lam * trE * ab;
 #pragma unroll
                         for (int i = 0; i < d; ++i)
@@ -589,7 +679,7 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* q, in
 // (global.rs:569-686) / assemble_scalar (global.rs:697-722)
 static fb200_status elliptic_common(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int* s_out) {
     FB200_TRY(ms_validate(ctx, q));
-    if (!op || (op->kind != FB200_LAPLACE && op->kind != FB200_LINEAR_ELASTIC && op->kind != FB200_STVK))
+    if (!op || (op->kind != FB200_LAPLACE && op->kind != FB200_LINEAR_ELASTIC && op->kind != FB200_STVK && op->kind != FB200_NEO_HOOKEAN))
         return fail(ctx, FB200_ERR_UNSUPPORTED, "operator has no device specialisation (no CPU fallback)");
     if (op->kind != FB200_LAPLACE && !q->data) return fail(ctx, FB200_ERR_SHAPE, "elastic materials need Lame data per point");
     if (!u) return fail(ctx, FB200_ERR_SHAPE, "null u");

@@ -62,8 +62,10 @@ enum {
     FB200_LAPLACE = 1,        /* LaplaceOperator, src/assembly/operators/laplace.rs:14,60-72; Parameters = () */
     FB200_LINEAR_ELASTIC = 2, /* MaterialEllipticOperator<LinearElasticMaterial>, fenris-solid/src/lib.rs:412-508,
                                  materials.rs:108-122; Parameters = LameParameters{mu, lambda} */
-    FB200_STVK = 3            /* MaterialEllipticOperator<StVKMaterial>, fenris-solid/src/materials.rs:355-469: state-dependent (F = I +
+    FB200_STVK = 3,           /* MaterialEllipticOperator<StVKMaterial>, fenris-solid/src/materials.rs:355-469: state-dependent (F = I +
                                  (grad u)^T); Parameters = LameParameters; uniform quadrature tables only */
+    FB200_NEO_HOOKEAN = 4     /* MaterialEllipticOperator<NeoHookeanMaterial>, materials.rs:232-353 (log J through logdet.rs:17-86); as STVK;
+                                 det F <= 0 gives NaN stress / contraction and +inf energy, as in the reference */
 };
 
 /* How element contributions reach the CSR values. All three give the same sums up to fp reassociation. */
@@ -87,7 +89,7 @@ typedef struct fb200_quadrature {
 } fb200_quadrature;
 
 typedef struct fb200_operator {
-    int32_t kind; /* FB200_LAPLACE | FB200_LINEAR_ELASTIC | FB200_STVK */
+    int32_t kind; /* FB200_LAPLACE | FB200_LINEAR_ELASTIC | FB200_STVK | FB200_NEO_HOOKEAN */
 } fb200_operator;
 
 /* ---- lifetime / errors ------------------------------------------------------------------ */
@@ -147,7 +149,8 @@ fb200_status fb200_colors_adopt(fb200_ctx* ctx, uint64_t num_colors, const uint6
 /* u: global solution vector (solution_dim * num_nodes, host) or NULL (= zeros, as the reference's linear call sites pass).
  *    LAPLACE / LINEAR_ELASTIC do not depend on u (laplace.rs:62, materials.rs:110) and take the tuned stiffness kernels; STVK assembles the
  *    tangent stiffness at u (elliptic.rs:361-439 with u_grad per point; contraction C = I (2 mu a.Eb + lambda tr(E) a.b) + mu Fb Fa^T +
- *    lambda Fa Fb^T + mu (a.b) F F^T, fenris-solid/src/materials.rs:417-437) with the ATOMIC or COLORED scatter.
+ *    lambda Fa Fb^T + mu (a.b) F F^T, fenris-solid/src/materials.rs:417-437), NEO_HOOKEAN likewise (C = lambda (F^-T a)(F^-T b)^T -
+ *    alpha (F^-T b)(F^-T a)^T + mu (a.b) I, alpha = -mu + lambda log J, materials.rs:291-318), with the ATOMIC or COLORED scatter.
  * accumulate != 0: values += contributions (assemble_into_csr);  == 0: values = contributions (assemble()).
  * The _device form only enqueues work on the ctx stream (values stay in HBM; call fb200_synchronize to
  * collect deferred errors).  The host form uploads `values` first when accumulating, waits, and copies
@@ -186,8 +189,8 @@ fb200_status fb200_assemble_vector(fb200_ctx* ctx, const fb200_quadrature* quadr
                                    int32_t per_element, int32_t scatter_mode, int32_t accumulate, double* out);
 /* ElementEllipticAssembler as ElementVectorAssembler / ElementScalarAssembler (src/assembly/local/elliptic.rs:342-359, 440-605): with
  * grad u = J^-T sum_I grad_ref phi_I (x) u_I (compute_volume_u_grad, :25-59) per quadrature point,
- *   vector  out[s I + i] (+)= sum w |det J| (g^T grad phi_I)_i      g = grad u (Laplace) | g^T = P(grad u) (LinearElasticMaterial / StVKMaterial stress)
- *   scalar  *energy = sum over elements and points of w |det J| psi(grad u)    psi = |grad u|^2 / 2 | mu eps:eps + lambda tr(eps)^2 / 2 | mu E:E + lambda tr(E)^2 / 2
+ *   vector  out[s I + i] (+)= sum w |det J| (g^T grad phi_I)_i      g = grad u (Laplace) | g^T = P(grad u) (LinearElasticMaterial / StVKMaterial / NeoHookeanMaterial stress)
+ *   scalar  *energy = sum over elements and points of w |det J| psi(grad u)    psi = |grad u|^2 / 2 | mu eps:eps + lambda tr(eps)^2 / 2 | mu E:E + lambda tr(E)^2 / 2 | mu tr(E) - mu log J + lambda (log J)^2 / 2
  * u: solution_dim * num_nodes doubles on the host.  Vector: VectorAssembler / VectorParAssembler semantics (ATOMIC | COLORED, accumulate);
  * scalar: assemble_scalar (global.rs:697-722).  Errors: FB200_ERR_SINGULAR_JACOBIAN with the element index. */
 fb200_status fb200_assemble_elliptic_vector(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature, const double* u,

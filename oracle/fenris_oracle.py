@@ -1261,6 +1261,54 @@ def stvk_contraction(F: np.ndarray, a: np.ndarray, b: np.ndarray, mu: float, lam
             + F @ F.T * mu * a_dot_b)
 
 
+NEO_HOOKEAN = 4
+
+
+def log_det_F(du_dX: np.ndarray):
+    """fenris-solid/src/logdet.rs:17-86: log det(I + du_dX) as log1p(gamma) (accurate for small displacement gradients); None when
+    det F <= 0."""
+    U = du_dX
+    if U.shape[0] == 2:
+        gamma = U[0, 0] * U[1, 1] + U[0, 0] + U[1, 1] - U[0, 1] * U[1, 0]
+    else:
+        u11, u22, u33 = U[0, 0], U[1, 1], U[2, 2]
+        a, e, i = 1.0 + u11, 1.0 + u22, 1.0 + u33
+        b, c, d, f, g, h = U[0, 1], U[0, 2], U[1, 0], U[1, 2], U[2, 0], U[2, 1]
+        gamma = (u11 * u22 * u33 + u11 * u22 + u11 * u33 + u22 * u33 + u11 + u22 + u33 + b * f * g + c * d * h - c * e * g - b * d * i
+                 - a * f * h)
+    return math.log1p(gamma) if gamma > -1.0 else None
+
+
+def neo_hookean_energy_density_du(u_grad: np.ndarray, mu: float, lam: float) -> float:
+    """materials.rs:251-265: psi = mu tr(E) - mu log J + lambda (log J)^2 / 2 with tr(E) = tr(U) + |U|^2 / 2, U = (grad u)^T."""
+    U = u_grad.T
+    logJ = log_det_F(U)
+    if logJ is None:
+        return math.inf
+    tr_E = float(np.trace(U)) + 0.5 * float(np.sum(U * U))
+    return mu * tr_E - mu * logJ + 0.5 * lam * logJ ** 2
+
+
+def neo_hookean_stress(F: np.ndarray, mu: float, lam: float) -> np.ndarray:
+    """materials.rs:267-289: P = F^-T (-mu + lambda log J) + mu F; NaN for J <= 0."""
+    J = det_small(F)
+    if J <= 0.0:
+        return np.full(F.shape, math.nan)
+    F_inv_T = try_inverse_small(F).T
+    return F_inv_T * (-mu + lam * math.log(J)) + F * mu
+
+
+def neo_hookean_contraction(F: np.ndarray, a: np.ndarray, b: np.ndarray, mu: float, lam: float) -> np.ndarray:
+    """materials.rs:291-318: C = lambda (F^-T a)(F^-T b)^T - alpha (F^-T b)(F^-T a)^T + mu (a.b) I, alpha = -mu + lambda log J."""
+    J = det_small(F)
+    if J <= 0.0:
+        return np.full(F.shape, math.nan)
+    F_inv_T = try_inverse_small(F).T
+    Ta, Tb = F_inv_T @ a, F_inv_T @ b
+    alpha = -mu + lam * math.log(J)
+    return np.outer(Ta, Tb) * lam - np.outer(Tb, Ta) * alpha + np.eye(F.shape[0]) * (mu * float(a @ b))
+
+
 _elliptic_operator_transpose_linear = elliptic_operator_transpose
 _elliptic_energy_density_linear = elliptic_energy_density
 
@@ -1268,12 +1316,16 @@ _elliptic_energy_density_linear = elliptic_energy_density
 def elliptic_operator_transpose(op: int, u_grad: np.ndarray, params) -> np.ndarray:  # noqa: F811 (extends the linear version with STVK)
     if op == STVK:
         return stvk_stress(np.eye(u_grad.shape[0]) + u_grad.T, params[0], params[1])
+    if op == NEO_HOOKEAN:
+        return neo_hookean_stress(np.eye(u_grad.shape[0]) + u_grad.T, params[0], params[1])
     return _elliptic_operator_transpose_linear(op, u_grad, params)
 
 
 def elliptic_energy_density(op: int, u_grad: np.ndarray, params) -> float:  # noqa: F811
     if op == STVK:
         return stvk_energy_density(np.eye(u_grad.shape[0]) + u_grad.T, params[0], params[1])
+    if op == NEO_HOOKEAN:  # MaterialEllipticOperator -> compute_energy_density_du (fenris-solid lib.rs:492-499)
+        return neo_hookean_energy_density_du(u_grad, params[0], params[1])
     return _elliptic_energy_density_linear(op, u_grad, params)
 
 
@@ -1282,6 +1334,8 @@ def contract_u(op: int, u_grad: np.ndarray, a: np.ndarray, b: np.ndarray, params
     (fenris-solid lib.rs:480-489, 140-151: F = I + (grad u)^T); the linear operators ignore u."""
     if op == STVK:
         return stvk_contraction(np.eye(u_grad.shape[0]) + u_grad.T, a, b, params[0], params[1])
+    if op == NEO_HOOKEAN:
+        return neo_hookean_contraction(np.eye(u_grad.shape[0]) + u_grad.T, a, b, params[0], params[1])
     return contract(op, a, b, params)
 
 
@@ -1289,7 +1343,7 @@ def element_matrix_u(elem_type: int, X_elem: np.ndarray, op: int, u_element: np.
     """assemble_element_elliptic_matrix (elliptic.rs:361-439) INCLUDING the state: grad u per point (compute_volume_u_grad), upper
     blocks I <= J of K += scale * contract(grad u, grad phi_I, grad phi_J) (operators.rs:176-188), then clone_upper_to_lower."""
     n, ng, d = element_info(elem_type)
-    s = d if op in (LINEAR_ELASTIC, STVK) else 1
+    s = d if op in (LINEAR_ELASTIC, STVK, NEO_HOOKEAN) else 1
     X = np.asarray(X_elem, dtype=np.float64)[:ng].T
     U = np.asarray(u_element, dtype=np.float64).reshape(n, s).T
     K = np.zeros((s * n, s * n))
@@ -1317,7 +1371,7 @@ def assemble_matrix_u_serial(elem_type: int, vertices, connectivity, op: int, u:
     conn = np.asarray(connectivity, dtype=np.int64)
     V = np.asarray(vertices, dtype=np.float64)
     _, _, d = element_info(elem_type)
-    s = d if op in (LINEAR_ELASTIC, STVK) else 1
+    s = d if op in (LINEAR_ELASTIC, STVK, NEO_HOOKEAN) else 1
     Uall = np.asarray(u, dtype=np.float64).reshape(-1, s)
     ro, ci = assemble_pattern(s, len(V), conn.tolist())
     values = np.zeros(len(ci))

@@ -84,3 +84,69 @@ def test_stvk_tangent_is_the_derivative_of_the_element_vector(et, mesh):
         ffd[k] = (fo.element_elliptic_energy(et, X, fo.STVK, u + D, prob.weights, prob.points, prob.params_per_point)
                   - fo.element_elliptic_energy(et, X, fo.STVK, u - D, prob.weights, prob.points, prob.params_per_point)) / (2 * h)
     assert np.abs(f - ffd).max() < 1e-7 * np.abs(f).max()
+
+
+# ---- NeoHookeanMaterial (fenris-solid/src/materials.rs:232-353), same test method (materials.rs:335-375 of the reference's unit tests)
+def test_neo_hookean_golden_strain_energies():
+    # compute_energy_density(F) = compute_energy_density_du((F - I)^T)  (materials.rs:246-249)
+    assert abs(fo.neo_hookean_energy_density_du((F2 - np.eye(2)).T, MU, LAM) - 5505.274620288603) < 1e-12 * 5505.0
+    assert abs(fo.neo_hookean_energy_density_du((F3 - np.eye(3)).T, MU, LAM) - 48833.26962613859) < 1e-12 * 48833.0
+    assert fo.neo_hookean_energy_density_du(-2.0 * np.eye(3), MU, LAM) == np.inf  # det F <= 0 (materials.rs:262-264)
+    assert np.isnan(fo.neo_hookean_stress(-np.eye(3), MU, LAM)).all()  # materials.rs:277-279
+
+
+@pytest.mark.parametrize("F", [F2, F3])
+def test_neo_hookean_stress_and_contraction_by_finite_differences(F):
+    d, h = F.shape[0], 1e-5
+    energy = lambda G: fo.neo_hookean_energy_density_du((G - np.eye(d)).T, MU, LAM)
+    P = fo.neo_hookean_stress(F, MU, LAM)
+    Pfd = np.zeros((d, d))
+    for i in range(d):
+        for j in range(d):
+            D = np.zeros((d, d))
+            D[i, j] = h
+            Pfd[i, j] = (energy(F + D) - energy(F - D)) / (2 * h)
+    assert np.abs(P - Pfd).max() < 1e-6 * np.abs(P).max()
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=d), rng.normal(size=d)
+    Cfd = np.zeros((d, d))
+    for j in range(d):
+        for m in range(d):
+            D = np.zeros((d, d))
+            D[j, m] = h
+            dP = (fo.neo_hookean_stress(F + D, MU, LAM) - fo.neo_hookean_stress(F - D, MU, LAM)) / (2 * h)
+            Cfd[:, j] += (dP @ a) * b[m]
+    C = fo.neo_hookean_contraction(F, a, b, MU, LAM)
+    assert np.abs(C - Cfd).max() < 1e-6 * np.abs(C).max()
+    assert np.abs(fo.neo_hookean_contraction(F, b, a, MU, LAM) - C.T).max() < 1e-12 * np.abs(C).max()
+
+
+def test_neo_hookean_at_the_reference_state_is_linear_elasticity():
+    rng = np.random.default_rng(5)
+    for d in (2, 3):
+        a, b = rng.normal(size=d), rng.normal(size=d)
+        assert np.allclose(fo.neo_hookean_contraction(np.eye(d), a, b, MU, LAM), fo.contract(fo.LINEAR_ELASTIC, a, b, (MU, LAM)), rtol=1e-14, atol=1e-12)
+    # log det through log1p keeps the small-strain energy accurate where log(det F) would cancel (logdet.rs:57-86)
+    U = 1e-9 * np.array([[1.0, 2.0, 0.5], [0.3, -1.0, 0.7], [0.2, 0.1, 0.4]])
+    assert abs(fo.log_det_F(U) - np.trace(U)) < 1e-17
+
+
+@pytest.mark.parametrize("et,mesh", [(fo.QUAD4, "quad"), (fo.HEX8, "hex")])
+def test_neo_hookean_tangent_is_the_derivative_of_the_element_vector(et, mesh):
+    v, c = {"quad": fo.create_unit_square_uniform_quad_mesh_2d, "hex": fo.create_unit_box_uniform_hex_mesh_3d}[mesh](1)
+    prob = fo.Problem(et, v, c, fo.NEO_HOOKEAN, params=(2.0, 3.0))
+    n, _, d = fo.element_info(et)
+    u = 0.1 * np.random.default_rng(9).normal(size=n * d)
+    X = v[c[0]]
+    args = (prob.weights, prob.points, prob.params_per_point)
+    K = fo.element_matrix_u(et, X, fo.NEO_HOOKEAN, u, *args)
+    Kfd, ffd = np.zeros_like(K), np.zeros(n * d)
+    h = 1e-6
+    for k in range(n * d):
+        D = np.zeros(n * d)
+        D[k] = h
+        Kfd[:, k] = (fo.element_elliptic_vector(et, X, fo.NEO_HOOKEAN, u + D, *args) - fo.element_elliptic_vector(et, X, fo.NEO_HOOKEAN, u - D, *args)) / (2 * h)
+        ffd[k] = (fo.element_elliptic_energy(et, X, fo.NEO_HOOKEAN, u + D, *args) - fo.element_elliptic_energy(et, X, fo.NEO_HOOKEAN, u - D, *args)) / (2 * h)
+    assert np.abs(K - Kfd).max() < 1e-7 * np.abs(K).max() and np.array_equal(K, K.T)
+    f = fo.element_elliptic_vector(et, X, fo.NEO_HOOKEAN, u, *args)
+    assert np.abs(f - ffd).max() < 1e-7 * np.abs(f).max()
