@@ -645,7 +645,8 @@ class CsrAssembler:
             if mode == nat.SCATTER_GATHER:
                 mode = nat.SCATTER_ATOMIC
             self.ctx.values_upload(csr.values)
-            self.ctx.assemble_into_csr_table_device(ea.op.kind, ea._rules(), ea.qtable.element_to_rule_map, scatter_mode=mode, accumulate=True)
+            u = np.asarray(ea.u, dtype=np.float64) if ea.op.kind in (nat.STVK, nat.NEO_HOOKEAN) and ea.u is not None else None
+            self.ctx.assemble_into_csr_table_device(ea.op.kind, ea._rules(), ea.qtable.element_to_rule_map, scatter_mode=mode, accumulate=True, u=u)
             self.ctx.synchronize()
             self.ctx.values_download(csr.values)
             return

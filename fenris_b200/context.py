@@ -257,8 +257,10 @@ class Context:
         self._check(self._lib.fb200_cg_solve(self._h, nat.ptr(bv), nat.ptr(x), float(rel_tol), int(max_iter), int(jacobi), C.byref(it), C.byref(res)))
         return x, int(it.value), float(res.value)
 
-    def assemble_into_csr_table_device(self, op_kind: int, rules, element_rule, scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False):
-        """rules: sequence of (weights, points, data) - a CompactQuadratureTable; element_rule: rule index per element."""
+    def assemble_into_csr_table_device(self, op_kind: int, rules, element_rule, scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False,
+                                       u: Optional[np.ndarray] = None):
+        """rules: sequence of (weights, points, data) - a CompactQuadratureTable; element_rule: rule index per element; u: the state of a
+        non-linear operator (STVK, NEO_HOOKEAN)."""
         keep, qs = [], (nat.Quadrature * len(rules))()
         for r, (weights, points, data) in enumerate(rules):
             _, q = self._structs(op_kind, weights, points, data)
@@ -267,7 +269,9 @@ class Context:
         er = np.ascontiguousarray(element_rule, dtype=np.uint32)
         op = nat.Operator(op_kind)
         self._keep = keep
-        self._check(self._lib.fb200_assemble_into_csr_table_device(self._h, C.byref(op), len(rules), qs, nat.ptr(er), None, scatter_mode, int(accumulate)))
+        uv = None if u is None else nat.as_f64(u).reshape(-1)
+        self._check(self._lib.fb200_assemble_into_csr_table_device(self._h, C.byref(op), len(rules), qs, nat.ptr(er), None if uv is None else nat.ptr(uv),
+                                                                   scatter_mode, int(accumulate)))
 
     def values_download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:

@@ -1126,10 +1126,11 @@ fb200_status fb200_assemble_into_csr(fb200_ctx* ctx, const fb200_operator* op, c
 // rule on the host; every group runs the uniform-table element kernel over its own element list with accumulate semantics.
 fb200_status fb200_assemble_into_csr_table_device(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
                                                   const uint32_t* element_rule, const double* u, int32_t scatter_mode, int32_t accumulate) {
-    (void)u;
     if (!ctx) return FB200_ERR_STATE;
     if (!op || !rules || !element_rule || num_rules == 0) return fail(ctx, FB200_ERR_SHAPE, "null operator / rules / element map");
-    for (uint32_t r = 0; r < num_rules; ++r) FB200_TRY(validate(ctx, op, &rules[r]));
+    // state-dependent operators (StVK, NeoHookean) run the kernel of mass_source.cu per group; the linear ones ignore u
+    const bool nonlinear = op->kind == FB200_STVK || op->kind == FB200_NEO_HOOKEAN;
+    for (uint32_t r = 0; r < num_rules && !nonlinear; ++r) FB200_TRY(validate(ctx, op, &rules[r]));
     if (!ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "no pattern: call fb200_assemble_pattern or fb200_pattern_adopt first");
     const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;
     if (s != ctx->sdim) return fail(ctx, FB200_ERR_SHAPE, "pattern solution_dim does not match the operator");
@@ -1164,14 +1165,26 @@ fb200_status fb200_assemble_into_csr_table_device(fb200_ctx* ctx, const fb200_op
         cudaError_t e = cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream);
         if (e != cudaSuccess) st = cuda_fail(ctx, e, "memset values");
     }
+    std::vector<double> zeros;
+    const double* state = u;  // uploaded with the first group, NULL afterwards
+    if (nonlinear && !state) {
+        zeros.assign((size_t)ctx->sdim * ctx->N + 1, 0.0);
+        state = zeros.data();
+    }
     for (uint32_t r = 0; r < num_rules && st == FB200_OK; ++r) {
         bool any = false;
         for (size_t c = 0; c + 1 < col_off.size(); ++c) any |= off[c * num_rules + r + 1] > off[c * num_rules + r];
         if (!any) continue;
-        st = upload_tables(ctx, op, &rules[r]);
+        if (!nonlinear) st = upload_tables(ctx, op, &rules[r]);
         for (size_t c = 0; c + 1 < col_off.size() && st == FB200_OK; ++c) {
             const size_t i = c * num_rules + r;
             if (off[i + 1] == off[i]) continue;
+            if (nonlinear) {
+                st = assemble_state_dependent_list(ctx, op, &rules[r], state, d_lists + off[i], off[i + 1] - off[i], colored ? 1 : 0);
+                if (state) cudaStreamSynchronize(ctx->stream);  // the copy of the state reads pageable memory
+                state = nullptr;
+                continue;
+            }
             AssembleParams p;
             fill_params(ctx, p);
             p.accumulate = 1;

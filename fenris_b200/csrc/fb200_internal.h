@@ -265,6 +265,8 @@ fb200_status read_errword(fb200_ctx* ctx);  // sync + translate deferred device 
 // mass_source.cu: CSR assembly of a state-dependent operator (FB200_STVK) at the host vector u (NULL = zeros)
 fb200_status assemble_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int scatter_mode,
                                       int accumulate);
+fb200_status assemble_state_dependent_list(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
+                                           const int32_t* d_list, uint64_t count, int plain);
 
 inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 

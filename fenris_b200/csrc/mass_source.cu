@@ -35,6 +35,10 @@ struct MsParams {
     const double* u;
     double* energies;
     unsigned long long* errword;
+    // host side only: launch over exactly this element list (quadrature tables with a rule per element), plain = coloured semantics
+    const int32_t* forced_list;
+    uint64_t forced_count;
+    int forced;
 };
 
 template <int d>
@@ -568,6 +572,7 @@ static fb200_status ms_launch_t(fb200_ctx* ctx, MsParams& p, int scatter_mode) {
         kernel<<<blocks, 128, smem, ctx->stream>>>(p);
         return check_launch(ctx, "mass_source_kernel");
     };
+    if (p.forced) return run(p.forced_list, p.forced_count);
     if (WHAT == 4) {  // energies: every owned element once, no scatter
         p.plain = 0;
         return run(nullptr, ctx->E_owned);
@@ -801,6 +806,35 @@ fb200_status fb200::assemble_state_dependent(fb200_ctx* ctx, const fb200_operato
     p.values = ctx->d_values;
     p.errword = ctx->d_errword;
     return ms_launch<5>(ctx, p, scatter_mode);
+}
+
+// One (colour, rule) group of fb200_assemble_into_csr_table_device for a state-dependent operator: u = NULL keeps the state uploaded by
+// the previous call of the same assembly; always accumulates (the caller clears the values once).
+fb200_status fb200::assemble_state_dependent_list(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
+                                                  const int32_t* d_list, uint64_t count, int plain) {
+    if (ctx->ragged || !ctx->d_blockmap) return fail(ctx, FB200_ERR_UNSUPPORTED, "needs a uniform-element space");
+    if (ctx->ei.d != ctx->sdim) return fail(ctx, FB200_ERR_SHAPE, "pattern solution_dim does not match the operator");
+    if (u) {
+        int s = 0;
+        FB200_TRY(elliptic_common(ctx, op, q, u, &s));
+    } else {
+        FB200_TRY(ms_validate(ctx, q));
+        if (!q->data) return fail(ctx, FB200_ERR_SHAPE, "elastic materials need Lame data per point");
+        FB200_TRY(ms_tables(ctx, q, 2));
+    }
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = ctx->sdim;
+    p.op = op->kind;
+    p.u = ctx->d_source;
+    p.values = ctx->d_values;
+    p.errword = ctx->d_errword;
+    p.forced = 1;
+    p.forced_list = d_list;
+    p.forced_count = count;
+    p.plain = plain;
+    return ms_launch<5>(ctx, p, FB200_SCATTER_ATOMIC);
 }
 
 extern "C" {

@@ -162,7 +162,8 @@ fb200_status fb200_assemble_into_csr(fb200_ctx* ctx, const fb200_operator* op, c
 /* The same with a rule PER ELEMENT: CompactQuadratureTable (rules + element_to_rule_map, quadrature_table.rs:312-439); a
  * GeneralQuadratureTable (:57-210) is the special case of one rule per element (the Python mirror merges identical rules).
  * rules[r].data follows the operator as above; element_rule[e] < num_rules for every element of the space.
- * scatter_mode: ATOMIC or COLORED.  Elements are grouped by rule; each group runs with its own uniform tables. */
+ * scatter_mode: ATOMIC or COLORED.  Elements are grouped by rule; each group runs with its own uniform tables.  u as above (STVK /
+ * NEO_HOOKEAN assemble the tangent stiffness at u with the rule and the Lame data of each element). */
 fb200_status fb200_assemble_into_csr_table_device(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
                                                   const uint32_t* element_rule, const double* u, int32_t scatter_mode, int32_t accumulate);
 fb200_status fb200_values_device(fb200_ctx* ctx, double** device_ptr, uint64_t* nnz);

@@ -1114,10 +1114,11 @@ def conjugate_gradient(apply_a, b, x0=None, rel_tol: float = 1e-8, max_iter: int
         zTr = zTr_next
 
 
-def assemble_with_quadrature_table(elem_type: int, vertices, connectivity, op: int, rules, element_to_rule):
+def assemble_with_quadrature_table(elem_type: int, vertices, connectivity, op: int, rules, element_to_rule, u=None):
     """CsrAssembler::assemble with an ElementEllipticAssembler whose QuadratureTable has a rule per element
     (CompactQuadratureTable / GeneralQuadratureTable, quadrature_table.rs:57-210, 312-439; the element loop of elliptic.rs:299-340 calls
-    populate_element_quadrature_from_table per element).  rules[r] = (weights, points, params_per_point)."""
+    populate_element_quadrature_from_table per element).  rules[r] = (weights, points, params_per_point); u: the state of a
+    state-dependent operator (STVK, NEO_HOOKEAN), zeros when omitted."""
     conn = np.asarray(connectivity, dtype=np.int64)
     V = np.asarray(vertices, dtype=np.float64)
     n, _, d = element_info(elem_type)
@@ -1126,7 +1127,11 @@ def assemble_with_quadrature_table(elem_type: int, vertices, connectivity, op: i
     values = np.zeros(len(ci))
     for e in range(len(conn)):
         w, p, params = rules[int(element_to_rule[e])]
-        K = element_matrix(elem_type, V[conn[e]], op, w, p, params)
+        if op in (LAPLACE, LINEAR_ELASTIC):
+            K = element_matrix(elem_type, V[conn[e]], op, w, p, params)
+        else:
+            ue = np.zeros(n * s) if u is None else np.asarray(u, dtype=np.float64).reshape(-1, s)[conn[e]].reshape(-1)
+            K = element_matrix_u(elem_type, V[conn[e]], op, ue, w, p, params)
         scatter_element(values, ro, ci, s, conn[e].tolist(), K)
     return ro, ci, values
 

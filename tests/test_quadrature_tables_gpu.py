@@ -1,5 +1,6 @@
 """GPU parity of assembly with a quadrature rule PER ELEMENT (CompactQuadratureTable / GeneralQuadratureTable,
-src/assembly/local/quadrature_table.rs:57-210, 312-439 - SURVEY 8f rank 4, tables only) against the literal oracle loop."""
+src/assembly/local/quadrature_table.rs:57-210, 312-439 - SURVEY 8f rank 4) against the literal oracle loop, for the linear operators and the
+state-dependent materials (StVK, NeoHookean) alike."""
 import numpy as np
 import pytest
 
@@ -36,7 +37,8 @@ def _rules(et, op):
     return rules
 
 
-@pytest.mark.parametrize("kind,n,op", [("hex8", 4, fo.LINEAR_ELASTIC), ("hex8", 3, fo.LAPLACE), ("tet4", 2, fo.LINEAR_ELASTIC), ("quad4", 6, fo.LAPLACE)])
+@pytest.mark.parametrize("kind,n,op", [("hex8", 4, fo.LINEAR_ELASTIC), ("hex8", 3, fo.LAPLACE), ("tet4", 2, fo.LINEAR_ELASTIC), ("quad4", 6, fo.LAPLACE),
+                                       ("hex8", 3, fo.STVK), ("quad4", 5, fo.NEO_HOOKEAN), ("tet4", 2, fo.NEO_HOOKEAN)])
 @pytest.mark.parametrize("mode", [fb.SCATTER_ATOMIC, fb.SCATTER_COLORED])
 def test_compact_table_assembly_equals_oracle(ctx, kind, n, op, mode):
     if kind == "hex8":
@@ -48,25 +50,28 @@ def test_compact_table_assembly_equals_oracle(ctx, kind, n, op, mode):
     v = fo.jitter_vertices(v, 1.0 / n, amp=0.15)
     rules = _rules(et, op)
     emap = (np.arange(len(c)) * 7 + 1) % 3  # every rule is used, in no particular order
-    oro, oci, ovals = fo.assemble_with_quadrature_table(et, v, c, op, [(w, p, par) for w, p, par, _ in rules], emap)
     s = 1 if op == fo.LAPLACE else v.shape[1]
+    # the state of the non-linear materials (elliptic.rs:393-399), small against the cell size so that no element inverts
+    u = (0.05 / n) * np.random.default_rng(17).normal(size=s * len(v)) if op in (fo.STVK, fo.NEO_HOOKEAN) else None
+    oro, oci, ovals = fo.assemble_with_quadrature_table(et, v, c, op, [(w, p, par) for w, p, par, _ in rules], emap, u=u)
+    assert not np.isnan(ovals).any()
     ctx.space_upload(et, v, c.astype(np.uint64))
     ctx.assemble_pattern(s)
     ctx.color_nodes()
-    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], emap, scatter_mode=mode)
+    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], emap, scatter_mode=mode, u=u)
     ctx.synchronize()
     ro, ci = ctx.pattern_download()
     assert np.array_equal(ro, oro) and np.array_equal(ci, oci)
     vals = ctx.values_download().copy()
     assert fo.rel_frobenius(vals, ovals) < TOL
     # accumulate semantics, and a map that uses one rule only == the uniform-table path
-    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], emap, scatter_mode=mode, accumulate=True)
+    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], emap, scatter_mode=mode, accumulate=True, u=u)
     ctx.synchronize()
     assert fo.rel_frobenius(ctx.values_download(), 2.0 * ovals) < TOL
-    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], np.zeros(len(c), dtype=np.uint32), scatter_mode=mode)
+    ctx.assemble_into_csr_table_device(op, [(w, p, d) for w, p, _, d in rules], np.zeros(len(c), dtype=np.uint32), scatter_mode=mode, u=u)
     ctx.synchronize()
     table_uniform = ctx.values_download().copy()
-    ctx.assemble_into_csr_device(op, rules[0][0], rules[0][1], rules[0][3], scatter_mode=mode)
+    ctx.assemble_into_csr_device(op, rules[0][0], rules[0][1], rules[0][3], scatter_mode=mode, u=u)
     ctx.synchronize()
     assert fo.rel_frobenius(table_uniform, ctx.values_download()) < 1e-13
 
