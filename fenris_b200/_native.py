@@ -103,6 +103,8 @@ def lib():
         "fb200_physical_quadrature_points": (i32, [vp, C.POINTER(Quadrature), vp]),
         "fb200_assemble_elliptic_vector": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), vp, i32, i32, vp]),
         "fb200_assemble_elliptic_scalar": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), vp, pdbl]),
+        "fb200_assemble_elliptic_vector_table": (i32, [vp, C.POINTER(Operator), C.c_uint32, C.POINTER(Quadrature), vp, vp, i32, i32, vp]),
+        "fb200_assemble_elliptic_scalar_table": (i32, [vp, C.POINTER(Operator), C.c_uint32, C.POINTER(Quadrature), vp, vp, pdbl]),
         "fb200_apply_homogeneous_dirichlet_bc_csr": (i32, [vp, u64, vp, pdbl]),
         "fb200_spmv": (i32, [vp, vp, vp]),
         "fb200_cg_solve": (i32, [vp, vp, vp, dbl, u64, i32, pu64, pdbl]),

@@ -501,6 +501,10 @@ class VectorAssembler:
         qt = ea.qtable
         if isinstance(ea, ElementEllipticAssembler):  # elliptic.rs:342-359: the operator's vector at ea.u
             assert ea.u is not None and len(ea.u) == s * n, "u has the wrong length"
+            if isinstance(qt, CompactQuadratureTable):  # a rule per element (quadrature_table.rs:57-210, 312-439)
+                ctx.assemble_elliptic_vector_table(ea.op.kind, ea._rules(), qt.element_to_rule_map, np.asarray(ea.u, dtype=np.float64), out=output,
+                                                   scatter_mode=mode, accumulate=True)
+                return output
             ctx.assemble_elliptic_vector(ea.op.kind, qt.weights, qt.points, ea._data(), np.asarray(ea.u, dtype=np.float64), out=output,
                                          scatter_mode=mode, accumulate=True)
             return output
@@ -688,6 +692,8 @@ def assemble_scalar(ea: ElementEllipticAssembler, ctx: Optional[Context] = None)
     ctx = ctx or Context()
     try:
         ctx.space_upload(ea.space.element_type, ea.space.vertices_, ea.space.connectivity_)
+        if isinstance(ea.qtable, CompactQuadratureTable):
+            return ctx.assemble_elliptic_scalar_table(ea.op.kind, ea._rules(), ea.qtable.element_to_rule_map, np.asarray(ea.u, dtype=np.float64))
         return ctx.assemble_elliptic_scalar(ea.op.kind, ea.qtable.weights, ea.qtable.points, ea._data(), np.asarray(ea.u, dtype=np.float64))
     finally:
         if own:

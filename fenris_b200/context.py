@@ -224,6 +224,35 @@ class Context:
         self._check(self._lib.fb200_assemble_elliptic_scalar(self._h, C.byref(op), C.byref(q), nat.ptr(uv), C.byref(e)))
         return float(e.value)
 
+    def _rule_structs(self, op_kind: int, rules, element_rule):
+        keep, qs = [], (nat.Quadrature * len(rules))()
+        for r, (weights, points, data) in enumerate(rules):
+            _, q = self._structs(op_kind, weights, points, data)
+            keep.append(self._keep)
+            qs[r] = q
+        er = np.ascontiguousarray(element_rule, dtype=np.uint32)
+        self._keep = keep
+        return nat.Operator(op_kind), qs, er
+
+    def assemble_elliptic_vector_table(self, op_kind: int, rules, element_rule, u: np.ndarray, out: Optional[np.ndarray] = None,
+                                       scatter_mode: int = nat.SCATTER_ATOMIC, accumulate: bool = False) -> np.ndarray:
+        """assemble_elliptic_vector with a rule per element (rules / element_rule as assemble_into_csr_table_device)."""
+        uv = nat.as_f64(u)
+        if out is None:
+            out = np.zeros_like(uv)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == uv.size
+        op, qs, er = self._rule_structs(op_kind, rules, element_rule)
+        self._check(self._lib.fb200_assemble_elliptic_vector_table(self._h, C.byref(op), len(rules), qs, nat.ptr(er), nat.ptr(uv), scatter_mode,
+                                                                   int(accumulate), nat.ptr(out)))
+        return out
+
+    def assemble_elliptic_scalar_table(self, op_kind: int, rules, element_rule, u: np.ndarray) -> float:
+        uv = nat.as_f64(u)
+        op, qs, er = self._rule_structs(op_kind, rules, element_rule)
+        e = C.c_double(0.0)
+        self._check(self._lib.fb200_assemble_elliptic_scalar_table(self._h, C.byref(op), len(rules), qs, nat.ptr(er), nat.ptr(uv), C.byref(e)))
+        return float(e.value)
+
     def physical_quadrature_points(self, weights, points, num_elements: int) -> np.ndarray:
         q = self._quad_only(weights, points)
         d = q.dim
@@ -261,14 +290,7 @@ class Context:
                                        u: Optional[np.ndarray] = None):
         """rules: sequence of (weights, points, data) - a CompactQuadratureTable; element_rule: rule index per element; u: the state of a
         non-linear operator (STVK, NEO_HOOKEAN)."""
-        keep, qs = [], (nat.Quadrature * len(rules))()
-        for r, (weights, points, data) in enumerate(rules):
-            _, q = self._structs(op_kind, weights, points, data)
-            keep.append(self._keep)
-            qs[r] = q
-        er = np.ascontiguousarray(element_rule, dtype=np.uint32)
-        op = nat.Operator(op_kind)
-        self._keep = keep
+        op, qs, er = self._rule_structs(op_kind, rules, element_rule)
         uv = None if u is None else nat.as_f64(u).reshape(-1)
         self._check(self._lib.fb200_assemble_into_csr_table_device(self._h, C.byref(op), len(rules), qs, nat.ptr(er), None if uv is None else nat.ptr(uv),
                                                                    scatter_mode, int(accumulate)))

@@ -1072,6 +1072,30 @@ static void fill_params(fb200_ctx* ctx, AssembleParams& p) {
 
 }  // namespace fb200
 
+// element lists per (colour, rule) of a quadrature table with a rule per element - one pseudo colour holding all owned elements for the
+// ATOMIC scatter; group (c, r) is flat[off[c * num_rules + r] .. off[c * num_rules + r + 1])
+fb200_status fb200::group_elements_by_rule(fb200_ctx* ctx, uint32_t num_rules, const uint32_t* element_rule, bool colored,
+                                           std::vector<uint64_t>& col_off, std::vector<int32_t>& flat, std::vector<uint64_t>& off) {
+    col_off = {0, ctx->E_owned};
+    if (colored) col_off = ctx->h_color_off;
+    std::vector<std::vector<int32_t>> lists((col_off.size() - 1) * (size_t)num_rules);
+    for (size_t c = 0; c + 1 < col_off.size(); ++c)
+        for (uint64_t k = col_off[c]; k < col_off[c + 1]; ++k) {
+            const uint64_t e = colored ? ctx->h_color_elems[k] : k;
+            if (e >= ctx->E_owned) continue;  // ghost elements of a partition are not assembled
+            const uint32_t r = element_rule[e];
+            if (r >= num_rules) return fail(ctx, FB200_ERR_INDEX_OOB, "element_to_rule_map entry out of bounds (quadrature_table.rs:361-366)", (int64_t)e);
+            lists[c * num_rules + r].push_back((int32_t)e);
+        }
+    flat.clear();
+    off.assign(lists.size() + 1, 0);
+    for (size_t i = 0; i < lists.size(); ++i) {
+        off[i + 1] = off[i] + lists[i].size();
+        flat.insert(flat.end(), lists[i].begin(), lists[i].end());
+    }
+    return FB200_OK;
+}
+
 using namespace fb200;
 
 extern "C" {
@@ -1139,25 +1163,10 @@ fb200_status fb200_assemble_into_csr_table_device(fb200_ctx* ctx, const fb200_op
     if (scatter_mode == FB200_SCATTER_COLORED && !ctx->has_colors)
         return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    // element lists per (colour, rule) - one pseudo colour holding all owned elements for the ATOMIC scatter
-    std::vector<uint64_t> col_off{0, ctx->E_owned};
     const bool colored = scatter_mode == FB200_SCATTER_COLORED;
-    if (colored) col_off = ctx->h_color_off;
-    std::vector<std::vector<int32_t>> lists((col_off.size() - 1) * (size_t)num_rules);
-    for (size_t c = 0; c + 1 < col_off.size(); ++c)
-        for (uint64_t k = col_off[c]; k < col_off[c + 1]; ++k) {
-            const uint64_t e = colored ? ctx->h_color_elems[k] : k;
-            if (e >= ctx->E_owned) continue;  // ghost elements of a partition are not assembled
-            const uint32_t r = element_rule[e];
-            if (r >= num_rules) return fail(ctx, FB200_ERR_INDEX_OOB, "element_to_rule_map entry out of bounds (quadrature_table.rs:361-366)", (int64_t)e);
-            lists[c * num_rules + r].push_back((int32_t)e);
-        }
+    std::vector<uint64_t> col_off, off;
     std::vector<int32_t> flat;
-    std::vector<uint64_t> off(lists.size() + 1, 0);
-    for (size_t i = 0; i < lists.size(); ++i) {
-        off[i + 1] = off[i] + lists[i].size();
-        flat.insert(flat.end(), lists[i].begin(), lists[i].end());
-    }
+    FB200_TRY(group_elements_by_rule(ctx, num_rules, element_rule, colored, col_off, flat, off));
     int32_t* d_lists = nullptr;
     FB200_TRY(upload_vec(ctx, &d_lists, flat));
     fb200_status st = FB200_OK;

@@ -261,6 +261,8 @@ void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const u
 void free_ordered(fb200_ctx* ctx);
 fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q);
 fb200_status read_errword(fb200_ctx* ctx);  // sync + translate deferred device errors
+fb200_status group_elements_by_rule(fb200_ctx* ctx, uint32_t num_rules, const uint32_t* element_rule, bool colored,
+                                    std::vector<uint64_t>& col_off, std::vector<int32_t>& flat, std::vector<uint64_t>& off);
 
 // mass_source.cu: CSR assembly of a state-dependent operator (FB200_STVK) at the host vector u (NULL = zeros)
 fb200_status assemble_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int scatter_mode,

@@ -839,6 +839,132 @@ fb200_status fb200::assemble_state_dependent_list(fb200_ctx* ctx, const fb200_op
 
 extern "C" {
 
+// The same two with a rule per element (CompactQuadratureTable / GeneralQuadratureTable, quadrature_table.rs:57-210, 312-439): elements
+// grouped by rule (x colour) on the host, one launch per group over its element list.
+static fb200_status elliptic_table_begin(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                         const uint32_t* element_rule, const double* u, int* s_out) {
+    if (!rules || !element_rule || num_rules == 0) return fail(ctx, FB200_ERR_SHAPE, "null rules / element map");
+    for (uint32_t r = 0; r < num_rules; ++r) {
+        FB200_TRY(ms_validate(ctx, &rules[r]));
+        if (op && op->kind != FB200_LAPLACE && !rules[r].data) return fail(ctx, FB200_ERR_SHAPE, "elastic materials need Lame data per point");
+    }
+    return elliptic_common(ctx, op, &rules[0], u, s_out);  // validates the operator, uploads u
+}
+
+fb200_status fb200_assemble_elliptic_vector_table(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                                  const uint32_t* element_rule, const double* u, int32_t scatter_mode, int32_t accumulate,
+                                                  double* out) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");
+    if (scatter_mode != FB200_SCATTER_ATOMIC && scatter_mode != FB200_SCATTER_COLORED)
+        return fail(ctx, FB200_ERR_UNSUPPORTED, "vector assembly supports the ATOMIC and COLORED scatter");
+    const bool colored = scatter_mode == FB200_SCATTER_COLORED;
+    if (colored && !ctx->has_colors) return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
+    int s = 0;
+    FB200_TRY(elliptic_table_begin(ctx, op, num_rules, rules, element_rule, u, &s));
+    std::vector<uint64_t> col_off, off;
+    std::vector<int32_t> flat;
+    FB200_TRY(group_elements_by_rule(ctx, num_rules, element_rule, colored, col_off, flat, off));
+    const uint64_t len = (uint64_t)s * ctx->N;
+    if (ctx->vector_capacity < len) {
+        dev_free(ctx->d_vector);
+        FB200_TRY(dev_alloc(ctx, &ctx->d_vector, len));
+        ctx->vector_capacity = len;
+    }
+    ctx->vector_len = len;
+    if (accumulate) {
+        if (len) FB200_CUDA(ctx, cudaMemcpyAsync(ctx->d_vector, out, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (len) {
+        FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_vector, 0, len * sizeof(double), ctx->stream));
+    }
+    int32_t* d_lists = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_lists, flat.size()));
+    fb200_status st = FB200_OK;
+    if (!flat.empty()) {
+        cudaError_t e = cudaMemcpyAsync(d_lists, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "H2D element lists");
+    }
+    for (uint32_t r = 0; r < num_rules && st == FB200_OK; ++r)
+        for (size_t c = 0; c + 1 < col_off.size() && st == FB200_OK; ++c) {
+            const size_t i = c * num_rules + r;
+            if (off[i + 1] == off[i]) continue;
+            st = ms_tables(ctx, &rules[r], op->kind != FB200_LAPLACE ? 2 : 0);
+            if (st != FB200_OK) break;
+            MsParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.nq = rules[r].num_points;
+            p.s = s;
+            p.op = op->kind;
+            p.u = ctx->d_source;
+            p.vector = ctx->d_vector;
+            p.errword = ctx->d_errword;
+            p.forced = 1;
+            p.forced_list = d_lists + off[i];
+            p.forced_count = off[i + 1] - off[i];
+            p.plain = colored ? 1 : 0;
+            st = ms_launch<3>(ctx, p, FB200_SCATTER_ATOMIC);
+        }
+    if (st == FB200_OK && len) {
+        cudaError_t e = cudaMemcpyAsync(out, ctx->d_vector, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "D2H vector");
+    }
+    if (st == FB200_OK) st = read_errword(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_lists);
+    return st;
+}
+
+fb200_status fb200_assemble_elliptic_scalar_table(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                                  const uint32_t* element_rule, const double* u, double* energy) {
+    if (!ctx) return FB200_ERR_STATE;
+    if (!energy) return fail(ctx, FB200_ERR_SHAPE, "null output");
+    int s = 0;
+    FB200_TRY(elliptic_table_begin(ctx, op, num_rules, rules, element_rule, u, &s));
+    *energy = 0.0;
+    if (ctx->E_owned == 0) return FB200_OK;
+    std::vector<uint64_t> col_off, off;
+    std::vector<int32_t> flat;
+    FB200_TRY(group_elements_by_rule(ctx, num_rules, element_rule, false, col_off, flat, off));
+    int32_t* d_lists = nullptr;
+    double* d_e = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_lists, flat.size()));
+    fb200_status st = dev_alloc(ctx, &d_e, ctx->E_owned + 1);
+    if (st == FB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_lists, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "H2D element lists");
+    }
+    for (uint32_t r = 0; r < num_rules && st == FB200_OK; ++r) {
+        if (off[r + 1] == off[r]) continue;
+        st = ms_tables(ctx, &rules[r], op->kind != FB200_LAPLACE ? 2 : 0);
+        if (st != FB200_OK) break;
+        MsParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.nq = rules[r].num_points;
+        p.s = s;
+        p.op = op->kind;
+        p.u = ctx->d_source;
+        p.energies = d_e + off[r];  // the kernel writes energies[position in its list]
+        p.errword = ctx->d_errword;
+        p.forced = 1;
+        p.forced_list = d_lists + off[r];
+        p.forced_count = off[r + 1] - off[r];
+        st = ms_launch<4>(ctx, p, FB200_SCATTER_ATOMIC);
+    }
+    if (st == FB200_OK) {
+        sum_energies_kernel<<<1, 256, 0, ctx->stream>>>(d_e, ctx->E_owned, d_e + ctx->E_owned);
+        st = check_launch(ctx, "sum_energies_kernel");
+    }
+    if (st == FB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(energy, d_e + ctx->E_owned, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "D2H energy");
+    }
+    if (st == FB200_OK) st = read_errword(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_e);
+    cudaFree(d_lists);
+    return st;
+}
+
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* q, double* out) {
     FB200_TRY(ms_validate(ctx, q));
     if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");

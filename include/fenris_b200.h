@@ -198,6 +198,12 @@ fb200_status fb200_assemble_elliptic_vector(fb200_ctx* ctx, const fb200_operator
                                             int32_t scatter_mode, int32_t accumulate, double* out);
 fb200_status fb200_assemble_elliptic_scalar(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature, const double* u,
                                             double* energy);
+/* The same two with a quadrature rule per element (rules / element_rule as fb200_assemble_into_csr_table_device). */
+fb200_status fb200_assemble_elliptic_vector_table(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                                  const uint32_t* element_rule, const double* u, int32_t scatter_mode, int32_t accumulate,
+                                                  double* out);
+fb200_status fb200_assemble_elliptic_scalar_table(fb200_ctx* ctx, const fb200_operator* op, uint32_t num_rules, const fb200_quadrature* rules,
+                                                  const uint32_t* element_rule, const double* u, double* energy);
 /* x_q = element.map_reference_coords(xi_q) for every element and point (FiniteElement::map_reference_coords; sub-parametric elements map
  * through their embedded linear element, hexahedron.rs:328-330): out[(e * num_points + q) * d + c]. */
 fb200_status fb200_physical_quadrature_points(fb200_ctx* ctx, const fb200_quadrature* quadrature, double* out);

@@ -1233,6 +1233,37 @@ def assemble_elliptic_scalar(problem: "Problem", u: np.ndarray) -> float:
     return total
 
 
+def assemble_elliptic_vector_with_table(elem_type: int, vertices, connectivity, op: int, rules, element_to_rule, u) -> np.ndarray:
+    """VectorAssembler::assemble_vector over an ElementEllipticAssembler whose table has a rule per element (elliptic.rs:456-526 with
+    populate_element_quadrature_from_table).  rules[r] = (weights, points, params_per_point)."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    _, _, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    U = np.asarray(u, dtype=np.float64).reshape(-1, s)
+    out = np.zeros(s * len(V))
+    for e in range(len(conn)):
+        w, p, params = rules[int(element_to_rule[e])]
+        local = element_elliptic_vector(elem_type, V[conn[e]], op, U[conn[e]].reshape(-1), w, p, params)
+        for a, I in enumerate(conn[e]):
+            out[s * I:s * I + s] += local[s * a:s * a + s]
+    return out
+
+
+def assemble_elliptic_scalar_with_table(elem_type: int, vertices, connectivity, op: int, rules, element_to_rule, u) -> float:
+    """assemble_scalar (global.rs:697-722) with a rule per element."""
+    conn = np.asarray(connectivity, dtype=np.int64)
+    V = np.asarray(vertices, dtype=np.float64)
+    _, _, d = element_info(elem_type)
+    s = solution_dim(op, d)
+    U = np.asarray(u, dtype=np.float64).reshape(-1, s)
+    total = 0.0
+    for e in range(len(conn)):
+        w, p, params = rules[int(element_to_rule[e])]
+        total += element_elliptic_energy(elem_type, V[conn[e]], op, U[conn[e]].reshape(-1), w, p, params)
+    return total
+
+
 # ------------------------------------------------------------------------------------------------------------------------
 # SURVEY 8(f) rank 4: a non-linear material - St. Venant-Kirchhoff (fenris-solid/src/materials.rs:355-469) with u != 0
 # ------------------------------------------------------------------------------------------------------------------------

@@ -109,3 +109,42 @@ def test_reference_api_general_and_compact_tables():
                                                     [(rules[r][0], rules[r][1], [(lame[r].mu, lame[r].lambda_)] * len(rules[r][0])) for r in range(2)], emap)
     for M in (A, B, Cp):
         assert fo.rel_frobenius(M.values, ovals) < TOL
+
+
+@pytest.mark.parametrize("kind,n,op", [("hex8", 3, fo.LINEAR_ELASTIC), ("quad4", 6, fo.LAPLACE), ("hex8", 3, fo.NEO_HOOKEAN), ("tet4", 2, fo.STVK)])
+def test_elliptic_vector_and_energy_with_a_rule_per_element(ctx, kind, n, op):
+    # ElementEllipticAssembler as vector / scalar assembler (elliptic.rs:342-359, 440-605) over a Compact table
+    if kind == "hex8":
+        et, (v, c) = fo.HEX8, fo.create_unit_box_uniform_hex_mesh_3d(n)
+    elif kind == "tet4":
+        et, (v, c) = fo.TET4, fo.create_unit_box_uniform_tet_mesh_3d(n)
+    else:
+        et, (v, c) = fo.QUAD4, fo.create_unit_square_uniform_quad_mesh_2d(n)
+    v = fo.jitter_vertices(v, 1.0 / n, amp=0.15)
+    rules = _rules(et, op)
+    emap = (np.arange(len(c)) * 5 + 2) % 3
+    s = 1 if op == fo.LAPLACE else v.shape[1]
+    u = (0.05 / n) * np.random.default_rng(23).normal(size=s * len(v))
+    orules = [(w, p, par) for w, p, par, _ in rules]
+    ref = fo.assemble_elliptic_vector_with_table(et, v, c, op, orules, emap, u)
+    oe = fo.assemble_elliptic_scalar_with_table(et, v, c, op, orules, emap, u)
+    assert np.isfinite(ref).all() and np.isfinite(oe)
+    ctx.space_upload(et, v, c.astype(np.uint64))
+    ctx.color_nodes()
+    drules = [(w, p, d) for w, p, _, d in rules]
+    for mode in (fb.SCATTER_ATOMIC, fb.SCATTER_COLORED):
+        f = ctx.assemble_elliptic_vector_table(op, drules, emap, u, scatter_mode=mode)
+        assert np.abs(f - ref).max() < TOL * np.abs(ref).max(), mode
+    f2 = ctx.assemble_elliptic_vector_table(op, drules, emap, u, out=f.copy(), accumulate=True)
+    assert np.abs(f2 - 2.0 * ref).max() < 2 * TOL * np.abs(ref).max()
+    e = ctx.assemble_elliptic_scalar_table(op, drules, emap, u)
+    assert abs(e - oe) < TOL * abs(oe)
+    # one rule for every element == the uniform-table entry points
+    zero = np.zeros(len(c), dtype=np.uint32)
+    fu = ctx.assemble_elliptic_vector(op, rules[0][0], rules[0][1], rules[0][3], u)
+    assert np.abs(ctx.assemble_elliptic_vector_table(op, drules, zero, u) - fu).max() < 1e-13 * np.abs(fu).max()
+    eu = ctx.assemble_elliptic_scalar(op, rules[0][0], rules[0][1], rules[0][3], u)
+    assert abs(ctx.assemble_elliptic_scalar_table(op, drules, zero, u) - eu) < 1e-13 * abs(eu)
+    with pytest.raises(fb.Fb200Error) as ei:
+        ctx.assemble_elliptic_vector_table(op, drules, np.where(np.arange(len(c)) == 2, 9, emap), u)
+    assert ei.value.status == fb.ERR_INDEX_OOB and ei.value.element_index == 2
