@@ -4,6 +4,12 @@
 //   global vector assembly     VectorAssembler / VectorParAssembler::assemble_vector_into, add_local_to_global
 //                              src/assembly/global.rs:569-686, 779-796
 //   physical quadrature points FiniteElement::map_reference_coords (what SourceFunction::evaluate receives, source.rs:253-255)
+// and SURVEY 8(f) rank 4 - the state-dependent side of the elliptic assembler:
+//   element vector / energy    assemble_element_elliptic_vector / _energy   src/assembly/local/elliptic.rs:440-605  (Laplace, linear elastic,
+//                              StVK, NeoHookean; compute_volume_u_grad :25-59)
+//   tangent stiffness at u     assemble_element_elliptic_matrix with u_grad  elliptic.rs:361-439 for StVKMaterial / NeoHookeanMaterial
+//                              (fenris-solid/src/materials.rs:232-469), one lane per node pair I <= J
+//   the same with a quadrature rule per element (quadrature_table.rs:57-210, 312-439): one launch per (colour, rule) element list
 // Same skeleton as the stiffness kernels (assemble.cu): tables of the uniform quadrature rule staged in shared memory, one warp
 // per element, geometry per quadrature point per lane, scatter through the node-block map (matrix) or by node id (vector) with
 // f64 reductions (ATOMIC) or plain read-modify-write inside a colour (COLORED = CsrParAssembler / VectorParAssembler semantics).
