@@ -18,6 +18,7 @@ Sources (all under /root/reference):
   * fenris-solid/tests/unit_tests/mod.rs:11-29            Lame parameters / deformation gradients fixtures
   * fenris-solid/tests/unit_tests/materials.rs:74-84      Lame from Young/Poisson
   * fenris-solid/tests/unit_tests/materials.rs:245-262    linear elastic energy densities
+  * fenris-solid/tests/unit_tests/materials.rs:299-351    StVK / NeoHookean energy densities
   * tests/unit_tests/assembly.rs:159-162                  reference Quad4 Laplace element matrix (commented-out but valid KAT)
   * tests/convergence_tests/reference_values/poisson3d_mms_{hex8,tet4}_summary.json, poisson2d_mms_quad4_summary.json
 """
@@ -111,7 +112,13 @@ def main():
     psi2 = float(re.search(r"fn linear_elastic_strain_energy_2d.*?assert_scalar_eq!\(psi,\s*([\d.]+)", mats, re.S).group(1))
     psi3 = float(re.search(r"fn linear_elastic_strain_energy_3d.*?assert_scalar_eq!\(psi,\s*([\d.]+)", mats, re.S).group(1))
     yp = re.search(r"fn lame_from_young_poisson.*?young:\s*([\deE.+-]+),\s*poisson:\s*([\d.]+).*?lame\.mu,\s*([\d.]+).*?lame\.lambda,\s*([\d.]+)", mats, re.S)
+    nonlinear = {}
+    for name in ("stvk", "neo_hookean"):
+        for dim in ("2d", "3d"):
+            m = re.search(r"fn %s_strain_energy_%s.*?assert_scalar_eq!\(psi,\s*([\d.]+)" % (name, dim), mats, re.S)
+            nonlinear["psi_%s_%s" % (name, dim)] = float(m.group(1))
     kats["materials"] = {
+        **nonlinear,
         "mu": mu, "lambda": lam, "F2": F2, "F3": F3, "psi_linear_2d": psi2, "psi_linear_3d": psi3,
         "young": float(yp.group(1)), "poisson": float(yp.group(2)),
         "lame_mu": float(yp.group(3)), "lame_lambda": float(yp.group(4)),

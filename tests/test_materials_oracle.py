@@ -1,19 +1,25 @@
 """Pins the StVK restatement (oracle/fenris_oracle.py, SURVEY 8(f) rank 4 - a non-linear material) to the reference's own tests:
 golden energies of fenris-solid/tests/unit_tests/materials.rs:299-315 (fixtures of tests/unit_tests/mod.rs:11-29), stress = dpsi/dF and
 contraction = a.dP/dF.b by central differences (materials.rs:10-120, 317-330), and the assembled tangent K(u) = df/du."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 from oracle import fenris_oracle as fo
 
-MU, LAM = 384.0, 577.0  # lame_parameters(), mod.rs:11-16
-F2 = np.array([[2.0, 1.0], [3.0, 4.0]])  # deformation_gradient_2d, mod.rs:18-22
-F3 = np.array([[2.0, 1.0, 3.0], [4.0, 6.0, 5.0], [2.0, 8.0, 9.0]])  # deformation_gradient_3d, mod.rs:24-29
+# the reference's own fixtures and golden values, extracted by tests/golden/make_golden.py
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["materials"]
+MU, LAM = KATS["mu"], KATS["lambda"]  # lame_parameters(), mod.rs:11-16
+F2 = np.array(KATS["F2"])  # deformation_gradient_2d, mod.rs:18-22
+F3 = np.array(KATS["F3"])  # deformation_gradient_3d, mod.rs:24-29
 
 
 def test_stvk_golden_strain_energies():
-    assert fo.stvk_energy_density(F2, MU, LAM) == 132578.0  # materials.rs:300-306
-    assert fo.stvk_energy_density(F3, MU, LAM) == 9136789.125  # materials.rs:309-315
+    assert KATS["psi_stvk_2d"] == 132578.0 and KATS["psi_stvk_3d"] == 9136789.125
+    assert fo.stvk_energy_density(F2, MU, LAM) == KATS["psi_stvk_2d"]  # materials.rs:300-306
+    assert fo.stvk_energy_density(F3, MU, LAM) == KATS["psi_stvk_3d"]  # materials.rs:309-315
 
 
 @pytest.mark.parametrize("F", [F2, F3])
@@ -89,8 +95,8 @@ def test_stvk_tangent_is_the_derivative_of_the_element_vector(et, mesh):
 # ---- NeoHookeanMaterial (fenris-solid/src/materials.rs:232-353), same test method (materials.rs:335-375 of the reference's unit tests)
 def test_neo_hookean_golden_strain_energies():
     # compute_energy_density(F) = compute_energy_density_du((F - I)^T)  (materials.rs:246-249)
-    assert abs(fo.neo_hookean_energy_density_du((F2 - np.eye(2)).T, MU, LAM) - 5505.274620288603) < 1e-12 * 5505.0
-    assert abs(fo.neo_hookean_energy_density_du((F3 - np.eye(3)).T, MU, LAM) - 48833.26962613859) < 1e-12 * 48833.0
+    assert abs(fo.neo_hookean_energy_density_du((F2 - np.eye(2)).T, MU, LAM) - KATS["psi_neo_hookean_2d"]) < 1e-12 * 5505.0
+    assert abs(fo.neo_hookean_energy_density_du((F3 - np.eye(3)).T, MU, LAM) - KATS["psi_neo_hookean_3d"]) < 1e-12 * 48833.0
     assert fo.neo_hookean_energy_density_du(-2.0 * np.eye(3), MU, LAM) == np.inf  # det F <= 0 (materials.rs:262-264)
     assert np.isnan(fo.neo_hookean_stress(-np.eye(3), MU, LAM)).all()  # materials.rs:277-279
 
