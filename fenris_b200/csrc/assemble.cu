@@ -790,11 +790,13 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     TileLists& tl = ctx->tiles;
     const int32_t* d_ids = ctx->d_order;
     const uint64_t count = ctx->order_count;
-    if ((tl.valid || tl.unusable) && tl.count == count && tl.ids == d_ids && tl.tile_bits == shape.tile_bits) return FB200_OK;
+    if ((tl.valid || tl.unusable) && tl.count == count && tl.ids == d_ids && tl.tile_bits == shape.tile_bits && tl.flush_rot == shape.flush_rot)
+        return FB200_OK;
     free_tiles(tl);
     tl.count = count;
     tl.ids = d_ids;
     tl.tile_bits = shape.tile_bits;
+    tl.flush_rot = shape.flush_rot;
     if (ctx->h_order_codes.size() != count) {
         tl.unusable = true;
         return FB200_OK;
@@ -830,7 +832,7 @@ static int hex8_tile_setting(const fb200_ctx* ctx) {
 
 // Hex8 tile kernel (hex8_tile_kernel.cuh): a CTA accumulates a tile of the Morton order in shared memory and updates every CSR
 // node block of the tile once.  *used = false when the mesh has no usable tile lists (the caller falls back to the element kernel).
-template <int OP, int MAXN, int MAXP>
+template <int OP, int MAXN, int MAXP, bool ROT>
 static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const TileShape& shape, bool* used) {
     *used = false;
     FB200_TRY(ensure_tiles(ctx, shape));
@@ -846,7 +848,7 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
     p.tile_emap = tl.d_emap;
     p.tile_elem = tl.d_elem;
     const size_t smem = Hex8TileSmem<OP, MAXN, MAXP>::bytes;
-    auto kernel = assemble_hex8_tile_kernel<OP, MAXN, MAXP>;
+    auto kernel = assemble_hex8_tile_kernel<OP, MAXN, MAXP, ROT>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     constexpr int THREADS = (2 * kTileGroupWarps + kTileHelperWarps) * 32;
@@ -866,8 +868,13 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
 template <int OP>
 static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* used) {
     *used = false;
-    if (hex8_tile_setting(ctx) == 64) return launch_hex8_tile_t<OP, 128, 1216>(ctx, p, kHex8TileShape, used);
-    return FB200_OK;
+    if (hex8_tile_setting(ctx) != 64) return FB200_OK;
+    if (ctx->tune_flush_rot) {  // opt-in: rotated flush reads (fb200_set_tuning("hex8_flush_rot"), profiles/r01/README.md)
+        TileShape shape = kHex8TileShape;
+        shape.flush_rot = 1;
+        return launch_hex8_tile_t<OP, 128, 1216, true>(ctx, p, shape, used);
+    }
+    return launch_hex8_tile_t<OP, 128, 1216, false>(ctx, p, kHex8TileShape, used);
 }
 
 // Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)

@@ -60,6 +60,7 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
+constexpr int kTileKBitsRot = 11;  // ... when the two top bits carry the row rotation of the entry (TileShape::flush_rot)
 constexpr int kTileHdrWords = 8;   // first schedule position, rounds, n_nodes, n_slots(P), node_begin, flush_begin, n_flush, n_elems
 struct TileShape {
     int tile_bits;    // low Morton bits dropped to name a tile (5: 4 x 4 x 2 elements, 6: 4 x 4 x 4)
@@ -67,11 +68,14 @@ struct TileShape {
     int warps;        // elements per round = warps per compute group
     int max_nodes;    // distinct nodes per tile (<= 128)
     int max_slots;    // accumulator positions per tile (upper-triangle node blocks + padding)
+    int flush_rot = 0;  // 1: flush words carry a per-entry rotation (bits 30-31) of the block row a lane reads first, chosen to spread the
+                        // shared-memory banks of a flush half-warp (opt-in: fb200_set_tuning("hex8_flush_rot"); k narrows to 11 bits)
 };
 struct HostTiles {
     std::vector<uint32_t> hdr;        // num_tiles * kTileHdrWords
     std::vector<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
     std::vector<uint32_t> flush;      // per (row node u, coupled node v) in CSR order: position | transposed << 11 | u << 12 | k << 19
+                                      // (| rotation << 30 with TileShape::flush_rot)
     std::vector<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
     std::vector<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
     std::vector<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
@@ -86,6 +90,7 @@ struct TileLists {
     uint64_t count = 0;
     const int32_t* ids = nullptr;
     int tile_bits = 0;
+    int flush_rot = 0;
     uint32_t num_tiles = 0;
     uint32_t* d_hdr = nullptr;
     int32_t* d_nodes = nullptr;
@@ -145,6 +150,7 @@ struct fb200_ctx {
     fb200::ChunkLists chunks;
     fb200::TileLists tiles;
     int tune_hex8_tile = -1;  // fb200_set_tuning("hex8_tile"); -1 = FB200_HEX8_TILE from the environment, else 64
+    int tune_flush_rot = 0;   // fb200_set_tuning("hex8_flush_rot"): rotated flush reads (see TileShape::flush_rot), off by default
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;

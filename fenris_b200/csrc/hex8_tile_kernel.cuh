@@ -81,7 +81,8 @@ struct Hex8TileSmem {
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int OP, int MAXN, int MAXP>
+// ROT: the flush words carry a per-entry rotation of the block row a lane reads first (TileShape::flush_rot, tiles.cpp) - opt-in
+template <int OP, int MAXN, int MAXP, bool ROT = false>
 __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32, 1) assemble_hex8_tile_kernel(const AssembleParams p) {
     using L = Hex8TileSmem<OP, MAXN, MAXP>;
     constexpr int N = 8, D = 3, S = L::S, BS = L::BS, GS = L::GS, WARPS = L::WARPS, GW = kTileGroupWarps;
@@ -226,19 +227,23 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                         const bool tr = (a >> 11) & 1u;
                         const double* src = pacc + (int)(a & 0x7ffu) * BS + (tr ? j * S : j);
                         const int sstride = tr ? 1 : S;
-                        double* dst = p.values + (base + (long long)(S * (int)(a >> 19) + j));
+                        const int kcol = ROT ? (int)((a >> 19) & ((1u << kTileKBitsRot) - 1u)) : (int)(a >> 19);
+                        const int rot = (ROT && S == 3) ? (int)(a >> 30) : 0;
+                        // row read by load i (and written by store i): i, or rotated per entry so that a half-warp spreads over the banks
+                        auto row_of = [&](int i) { return ROT ? (i + rot >= S ? i + rot - S : i + rot) : i; };
+                        double* dst = p.values + (base + (long long)(S * kcol + j));
                         double v[S];
 #pragma unroll
-                        for (int i = 0; i < S; ++i) v[i] = src[i * sstride];
+                        for (int i = 0; i < S; ++i) v[i] = src[row_of(i) * sstride];
                         if (dbg & 2) continue;
                         if (__all_sync(FULL, rlf < 0 || !ok)) {
                             if (ok) {
 #pragma unroll
-                                for (int i = 0; i < S; ++i) dst[(long long)i * rl] = v[i];
+                                for (int i = 0; i < S; ++i) dst[(long long)row_of(i) * rl] = v[i];
                             }
                         } else if (ok) {
 #pragma unroll
-                            for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
+                            for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)row_of(i) * rl, v[i], pol_keep);
                         }
                     }
                 };

@@ -94,6 +94,58 @@ struct Builder {
         (void)ne;
     }
 
+    // Flush reads (hex8_tile_kernel.cuh): item 3 e + j of the list is lane (entry e, column j); it reads the words 9 pos + 3 i + j
+    // (transposed: 9 pos + 3 j + i) for i = 0, 1, 2 in three loads, 16 lanes = 16 eight-byte banks per half-warp.  Entries of one row
+    // share few bank classes (pos mod 16 = 4 alpha(u) + ...), so consecutive entries collide.  With a rotation r_e the lane reads row
+    // (i + r_e) mod 3 in load i: chosen greedily, entry by entry, to minimise the bank maxima of the half-warps the entry touches.
+    static void rotate_flush_rows(std::vector<uint32_t>& flush) {
+        const size_t nf = flush.size();
+        const size_t halves = (3 * nf + 15) / 16;
+        std::vector<uint8_t> count(halves * 3 * 16, 0);  // [half-warp][load][bank]
+        std::vector<uint8_t> peak(halves * 3, 0);
+        for (size_t e = 0; e < nf; ++e) {
+            const uint32_t a = flush[e];
+            const int pos = (int)(a & 0x7ffu);
+            const bool tr = (a >> 11) & 1u;
+            int best = 0, best_cost = 1 << 30;
+            for (int r = 0; r < 3; ++r) {
+                int cost = 0;
+                for (int i = 0; i < 3; ++i) {
+                    const int ii = (i + r) % 3;
+                    uint8_t add[2][16] = {{0}};  // the entry's lanes may straddle two half-warps
+                    const size_t h0 = (3 * e) / 16;
+                    for (int j = 0; j < 3; ++j) {
+                        const size_t h = (3 * e + j) / 16;
+                        const int word = pos * 9 + (tr ? j * 3 + ii : ii * 3 + j);
+                        ++add[h - h0][word & 15];
+                    }
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (h0 + hh >= halves) continue;
+                        int m = peak[(h0 + hh) * 3 + i];
+                        for (int b = 0; b < 16; ++b)
+                            if (add[hh][b]) m = std::max<int>(m, count[((h0 + hh) * 3 + i) * 16 + b] + add[hh][b]);
+                        cost += m - peak[(h0 + hh) * 3 + i];
+                    }
+                }
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best = r;
+                }
+            }
+            for (int i = 0; i < 3; ++i) {
+                const int ii = (i + best) % 3;
+                for (int j = 0; j < 3; ++j) {
+                    const size_t h = (3 * e + j) / 16;
+                    const int word = pos * 9 + (tr ? j * 3 + ii : ii * 3 + j);
+                    uint8_t& c = count[(h * 3 + i) * 16 + (word & 15)];
+                    ++c;
+                    peak[h * 3 + i] = std::max(peak[h * 3 + i], c);
+                }
+            }
+            flush[e] = a | ((uint32_t)best << 30);
+        }
+    }
+
     bool build_one(uint64_t p0, int ne, TileOut& t) {
         constexpr int n = 8, n2 = 64;
         // ---- nodes
@@ -205,9 +257,10 @@ struct Builder {
                         }
                     tr = 1;
                 }
-                if (x.k >= (1u << kTileKBits)) degenerate = true;
+                if (x.k >= (1u << (shape.flush_rot ? kTileKBitsRot : kTileKBits))) degenerate = true;
                 t.flush.push_back(pos | (tr << 11) | ((uint32_t)u << 12) | ((uint32_t)x.k << 19));
             }
+        if (shape.flush_rot) rotate_flush_rows(t.flush);
         // ---- schedule: greedy node-disjoint colouring inside the tile; every colour class is cut into rounds of at most
         // `warps` elements; rounds are padded to `warps` schedule positions (padding: node byte 0 = 0xff, no accumulators)
         std::vector<uint64_t> node_mask(nn, 0);
@@ -358,6 +411,15 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
 // ---------------------------------------------------------------------------------------------------------------- host self check
 extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
                                                   uint64_t num_owned, uint64_t stats[8], int32_t* failed_check) {
+    uint64_t st[10];
+    const fb200_status s = fb200_tile_lists_selftest_ex(num_nodes, vertices, num_elements, connectivity, num_owned, 0, st, failed_check);
+    if (s == FB200_OK && stats) std::copy(st, st + 8, stats);
+    return s;
+}
+
+extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const double* vertices, uint64_t num_elements,
+                                                     const uint64_t* connectivity, uint64_t num_owned, int32_t flush_rot, uint64_t stats[10],
+                                                     int32_t* failed_check) {
     using namespace fb200;
     constexpr int n = 8, n2 = 64;
     if (failed_check) *failed_check = 0;
@@ -396,7 +458,10 @@ extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const doub
             order.push_back(order_all[i]);
             codes.push_back(codes_all[i]);
         }
-    const TileShape shape{6, 64, 8, 128, 1216};
+    TileShape shape{6, 64, 8, 128, 1216};
+    shape.flush_rot = flush_rot ? 1 : 0;
+    const int kbits = shape.flush_rot ? kTileKBitsRot : kTileKBits;
+    uint64_t flush_loads = 0, flush_wavefronts = 0;  // model of the flush's shared-memory reads (see Builder::rotate_flush_rows)
     HostTiles ht;
     build_tile_lists(shape, order.size(), order.data(), codes.data(), conn.data(), num_elements, num_nodes, map.data(), ht);
     if (ht.bank_conflict_share < 0.0) return FB200_ERR_UNSUPPORTED;
@@ -474,8 +539,9 @@ extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const doub
         uint32_t last_u = 0, last_k = 0;
         for (uint32_t f = 0; f < nf; ++f) {
             const uint32_t w = ht.flush[fb + f];
-            const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = w >> 19;
+            const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = (w >> 19) & ((1u << kbits) - 1u);
             if (u >= nn) return fail_check(13);
+            if ((w >> 19) >> kbits >= 3u || (!shape.flush_rot && (w >> 19) >> kbits)) return fail_check(21);  // rotation 0..2, none without the flag
             if (f && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
             last_u = u;
             last_k = k;
@@ -490,6 +556,27 @@ extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const doub
             const auto pit = std::lower_bound(pairs.begin(), pairs.end(), std::make_pair(key, 0u));
             if (pit == pairs.end() || pit->first != key || pit->second != ps) return fail_check(18);
         }
+        // the three 64-bit loads of every 32-item group: two half-warps each, max distinct words per 8-byte bank
+        for (uint32_t g = 0; g < 3 * nf; g += 16)
+            for (int i = 0; i < 3; ++i) {
+                int words[16], cnt = 0, worst = 0;
+                for (uint32_t it = g; it < std::min(g + 16, 3 * nf); ++it) {
+                    const uint32_t w = ht.flush[fb + it / 3];
+                    const int j = (int)(it % 3), ii = (i + (int)(shape.flush_rot ? w >> 30 : 0)) % 3;
+                    words[cnt++] = (int)(w & 0x7ffu) * 9 + (((w >> 11) & 1u) ? j * 3 + ii : ii * 3 + j);
+                }
+                for (int b = 0; b < 16; ++b) {
+                    int m = 0;
+                    for (int x = 0; x < cnt; ++x) {
+                        bool first = (words[x] & 15) == b;
+                        for (int y = 0; first && y < x; ++y) first = words[y] != words[x];
+                        m += first;
+                    }
+                    worst = std::max(worst, m);
+                }
+                flush_wavefronts += worst;
+                flush_loads += (g % 32 == 0);
+            }
         for (uint32_t u = 0; u < nn; ++u) {
             const bool flag = ht.nodes[nb + u] < 0;
             if (flag != (inc[u] == degree[ht.nodes[nb + u] & 0x7fffffff])) return fail_check(19);
@@ -506,5 +593,7 @@ extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const doub
     stats[5] = (uint64_t)(ht.bank_conflict_share * 1e6);
     stats[6] = scheduled;
     stats[7] = max_rounds;
+    stats[8] = flush_loads;
+    stats[9] = flush_wavefronts;
     return FB200_OK;
 }

@@ -110,7 +110,9 @@ fb200_status fb200_timer_end(fb200_ctx* ctx, float* milliseconds); /* synchroniz
 /* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t fb200_launch_count(fb200_ctx* ctx);
 /* Kernel-selection knobs (no reference counterpart; results never depend on them beyond fp reassociation).
- * "hex8_tile": elements per shared-memory tile of the Hex8 atomic scatter - 64 (default) or 0 = per-element kernel. */
+ * "hex8_tile": elements per shared-memory tile of the Hex8 atomic scatter - 64 (default) or 0 = per-element kernel.
+ * "hex8_flush_rot": 1 = the tile kernel's flush reads its accumulator rows in a per-entry rotated order chosen on the host to spread the
+ *   shared-memory banks (same sums; block rows limited to 2048 coupled nodes); 0 (default) = rows in order. */
 fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value);
 
 /* ---- the space: Mesh<f64, D, C>  (src/mesh.rs:23-40) --------------------------------------- */
@@ -270,7 +272,11 @@ void fb200_lame_from_young_poisson(double young, double poisson, double* mu, dou
  * coupled pair of the tile exactly once with the right position in the CSR block row, complete flags, size limits.
  * stats[0..7] = tiles, max nodes, max accumulator positions, flush entries, complete nodes, bank-conflict share * 1e6, schedule positions,
  * max rounds.  Returns FB200_OK, FB200_ERR_UNSUPPORTED when the mesh cannot use tiles (repeated nodes), FB200_ERR_STATE + (*failed_check = id)
- * when a check fails. */
+ * when a check fails.  The _ex form also builds the lists with the rotated flush reads (flush_rot != 0, see fb200_set_tuning
+ * "hex8_flush_rot") and reports a model of the flush's shared-memory reads: stats[8] = 64-bit loads per warp, stats[9] = their wavefronts
+ * (two half-warps per load, max distinct words per 8-byte bank; 2 per load is conflict free). */
+fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
+                                          uint64_t num_owned, int32_t flush_rot, uint64_t stats[10], int32_t* failed_check);
 fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
                                        uint64_t num_owned, uint64_t stats[8], int32_t* failed_check);
 

@@ -3,6 +3,8 @@
 The tile kernel replaces the per-element row scatter of global.rs:155-178, 504-537 for Hex8 + ATOMIC; the per-element
 kernel (hex8_tile = 0), the coloured and the gather scatter are independent implementations of the same sums.
 Tolerance: 1e-12 relative Frobenius norm (north_star); symmetry to rounding."""
+import os
+
 import numpy as np
 import pytest
 
@@ -175,3 +177,24 @@ def test_tile_repeatable(ctx):
     a = ctx.values_download().copy()
     _assemble(ctx, m, fo.LINEAR_ELASTIC, 64)
     assert fo.rel_frobenius(ctx.values_download(), a) < 1e-15
+
+
+@pytest.mark.skipif(not os.environ.get("FB200_TEST_EXPERIMENTAL"),
+                    reason="opt-in kernel variant written after the round's GPU budget was spent; enable once measured (profiles/r01/README.md)")
+@pytest.mark.parametrize("n,op,scramble", [(9, fo.LINEAR_ELASTIC, False), (10, fo.LAPLACE, False), (7, fo.LINEAR_ELASTIC, True)])
+def test_tile_rotated_flush_equals_default(ctx, n, op, scramble):
+    # fb200_set_tuning("hex8_flush_rot", 1): every lane reads and writes the same three (row, column) entries, in a rotated order
+    m = _hex(n, 0.15, scramble)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(1 if op == fo.LAPLACE else 3)
+    _assemble(ctx, m, op, 64)
+    ref = ctx.values_download().copy()
+    ctx.set_tuning("hex8_flush_rot", 1)
+    try:
+        ctx.values_upload(np.full(ctx.nnz, 1e300))
+        prob = _assemble(ctx, m, op, 64)
+        vals = ctx.values_download().copy()
+    finally:
+        ctx.set_tuning("hex8_flush_rot", 0)
+    assert fo.rel_frobenius(vals, ref) < 1e-15
+    assert fo.rel_frobenius(vals, fo.assemble_fast(prob)[2]) < TOL

@@ -21,6 +21,16 @@ def _selftest(v, c, owned=None):
     return st, failed.value, list(stats)
 
 
+def _selftest_ex(v, c, flush_rot, owned=None):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.uint64)
+    stats = (C.c_uint64 * 10)()
+    failed = C.c_int32(0)
+    st = nat.lib().fb200_tile_lists_selftest_ex(len(v), nat.ptr(v), len(c), nat.ptr(c), len(c) if owned is None else owned, flush_rot, stats,
+                                                C.byref(failed))
+    return st, failed.value, list(stats)
+
+
 @pytest.mark.parametrize("n", [1, 3, 4, 8, 13])
 def test_structured_cubes(n):
     m = fb.create_unit_box_uniform_hex_mesh_3d(n)
@@ -69,3 +79,28 @@ def test_index_out_of_bounds():
     c = m.connectivity().copy()
     c[0, 0] = m.num_nodes()
     assert _selftest(m.vertices(), c)[0] == nat.ERR_INDEX_OOB
+
+
+def test_rotated_flush_lists_keep_every_invariant_and_spread_the_banks():
+    # opt-in fb200_set_tuning("hex8_flush_rot"): the flush words carry a rotation (bits 30-31) of the block row a lane reads first.
+    # Same lists otherwise (all 21 checks), and the modelled shared-memory wavefronts per flush load drop (the model reproduces the
+    # ncu source counters of the shipped order: 6.2 vs 5.6-6.6 measured, profiles/r01/README.md)
+    m = fb.create_unit_box_uniform_hex_mesh_3d(12)
+    st0, failed0, s0 = _selftest_ex(m.vertices(), m.connectivity(), 0)
+    st1, failed1, s1 = _selftest_ex(m.vertices(), m.connectivity(), 1)
+    assert st0 == nat.OK and st1 == nat.OK, (failed0, failed1)
+    assert s0[:8] == s1[:8] and s0[8] == s1[8] > 0
+    per_load0, per_load1 = s0[9] / s0[8], s1[9] / s1[8]
+    assert 5.5 < per_load0 < 6.8 and per_load1 < 0.72 * per_load0 and per_load1 >= 2.0
+    # unstructured numbering, ghosts
+    v = fo.jitter_vertices(m.vertices(), 1.0 / 12, amp=0.2)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(v))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(v))
+    c = inv[m.connectivity().astype(np.int64)][rng.permutation(m.num_elements())]
+    st, failed, s = _selftest_ex(v[perm], c, 1)
+    assert st == nat.OK, f"check {failed} failed"
+    verts, conn, n_owned, _ = structured_hex_slab(8, 8, 12, 1.0 / 8, 1, 3)
+    st, failed, s = _selftest_ex(verts, conn, 1, owned=n_owned)
+    assert st == nat.OK, f"check {failed} failed"
