@@ -13,7 +13,7 @@ The reference has no distributed mode (README.md:58); this is the north-star ext
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+from typing import List
 
 import numpy as np
 

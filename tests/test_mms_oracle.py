@@ -1,7 +1,6 @@
 """End-to-end pin of the ORACLE's global Laplace matrices against the reference's stored convergence results
 (tests/convergence_tests/reference_values/poisson{2d,3d}_mms_{quad4,hex8,tet4}_summary.json; 1 % tolerance as in
 poisson_mms_common.rs:40-65).  CPU only."""
-import numpy as np
 import pytest
 
 from oracle import fenris_oracle as fo
