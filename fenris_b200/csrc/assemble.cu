@@ -869,7 +869,8 @@ template <int OP>
 static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* used) {
     *used = false;
     if (hex8_tile_setting(ctx) != 64) return FB200_OK;
-    if (ctx->tune_flush_rot) {  // opt-in: rotated flush reads (fb200_set_tuning("hex8_flush_rot"), profiles/r01/README.md)
+    static const int env_rot = std::getenv("FB200_HEX8_FLUSH_ROT") ? std::atoi(std::getenv("FB200_HEX8_FLUSH_ROT")) : 0;
+    if (ctx->tune_flush_rot >= 0 ? ctx->tune_flush_rot != 0 : env_rot != 0) {  // opt-in: rotated flush reads (fb200_set_tuning("hex8_flush_rot"), profiles/r01/README.md)
         TileShape shape = kHex8TileShape;
         shape.flush_rot = 1;
         return launch_hex8_tile_t<OP, 128, 1216, true>(ctx, p, shape, used);

@@ -150,7 +150,8 @@ struct fb200_ctx {
     fb200::ChunkLists chunks;
     fb200::TileLists tiles;
     int tune_hex8_tile = -1;  // fb200_set_tuning("hex8_tile"); -1 = FB200_HEX8_TILE from the environment, else 64
-    int tune_flush_rot = 0;   // fb200_set_tuning("hex8_flush_rot"): rotated flush reads (see TileShape::flush_rot), off by default
+    int tune_flush_rot = -1;  // fb200_set_tuning("hex8_flush_rot"): rotated flush reads (see TileShape::flush_rot); -1 = FB200_HEX8_FLUSH_ROT
+                              // from the environment, else off
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;
