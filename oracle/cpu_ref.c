@@ -56,9 +56,12 @@
 
 typedef uint64_t u64;
 
+/* Threads the CPU path can use: the processors available to the process, NOT omp_get_max_threads() - torchrun exports
+ * OMP_NUM_THREADS=1 to every rank, which would silently time the multi-rank reference arm of bench.py on one thread. */
 int oref_max_threads(void) {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    int n = omp_get_num_procs();
+    return n > 0 ? n : 1;
 #else
     return 1;
 #endif
@@ -341,7 +344,7 @@ int oref_assemble_colored(int elem_type, int op, int q, const double* w, const d
     u64 c;
     if (st) return st;
 #ifdef _OPENMP
-    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    if (nthreads <= 0) nthreads = oref_max_threads();
 #else
     nthreads = 1;
 #endif
