@@ -156,3 +156,50 @@ def test_neo_hookean_tangent_is_the_derivative_of_the_element_vector(et, mesh):
     assert np.abs(K - Kfd).max() < 1e-7 * np.abs(K).max() and np.array_equal(K, K.T)
     f = fo.element_elliptic_vector(et, X, fo.NEO_HOOKEAN, u, *args)
     assert np.abs(f - ffd).max() < 1e-7 * np.abs(f).max()
+
+
+def _rotation(d, rng):
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_hyperelastic_materials_are_frame_indifferent(d):
+    # psi(Q F) = psi(F) and P(Q F) = Q P(F) for rotations Q: holds for StVK and NeoHookean, not for the linear material
+    rng = np.random.default_rng(31)
+    F = np.eye(d) + 0.2 * rng.normal(size=(d, d))
+    Q = _rotation(d, rng)
+    for energy, stress in ((lambda G: fo.stvk_energy_density(G, MU, LAM), lambda G: fo.stvk_stress(G, MU, LAM)),
+                           (lambda G: fo.neo_hookean_energy_density_du((G - np.eye(d)).T, MU, LAM), lambda G: fo.neo_hookean_stress(G, MU, LAM))):
+        assert abs(energy(Q @ F) - energy(F)) < 1e-11 * abs(energy(F))
+        assert np.abs(stress(Q @ F) - Q @ stress(F)).max() < 1e-11 * np.abs(stress(F)).max()
+
+
+@pytest.mark.parametrize("mat", [fo.STVK, fo.NEO_HOOKEAN])
+def test_rigid_rotation_produces_no_internal_forces_and_no_energy(mat):
+    # u(X) = (Q - I) X + t on a jittered Hex8 mesh: F = Q exactly for the trilinear element, so E = 0, P = 0, psi = 0
+    v, c = fo.create_unit_box_uniform_hex_mesh_3d(2)
+    v = fo.jitter_vertices(v, 0.5, amp=0.15)
+    rng = np.random.default_rng(8)
+    Q = _rotation(3, rng)
+    u = (v @ (Q - np.eye(3)).T + np.array([0.3, -0.2, 0.1])).reshape(-1)
+    prob = fo.Problem(fo.HEX8, v, c, mat, params=(MU, LAM))
+    f = fo.assemble_elliptic_vector_serial(prob, u)
+    scale = MU * np.abs(u).max()
+    assert np.abs(f).max() < 1e-11 * scale
+    assert abs(fo.assemble_elliptic_scalar(prob, u)) < 1e-11 * scale
+    # the linear material does see a finite rotation
+    lin = fo.Problem(fo.HEX8, v, c, fo.LINEAR_ELASTIC, params=(MU, LAM))
+    assert np.abs(fo.assemble_elliptic_vector_serial(lin, u)).max() > 1e-3 * scale
+    # and the tangent at the rotated state has the infinitesimal rigid motions of the CURRENT configuration in its null space
+    _, _, k = fo.assemble_matrix_u_serial(fo.HEX8, v, c, mat, u, prob.weights, prob.points, prob.params_per_point)
+    ro, ci = fo.assemble_pattern(3, len(v), c.tolist())
+    import scipy.sparse as sp
+    K = sp.csr_matrix((k, ci, ro), shape=(3 * len(v),) * 2)
+    x = v @ Q.T  # current positions (up to the translation)
+    W = np.array([[0.0, -1.0, 0.5], [1.0, 0.0, -0.3], [-0.5, 0.3, 0.0]])  # skew: w(x) = W x
+    w = (x @ W.T).reshape(-1)
+    assert np.abs(K @ w).max() < 1e-10 * np.abs(k).max() * np.abs(w).max()
+    assert np.abs(K @ np.tile([1.0, 2.0, 3.0], len(v))).max() < 1e-10 * np.abs(k).max()
