@@ -16,26 +16,25 @@ MODES = {"atomic": 0, "colored": 1, "gather": 2}
 
 
 def measure_mass_or_vector(what, steps, peak):
-    from oracle import fenris_oracle as fo  # quadrature rule tables only (host side)
     mesh = fb.create_unit_box_uniform_hex_mesh_3d(126)
     E, N = mesh.num_elements(), mesh.num_nodes()
     with fb.Context(0) as ctx:
         ctx.space_upload(mesh.element_type, mesh.vertices(), mesh.connectivity())
         if what == "mass":
-            w, p = fo.hexahedron_gauss(3)
+            w, p = fb.canonical_stiffness_quadrature(fb.HEX27)  # Gauss 3^3 (canonical.rs:102-112)
             nrows, nnz = ctx.assemble_pattern(3)
             fn = lambda: ctx.assemble_mass_into_csr_device(w, p, 1000.0, accumulate=False)
             b_algo = 4 * 8 * E + 8 * 3 * N + 4 * 64 * E + 16 * nnz
             name = "Hex8 mass matrix (s = 3, Gauss 3^3) on the C3 mesh, device-resident CSR"
         elif what == "stvk":  # tangent stiffness of StVKMaterial at u (u is copied host -> device inside the step)
-            w, p = fo.hexahedron_gauss(2)
+            w, p = fb.canonical_stiffness_quadrature(fb.HEX8)  # Gauss 2^3
             nrows, nnz = ctx.assemble_pattern(3)
             u = 0.01 * np.random.default_rng(0).normal(size=3 * N)
             fn = lambda: ctx.assemble_into_csr_device(fb.STVK, w, p, (3.0e5, 2.0e5), accumulate=False, u=u)
             b_algo = 4 * 8 * E + 8 * 3 * N + 8 * 3 * N + 4 * 64 * E + 16 * nnz
             name = "Hex8 StVK tangent stiffness at u (Gauss 2^3) on the C3 mesh, device-resident CSR"
         else:
-            w, p = fo.hexahedron_gauss(2)
+            w, p = fb.canonical_stiffness_quadrature(fb.HEX8)  # Gauss 2^3
             nnz = 0
             out = np.zeros(3 * N)
             g = np.tile([0.0, -9.81, 0.0], (len(w), 1))
@@ -56,10 +55,9 @@ def measure_mass_or_vector(what, steps, peak):
 
 def measure_cg(peak):
     import time
-    from oracle import fenris_oracle as fo
     mesh = fb.create_unit_box_uniform_hex_mesh_3d(126)
     lame = fb.LameParameters.from_young_poisson(fb.YoungPoisson(1e6, 0.2))
-    w, p = fo.hexahedron_gauss(2)
+    w, p = fb.canonical_stiffness_quadrature(fb.HEX8)  # Gauss 2^3
     N = mesh.num_nodes()
     with fb.Context(0) as ctx:
         ctx.space_upload(mesh.element_type, mesh.vertices(), mesh.connectivity())
