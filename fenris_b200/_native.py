@@ -113,6 +113,7 @@ def lib():
         "fb200_interface_set": (i32, [vp, u64, vp, vp, u64]),
         "fb200_interface_set_peers": (i32, [vp, u64, vp, vp, vp]),
         "fb200_interface_allreduce": (i32, [vp]),
+        "fb200_interface_enable_p2p": (i32, [vp]),
         "fb200_gen_hex_mesh": (i32, [u64, u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_gen_tet_mesh": (i32, [u64, u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_gen_quad_mesh": (i32, [u64, u64, dbl, pu64, pu64, vp, vp]),

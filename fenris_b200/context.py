@@ -350,3 +350,12 @@ class Context:
 
     def interface_allreduce(self):
         self._check(self._lib.fb200_interface_allreduce(self._h))
+
+    def interface_enable_p2p(self) -> bool:
+        """Fuse the interface exchange into the tile kernel's flush (peer-mapped values over NVLink).  Collective over the neighbours.
+        Returns False when the partition / the machine cannot use it (the packed ncclSend/ncclRecv exchange then stays in use)."""
+        st = self._lib.fb200_interface_enable_p2p(self._h)
+        if st == nat.ERR_UNSUPPORTED:
+            return False
+        self._check(st)
+        return True

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "fb200_internal.h"
 
@@ -85,7 +86,23 @@ struct AssembleParams {
     const uint8_t* tile_lnodes;
     const uint16_t* tile_emap;
     const int32_t* tile_elem;
+    const uint32_t* tile_wait;   // owner stores: tiles whose published stores a tile's reductions wait for
+    uint32_t* tile_flag;         // ... per tile: epoch of the last launch whose stores of the tile are published
+    uint32_t tile_epoch;         // ... this launch's epoch; 0 = no ownership (the values were zero-filled, complete rows are stored)
+    int tile_static;             // tiles round-robin over the CTAs instead of an atomic ticket
+    // fused interface exchange (comm.cu): per node 0, or (block-row offset on the neighbouring rank + 1) | neighbour slot << 31
+    const uint32_t* peer_row;
+    double* peer_values[2];
 };
+
+// an overwriting assembly ("values = contributions", global.rs:124-131) was requested and nothing has cleared the values yet: every
+// launcher calls this before its first kernel - except the Hex8 tile kernel with owner lists, which stores every row itself
+static fb200_status clear_values_if_pending(fb200_ctx* ctx) {
+    if (!ctx->pending_zero) return FB200_OK;
+    ctx->pending_zero = false;
+    if (ctx->nnz) FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
+    return FB200_OK;
+}
 
 __device__ __forceinline__ void flag_error(unsigned long long* errword, uint64_t elem, int code) {
     atomicMin(errword, ((unsigned long long)elem << 8) | (unsigned long long)code);
@@ -468,7 +485,15 @@ fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200
         // Laplace has no parameters: express it through the general path with mu = 1, lambda = 0
         for (int k = 0; k < nq; ++k) { mu[k] = 1.0; lam[k] = 0.0; }
     }
-    if (ctx->tab.d_data && ctx->tab.host == h) return FB200_OK;  // unchanged tables stay resident (no sync per call)
+    // unchanged tables stay resident (no sync per call).  The derived fields depend on the operator kind as well - a Laplace table and an
+    // elastic table with mu = lambda = 0 have identical contents - so they are refreshed on a hit too.
+    const bool hit = ctx->tab.d_data && ctx->tab.host == h;
+    ctx->tab.nq = nq;
+    ctx->tab.uniform_params = uniform;
+    ctx->tab.mu0 = op->kind == FB200_LINEAR_ELASTIC ? mu[0] : 1.0;
+    ctx->tab.lam0 = op->kind == FB200_LINEAR_ELASTIC ? lam[0] : 0.0;
+    if (hit) return FB200_OK;
+    ctx->tab.host.clear();  // (a failed upload below must not leave a stale key)
     if (ctx->tab.capacity < len) {
         dev_free(ctx->tab.d_data);
         FB200_TRY(dev_alloc(ctx, &ctx->tab.d_data, len));
@@ -477,15 +502,12 @@ fb200_status upload_tables(fb200_ctx* ctx, const fb200_operator* op, const fb200
     FB200_CUDA(ctx, cudaMemcpyAsync(ctx->tab.d_data, h.data(), len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h is pageable
     ctx->tab.host = h;
-    ctx->tab.nq = nq;
-    ctx->tab.uniform_params = uniform;
-    ctx->tab.mu0 = op->kind == FB200_LINEAR_ELASTIC ? mu[0] : 1.0;
-    ctx->tab.lam0 = op->kind == FB200_LINEAR_ELASTIC ? lam[0] : 0.0;
     return FB200_OK;
 }
 
 template <int N, int NG, int D, int OP, int MODE>
 static fb200_status launch_elements(fb200_ctx* ctx, AssembleParams& p) {
+    FB200_TRY(clear_values_if_pending(ctx));
     constexpr int G = (N <= 4) ? 8 : 32;
     constexpr int THREADS = 128;
     constexpr int SLOTS = THREADS / G;
@@ -618,6 +640,7 @@ static fb200_status ensure_ordered(fb200_ctx* ctx, OrderedCopy& oc, const int32_
 
 template <int OP, int MODE, int MINB, bool DYN, bool HINT, int CHUNK = 8, bool ZFUSE = false>
 static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
+    if (!ZFUSE) FB200_TRY(clear_values_if_pending(ctx));
     constexpr int THREADS = 128, WARPS = THREADS / 32;
     constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8, TS = 33;
     constexpr int KLEN = S == 1 ? SN * (SN + 1) : SN * SN + 4;
@@ -653,6 +676,7 @@ static fb200_status launch_hex8(fb200_ctx* ctx, AssembleParams& p) {
 // FP64 tensor-core variant (hex8_mma_kernel.cuh): reference gradients in registers, S = G G^T by DMMA
 template <int OP, int MODE, bool DYN, bool HINT, int CHUNK = 8>
 static fb200_status launch_hex8_mma(fb200_ctx* ctx, AssembleParams& p) {
+    FB200_TRY(clear_values_if_pending(ctx));
     constexpr int THREADS = 128, WARPS = THREADS / 32, MINB = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : 3, SN = S * 8;
     constexpr int KLEN = S == 1 ? SN * (SN + 1) : SN * SN + 4;
@@ -693,7 +717,7 @@ static void free_chunks(ChunkLists& cl) {
 template <class T>
 static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T>& h) {
     FB200_TRY(dev_alloc(ctx, d, h.size()));
-    if (!h.empty()) FB200_CUDA(ctx, cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!h.empty()) FB200_CUDA(ctx, h2d_copy(ctx, *d, h.data(), h.size() * sizeof(T)));
     return FB200_OK;
 }
 
@@ -736,6 +760,7 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
 
 template <int OP, int C, int T>
 static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
+    FB200_TRY(clear_values_if_pending(ctx));
     if (p.count == 0) return FB200_OK;
     FB200_TRY(ensure_chunks(ctx, ctx->d_order, ctx->order_count, C));
     const ChunkLists& cl = ctx->chunks;
@@ -776,27 +801,32 @@ static void free_tiles(TileLists& tl) {
     dev_free(tl.d_hdr);
     dev_free(tl.d_nodes);
     dev_free(tl.d_flush);
+    dev_free(tl.d_wait);
+    dev_free(tl.d_flag);
+    dev_free(tl.d_zero_nodes);
     dev_free(tl.d_lnodes);
     dev_free(tl.d_emap);
     dev_free(tl.d_elem);
     tl.valid = false;
     tl.unusable = false;
+    tl.owner = false;
     tl.count = 0;
     tl.ids = nullptr;
     tl.num_tiles = 0;
+    tl.zero_node_count = 0;
 }
 
 static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     TileLists& tl = ctx->tiles;
     const int32_t* d_ids = ctx->d_order;
     const uint64_t count = ctx->order_count;
-    if ((tl.valid || tl.unusable) && tl.count == count && tl.ids == d_ids && tl.tile_bits == shape.tile_bits && tl.flush_rot == shape.flush_rot)
+    if ((tl.valid || tl.unusable) && tl.count == count && tl.ids == d_ids && tl.tile_bits == shape.tile_bits && tl.owner_stores == shape.owner_stores)
         return FB200_OK;
     free_tiles(tl);
     tl.count = count;
     tl.ids = d_ids;
     tl.tile_bits = shape.tile_bits;
-    tl.flush_rot = shape.flush_rot;
+    tl.owner_stores = shape.owner_stores;
     if (ctx->h_order_codes.size() != count) {
         tl.unusable = true;
         return FB200_OK;
@@ -804,11 +834,13 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<int32_t> conn(ctx->E * 8), ids(count);
     std::vector<uint16_t> map(ctx->E * (uint64_t)64);
+    std::vector<int64_t> blk_off(ctx->N + 1);
     FB200_CUDA(ctx, cudaMemcpy(conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     FB200_CUDA(ctx, cudaMemcpy(ids.data(), d_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
     HostTiles ht;
-    build_tile_lists(shape, count, ids.data(), ctx->h_order_codes.data(), conn.data(), ctx->E, ctx->N, map.data(), ht);
+    build_tile_lists(shape, count, ids.data(), ctx->h_order_codes.data(), conn.data(), ctx->E, ctx->E_owned, ctx->N, map.data(), blk_off.data(), ht);
     if (ht.bank_conflict_share < 0.0 || ht.flush.size() >= (1ull << 32) || ht.nodes.size() >= (1ull << 32)) {
         tl.unusable = true;  // degenerate elements (repeated nodes) or lists beyond 32-bit offsets: keep the per-element kernel
         return FB200_OK;
@@ -817,9 +849,15 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     FB200_TRY(upload_vec(ctx, &tl.d_hdr, ht.hdr));
     FB200_TRY(upload_vec(ctx, &tl.d_nodes, ht.nodes));
     FB200_TRY(upload_vec(ctx, &tl.d_flush, ht.flush));
+    FB200_TRY(upload_vec(ctx, &tl.d_wait, ht.wait));
+    FB200_TRY(upload_vec(ctx, &tl.d_zero_nodes, ht.zero_nodes));
     FB200_TRY(upload_vec(ctx, &tl.d_lnodes, ht.lnodes));
     FB200_TRY(upload_vec(ctx, &tl.d_emap, ht.emap));
     FB200_TRY(upload_vec(ctx, &tl.d_elem, ht.elem));
+    FB200_TRY(dev_alloc(ctx, &tl.d_flag, tl.num_tiles));
+    FB200_CUDA(ctx, cudaMemsetAsync(tl.d_flag, 0, std::max<size_t>(tl.num_tiles, 1) * sizeof(uint32_t), ctx->stream));
+    tl.zero_node_count = ht.zero_nodes.size();
+    tl.owner = ht.owner_stores;
     tl.valid = true;
     return FB200_OK;
 }
@@ -829,16 +867,56 @@ static int hex8_tile_setting(const fb200_ctx* ctx) {
     static const int env_tile = std::getenv("FB200_HEX8_TILE") ? std::atoi(std::getenv("FB200_HEX8_TILE")) : 64;
     return ctx->tune_hex8_tile >= 0 ? ctx->tune_hex8_tile : env_tile;
 }
+static int hex8_owner_setting(const fb200_ctx* ctx) {
+    static const int env_owner = std::getenv("FB200_HEX8_OWNER") ? std::atoi(std::getenv("FB200_HEX8_OWNER")) : 1;
+    return (ctx->tune_owner >= 0 ? ctx->tune_owner : env_owner) ? 1 : 0;
+}
+
+// the s rows of every listed node = 0 (one warp per node)
+__global__ void zero_node_rows_kernel(const int32_t* __restrict__ nodes, uint64_t count, const int64_t* __restrict__ blk_off, int ss,
+                                      double* __restrict__ values) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t k = gwarp; k < count; k += nwarps) {
+        const int32_t node = nodes[k];
+        const int64_t b = blk_off[node];
+        const int64_t len = (blk_off[node + 1] - b) * ss;
+        double* v = values + b * ss;
+        for (int64_t t = lane; t < len; t += 32) v[t] = 0.0;
+    }
+}
 
 // Hex8 tile kernel (hex8_tile_kernel.cuh): a CTA accumulates a tile of the Morton order in shared memory and updates every CSR
 // node block of the tile once.  *used = false when the mesh has no usable tile lists (the caller falls back to the element kernel).
-template <int OP, int MAXN, int MAXP, bool ROT>
+template <int OP, int MAXN, int MAXP>
 static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const TileShape& shape, bool* used) {
     *used = false;
     FB200_TRY(ensure_tiles(ctx, shape));
     const TileLists& tl = ctx->tiles;
     if (!tl.valid) return FB200_OK;
     *used = true;
+    p.tile_epoch = 0;
+    if (ctx->pending_zero) {
+        if (tl.owner) {
+            // owner lists: every row has a storing tile, except the rows ghost elements touch (and rows of nodes without owned
+            // elements) - those few are cleared here
+            ctx->pending_zero = false;
+            if (++ctx->tile_epoch == 0) {  // the 32-bit epoch wrapped: restart the flags
+                FB200_CUDA(ctx, cudaMemsetAsync(tl.d_flag, 0, std::max<size_t>(tl.num_tiles, 1) * sizeof(uint32_t), ctx->stream));
+                ctx->tile_epoch = 1;
+            }
+            p.tile_epoch = ctx->tile_epoch;
+            if (tl.zero_node_count) {
+                const int ss = ctx->sdim * ctx->sdim;
+                const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(tl.zero_node_count * 32, 256), (uint64_t)ctx->sm_count * 8));
+                zero_node_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(tl.d_zero_nodes, tl.zero_node_count, ctx->d_blk_off, ss, ctx->d_values);
+                FB200_TRY(check_launch(ctx, "zero_node_rows_kernel"));
+            }
+        } else {
+            FB200_TRY(clear_values_if_pending(ctx));
+        }
+    }
     if (tl.num_tiles == 0) return FB200_OK;
     p.num_tiles = tl.num_tiles;
     p.tile_hdr = tl.d_hdr;
@@ -847,8 +925,20 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
     p.tile_lnodes = tl.d_lnodes;
     p.tile_emap = tl.d_emap;
     p.tile_elem = tl.d_elem;
+    p.tile_wait = tl.d_wait;
+    p.tile_flag = tl.d_flag;
+    // fused interface exchange (comm.cu): the flush also reduces interface rows into the neighbouring ranks' values.  The rows were
+    // just cleared when the call overwrites: no neighbour may add to them before that, hence the neighbour barrier
+    const bool peer = ctx->p2p.enabled && ctx->p2p.num_peers > 0;
+    if (peer) {
+        p.peer_row = ctx->p2p.d_peer_row;
+        p.peer_values[0] = ctx->p2p.values[0];
+        p.peer_values[1] = ctx->p2p.values[1];
+        if (!p.accumulate) FB200_TRY(p2p_neighbour_barrier(ctx));
+        ctx->p2p.pending = true;
+    }
     const size_t smem = Hex8TileSmem<OP, MAXN, MAXP>::bytes;
-    auto kernel = assemble_hex8_tile_kernel<OP, MAXN, MAXP, ROT>;
+    auto kernel = peer ? assemble_hex8_tile_kernel<OP, MAXN, MAXP, true> : assemble_hex8_tile_kernel<OP, MAXN, MAXP, false>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     constexpr int THREADS = (2 * kTileGroupWarps + kTileHelperWarps) * 32;
@@ -858,29 +948,40 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
     p.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
     static const int debug = std::getenv("FB200_DEBUG") ? std::atoi(std::getenv("FB200_DEBUG")) : 0;
     p.debug = debug;
+    // owner stores make a tile wait for lower-numbered tiles.  With the atomic ticket a CTA holds the six tiles it fetches tables for; a
+    // CTA that waits lets them age while the others take newer tiles that depend on exactly those: measured 5.3 - 6.2 ms per C3
+    // assembly instead of 2.45.  Round-robin keeps Morton neighbours in the same step of neighbouring CTAs: waits of ~3 polls, 2.58 ms
+    // (profiles/r02/README.md).  Without waits (accumulating call, zero-fill lists) the ticket balances the SMs better: 2.45 vs 2.52 ms.
+    static const int env_static = std::getenv("FB200_TILE_STATIC") ? std::atoi(std::getenv("FB200_TILE_STATIC")) : -1;
+    p.tile_static = env_static >= 0 ? env_static : (p.tile_epoch != 0 ? 1 : 0);
     FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
     kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+    if (debug & 64) {  // diagnostics of the owner-store waits (hex8_tile_kernel.cuh)
+        unsigned long long dc[16];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(dc, ctx->d_ticket, sizeof(dc), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[tile waits] blocked %llu spins %llu max %llu | owner distance: mean %.1f max %llu | blocked by distance <8 %llu <64 %llu <512 %llu more %llu | spins %llu %llu %llu %llu\n",
+                     dc[2], dc[3], dc[4], dc[2] ? (double)dc[5] / (double)dc[2] : 0.0, dc[6], dc[7], dc[8], dc[9], dc[10], dc[11], dc[12], dc[13], dc[14]);
+        cudaMemset(ctx->d_ticket, 0, sizeof(dc));
+    }
     return check_launch(ctx, "assemble_hex8_tile_kernel");
 }
 
 // tile shape: 4 x 4 x 4 elements, one CTA of 16 compute + 8 helper warps per SM (double-buffered accumulators: 2 x 85.5 KB);
-// FB200_HEX8_TILE = 64 | 0 (off), overridden by fb200_set_tuning("hex8_tile")
+// FB200_HEX8_TILE = 64 | 0 (off), overridden by fb200_set_tuning("hex8_tile"); FB200_HEX8_OWNER / "hex8_owner_stores": first-writer stores
 template <int OP>
 static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* used) {
     *used = false;
     if (hex8_tile_setting(ctx) != 64) return FB200_OK;
-    static const int env_rot = std::getenv("FB200_HEX8_FLUSH_ROT") ? std::atoi(std::getenv("FB200_HEX8_FLUSH_ROT")) : 0;
-    if (ctx->tune_flush_rot >= 0 ? ctx->tune_flush_rot != 0 : env_rot != 0) {  // opt-in: rotated flush reads (fb200_set_tuning("hex8_flush_rot"), profiles/r01/README.md)
-        TileShape shape = kHex8TileShape;
-        shape.flush_rot = 1;
-        return launch_hex8_tile_t<OP, 128, 1216, true>(ctx, p, shape, used);
-    }
-    return launch_hex8_tile_t<OP, 128, 1216, false>(ctx, p, kHex8TileShape, used);
+    TileShape shape = kHex8TileShape;
+    shape.owner_stores = hex8_owner_setting(ctx);
+    return launch_hex8_tile_t<OP, 128, 1216>(ctx, p, shape, used);
 }
 
 // Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)
 template <int OP, int MODE>
 static fb200_status launch_hex27_mma(fb200_ctx* ctx, AssembleParams& p) {
+    FB200_TRY(clear_values_if_pending(ctx));
     if (p.count == 0) return FB200_OK;
     const size_t smem = hex27_smem_bytes<OP>(p.nq);
     auto kernel = assemble_hex27_mma_kernel<OP, MODE>;
@@ -1119,6 +1220,10 @@ fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator
     if (scatter_mode == FB200_SCATTER_COLORED && !ctx->has_colors)
         return fail(ctx, FB200_ERR_STATE, "coloured scatter needs fb200_color_nodes or fb200_colors_adopt");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->p2p.pending) {  // a fused assembly was never closed by fb200_interface_allreduce: neighbours may still be adding to our rows
+        ctx->p2p.pending = false;
+        FB200_TRY(p2p_neighbour_barrier(ctx));
+    }
     FB200_TRY(upload_tables(ctx, op, q));
     if (scatter_mode == FB200_SCATTER_GATHER) FB200_TRY(build_adjacency(ctx));
     AssembleParams p;
@@ -1134,11 +1239,13 @@ fb200_status fb200_assemble_into_csr_device(fb200_ctx* ctx, const fb200_operator
                ctx->order_count == p.count && p.count > 0)
                   ? 1
                   : 0;
-    // (clearing only the rows that receive reductions - the tile kernel overwrites the rows of tile-complete nodes - was measured:
-    //  a row-list kernel reaches 4.7 TB/s on the 58 % it has to clear, no faster than the 7.4 TB/s memset of everything)
-    if (!accumulate && scatter_mode != FB200_SCATTER_GATHER && !p.zfuse)
-        FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_values, 0, ctx->nnz * sizeof(double), ctx->stream));
-    return dispatch(ctx, p, op->kind, scatter_mode);
+    // "values = contributions": whichever kernel runs first clears the values (clear_values_if_pending) - except the Hex8 tile kernel with
+    // owner lists, which stores every row itself and needs no zero-fill pass (hex8_tile_kernel.cuh "ownership")
+    ctx->pending_zero = !accumulate && scatter_mode != FB200_SCATTER_GATHER && !p.zfuse;
+    const fb200_status st = dispatch(ctx, p, op->kind, scatter_mode);
+    if (st == FB200_OK) FB200_TRY(clear_values_if_pending(ctx));  // (nothing was launched: no owned elements)
+    ctx->pending_zero = false;
+    return st;
 }
 
 fb200_status fb200_assemble_into_csr(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
@@ -1256,7 +1363,7 @@ fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, co
     if (st == FB200_OK) {
         std::vector<int32_t> list(count);
         for (uint64_t k = 0; k < count; ++k) list[k] = (int32_t)(first + k);
-        cudaMemcpy(d_list, list.data(), count * sizeof(int32_t), cudaMemcpyHostToDevice);
+        h2d_copy(ctx, d_list, list.data(), count * sizeof(int32_t));
         AssembleParams p;
         fill_params(ctx, p);
         p.elem_list = d_list;

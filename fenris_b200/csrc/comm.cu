@@ -104,13 +104,75 @@ __global__ void iface_add_kernel(const int32_t* __restrict__ nodes, const int64_
     }
 }
 
+// ---- fused exchange over peer memory: neighbour barrier.  Thread t signals peer t (writes the sequence number into MY slot of the peer's
+// signal words, system scope, after a system fence) and waits until the peer's number has arrived in ITS slot of mine.
+struct PeerSignals {
+    unsigned long long* remote[2];
+    int rank[2];
+    int n;
+};
+__global__ void peer_barrier_kernel(unsigned long long* mine, PeerSignals ps, int my_rank, unsigned long long seq, unsigned long long* errword) {
+    const int t = threadIdx.x;
+    if (t >= ps.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ps.remote[t] + my_rank), "l"(seq) : "memory");
+    const unsigned long long* slot = mine + ps.rank[t];
+    unsigned long long v;
+    unsigned int spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slot) : "memory");
+        if (v >= seq) break;
+        __nanosleep(100);
+        if (++spins > (1u << 26)) {  // several seconds: a neighbour is gone - report instead of hanging the stream
+            atomicMin(errword, ((unsigned long long)ps.rank[t] << 8) | (unsigned long long)FB200_ERR_NCCL);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace fb200
 
 using namespace fb200;
 
+void fb200::p2p_disable(fb200_ctx* ctx) {
+    if (!ctx) return;
+    auto& pp = ctx->p2p;
+    for (int k = 0; k < 2; ++k) {
+        if (pp.values[k]) cudaIpcCloseMemHandle(pp.values[k]);
+        if (pp.signal[k]) cudaIpcCloseMemHandle(pp.signal[k]);
+        pp.values[k] = nullptr;
+        pp.signal[k] = nullptr;
+        pp.peer_rank[k] = -1;
+    }
+    dev_free(pp.d_peer_row);
+    pp.enabled = false;
+    pp.pending = false;
+    pp.num_peers = 0;
+    // (d_signal stays allocated: a neighbour may still hold a mapping of it; freed with the context)
+}
+
+fb200_status fb200::p2p_neighbour_barrier(fb200_ctx* ctx) {
+    auto& pp = ctx->p2p;
+    if (!pp.enabled || pp.num_peers == 0) return FB200_OK;
+    PeerSignals ps;
+    ps.n = pp.num_peers;
+    for (int k = 0; k < 2; ++k) {
+        ps.remote[k] = pp.signal[k];
+        ps.rank[k] = pp.peer_rank[k];
+    }
+    ++pp.seq;
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pp.d_signal, ps, ctx->rank, pp.seq, ctx->d_errword);
+    return check_launch(ctx, "peer_barrier_kernel");
+}
+
 extern "C" {
 
 void fb200_comm_destroy_internal(fb200_ctx* ctx) {
+    if (ctx) {
+        p2p_disable(ctx);
+        dev_free(ctx->p2p.d_signal);
+    }
     if (ctx && ctx->nccl_comm && g_nccl.CommDestroy) {
         g_nccl.CommDestroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
@@ -171,8 +233,8 @@ fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t*
     FB200_TRY(dev_alloc(ctx, &ctx->d_iface_offsets, count));
     FB200_TRY(dev_alloc(ctx, &ctx->d_iface_packed, packed_len));
     if (count) {
-        FB200_CUDA(ctx, cudaMemcpy(ctx->d_iface_nodes, nodes.data(), count * sizeof(int32_t), cudaMemcpyHostToDevice));
-        FB200_CUDA(ctx, cudaMemcpy(ctx->d_iface_offsets, offs.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice));
+        FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_iface_nodes, nodes.data(), count * sizeof(int32_t)));
+        FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_iface_offsets, offs.data(), count * sizeof(int64_t)));
     }
     ctx->iface_count = count;
     ctx->iface_packed_len = packed_len;
@@ -191,6 +253,9 @@ fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const
     ctx->peer_ranks.clear();
     ctx->peer_seg_off.clear();
     ctx->peer_count = 0;
+    ctx->h_peer_nodes.clear();
+    ctx->h_peer_begin.clear();
+    p2p_disable(ctx);
     if (num_peers == 0) return FB200_OK;
     std::vector<int64_t> off(ctx->N + 1);
     FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -217,12 +282,14 @@ fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const
     FB200_TRY(dev_alloc(ctx, &ctx->d_peer_send, pos));
     FB200_TRY(dev_alloc(ctx, &ctx->d_peer_recv, pos));
     if (total_nodes) {
-        FB200_CUDA(ctx, cudaMemcpy(ctx->d_peer_nodes, h_nodes.data(), total_nodes * sizeof(int32_t), cudaMemcpyHostToDevice));
-        FB200_CUDA(ctx, cudaMemcpy(ctx->d_peer_offsets, h_offs.data(), total_nodes * sizeof(int64_t), cudaMemcpyHostToDevice));
+        FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_peer_nodes, h_nodes.data(), total_nodes * sizeof(int32_t)));
+        FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_peer_offsets, h_offs.data(), total_nodes * sizeof(int64_t)));
     }
     ctx->peer_ranks.assign(peer_ranks, peer_ranks + num_peers);
     ctx->peer_seg_off = seg;
     ctx->peer_count = total_nodes;
+    ctx->h_peer_nodes = h_nodes;
+    ctx->h_peer_begin.assign(peer_begin, peer_begin + num_peers + 1);
     return FB200_OK;
 }
 
@@ -257,10 +324,125 @@ static fb200_status interface_exchange_peers(fb200_ctx* ctx) {
     return FB200_OK;
 }
 
+fb200_status fb200_interface_enable_p2p(fb200_ctx* ctx) {
+    if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_enable_p2p needs a pattern");
+    if (!ctx->nccl_comm) return fail(ctx, FB200_ERR_STATE, "fb200_comm_init has not been called");
+    if (!g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) return fail(ctx, FB200_ERR_NCCL, "libnccl lacks ncclSend/ncclRecv");
+    FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    p2p_disable(ctx);
+    auto& pp = ctx->p2p;
+    const size_t np = ctx->peer_ranks.size();
+    // the fused flush carries ONE neighbour per interface node and at most two neighbours per rank (slab-like partitions); anything else
+    // keeps the packed ncclSend / ncclRecv exchange.  The answer must be the same on every rank of a neighbourhood, and it is: a node
+    // shared by three ranks is in two peer lists on each of them.
+    bool ok = np >= 1 && np <= 2 && ctx->N < (1ull << 31);
+    std::vector<uint32_t> owner(ctx->N, 0xffffffffu);
+    for (size_t pr = 0; pr < np && ok; ++pr)
+        for (uint64_t k = ctx->h_peer_begin[pr]; k < ctx->h_peer_begin[pr + 1]; ++k) {
+            uint32_t& o = owner[ctx->h_peer_nodes[k]];
+            if (o != 0xffffffffu) ok = false;
+            o = (uint32_t)pr;
+        }
+    // every rank must reach the exchanges below or none: agree on `ok` with the neighbours first (a refusal is sent as a zero-length layout)
+    const uint64_t total = ctx->peer_count;
+    std::vector<int64_t> off(ctx->N + 1);
+    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    // message to peer pr: [ok, ipc handle of values (64 B), ipc handle of the signal words (64 B)] as 17 int64, then (offset, count) per node
+    if (!pp.d_signal) {
+        FB200_TRY(dev_alloc(ctx, &pp.d_signal, (size_t)std::max(ctx->nranks, 1)));
+        FB200_CUDA(ctx, cudaMemsetAsync(pp.d_signal, 0, sizeof(unsigned long long) * (size_t)std::max(ctx->nranks, 1), ctx->stream));
+        FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    constexpr size_t HDR = 17;
+    std::vector<int64_t> send(np * HDR + 2 * total, 0), recv(np * HDR + 2 * total, 0);
+    cudaIpcMemHandle_t hv, hs;
+    FB200_CUDA(ctx, cudaIpcGetMemHandle(&hv, ctx->d_values));
+    FB200_CUDA(ctx, cudaIpcGetMemHandle(&hs, pp.d_signal));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    std::vector<size_t> seg(np + 1, 0);
+    for (size_t pr = 0; pr < np; ++pr) {
+        const size_t nn = (size_t)(ctx->h_peer_begin[pr + 1] - ctx->h_peer_begin[pr]);
+        int64_t* m = send.data() + seg[pr];
+        m[0] = ok ? 1 : 0;
+        std::memcpy(m + 1, &hv, 64);
+        std::memcpy(m + 9, &hs, 64);
+        for (size_t k = 0; k < nn; ++k) {
+            const int32_t node = ctx->h_peer_nodes[ctx->h_peer_begin[pr] + k];
+            m[HDR + 2 * k] = off[node];
+            m[HDR + 2 * k + 1] = off[node + 1] - off[node];
+        }
+        seg[pr + 1] = seg[pr] + HDR + 2 * nn;
+    }
+    int64_t *d_send = nullptr, *d_recv = nullptr;
+    FB200_TRY(dev_alloc(ctx, &d_send, send.size()));
+    fb200_status st = dev_alloc(ctx, &d_recv, recv.size());
+    if (st == FB200_OK && h2d_copy(ctx, d_send, send.data(), send.size() * sizeof(int64_t)) != cudaSuccess) st = fail(ctx, FB200_ERR_CUDA, "H2D p2p layout");
+    if (st == FB200_OK) {
+        int rc = g_nccl.GroupStart();
+        for (size_t pr = 0; pr < np && rc == 0; ++pr) {
+            rc = g_nccl.Send(d_send + seg[pr], seg[pr + 1] - seg[pr], /*ncclInt64*/ 4, ctx->peer_ranks[pr], ctx->nccl_comm, ctx->stream);
+            if (rc == 0) rc = g_nccl.Recv(d_recv + seg[pr], seg[pr + 1] - seg[pr], /*ncclInt64*/ 4, ctx->peer_ranks[pr], ctx->nccl_comm, ctx->stream);
+        }
+        const int rc_end = g_nccl.GroupEnd();
+        if (rc != 0 || rc_end != 0) st = nccl_fail(ctx, rc ? rc : rc_end, "p2p layout exchange");
+    }
+    if (st == FB200_OK && cudaMemcpyAsync(recv.data(), d_recv, recv.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        st = fail(ctx, FB200_ERR_CUDA, "D2H p2p layout");
+    if (st == FB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FB200_ERR_CUDA, "p2p layout exchange");
+    dev_free(d_send);
+    dev_free(d_recv);
+    FB200_TRY(st);
+    for (size_t pr = 0; pr < np; ++pr) ok = ok && recv[seg[pr]] == 1;
+    if (!ok) return fail(ctx, FB200_ERR_UNSUPPORTED, "fused p2p exchange needs one neighbour per interface node and at most two neighbours per rank");
+    std::vector<uint32_t> row(ctx->N, 0u);
+    for (size_t pr = 0; pr < np; ++pr) {
+        const size_t nn = (size_t)(ctx->h_peer_begin[pr + 1] - ctx->h_peer_begin[pr]);
+        const int64_t* m = recv.data() + seg[pr];
+        cudaIpcMemHandle_t rv, rs;
+        std::memcpy(&rv, m + 1, 64);
+        std::memcpy(&rs, m + 9, 64);
+        for (size_t k = 0; k < nn; ++k) {
+            const int32_t node = ctx->h_peer_nodes[ctx->h_peer_begin[pr] + k];
+            if (m[HDR + 2 * k + 1] != off[node + 1] - off[node] || m[HDR + 2 * k] < 0 || m[HDR + 2 * k] >= (int64_t)0x7fffffff) {
+                p2p_disable(ctx);
+                return fail(ctx, FB200_ERR_SHAPE, "interface rows have different layouts on the two ranks (ghost elements missing?)");
+            }
+            row[node] = ((uint32_t)m[HDR + 2 * k] + 1u) | ((uint32_t)pr << 31);
+        }
+        void *pv = nullptr, *ps = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&pv, rv, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ps, rs, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            if (pv) cudaIpcCloseMemHandle(pv);
+            p2p_disable(ctx);
+            cudaGetLastError();
+            return fail(ctx, FB200_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle failed (no peer access between the ranks?): ") + cudaGetErrorString(e));
+        }
+        pp.values[pr] = static_cast<double*>(pv);
+        pp.signal[pr] = static_cast<unsigned long long*>(ps);
+        pp.peer_rank[pr] = ctx->peer_ranks[pr];
+    }
+    FB200_TRY(dev_alloc(ctx, &pp.d_peer_row, (size_t)ctx->N));
+    if (ctx->N) FB200_CUDA(ctx, h2d_copy(ctx, pp.d_peer_row, row.data(), ctx->N * sizeof(uint32_t)));
+    pp.num_peers = (int)np;
+    pp.enabled = true;
+    pp.pending = false;
+    // nobody may start reducing into a neighbour before that neighbour has mapped everything: one barrier to finish the set-up
+    FB200_TRY(p2p_neighbour_barrier(ctx));
+    FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return read_errword(ctx);
+}
+
 fb200_status fb200_interface_allreduce(fb200_ctx* ctx) {
     if (!ctx || !ctx->has_pattern) return fail(ctx, FB200_ERR_STATE, "interface_allreduce needs a pattern");
     if (ctx->nranks > 1 && !ctx->nccl_comm) return fail(ctx, FB200_ERR_STATE, "fb200_comm_init has not been called");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->p2p.pending) {
+        // the last assembly already reduced this rank's interface sums into the neighbours' rows (hex8_tile_kernel.cuh, PEER); the rows
+        // are complete once every neighbour's kernel has finished: one neighbour barrier, no data moves here
+        ctx->p2p.pending = false;
+        return p2p_neighbour_barrier(ctx);
+    }
     if (!ctx->peer_ranks.empty()) return interface_exchange_peers(ctx);
     if (ctx->iface_packed_len == 0) return FB200_OK;
     const int ss = ctx->sdim * ctx->sdim;

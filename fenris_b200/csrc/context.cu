@@ -29,6 +29,7 @@ fb200_status check_launch(fb200_ctx* ctx, const char* name) {
 }
 
 void free_pattern(fb200_ctx* ctx) {
+    p2p_disable(ctx);  // the neighbours' row offsets and the exported values belong to this pattern
     free_ordered(ctx);
     dev_free(ctx->d_blk_off);
     dev_free(ctx->d_blk_cols);
@@ -106,7 +107,7 @@ static fb200_status upload_order(fb200_ctx* ctx) {
         }
     }
     FB200_TRY(dev_alloc(ctx, &ctx->d_order, owned.size()));
-    if (!owned.empty()) FB200_CUDA(ctx, cudaMemcpy(ctx->d_order, owned.data(), owned.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!owned.empty()) FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_order, owned.data(), owned.size() * sizeof(int32_t)));
     ctx->order_count = owned.size();
     return FB200_OK;
 }
@@ -220,10 +221,11 @@ fb200_status fb200_create(int32_t device, fb200_ctx** out) {
     cudaEventCreate(&ctx->ev1);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaMalloc((void**)&ctx->d_errword, sizeof(unsigned long long));
-    cudaMalloc((void**)&ctx->d_ticket, sizeof(unsigned long long));
+    cudaMalloc((void**)&ctx->d_ticket, 16 * sizeof(unsigned long long));  // [0] work counter; [1..15] debug counters (FB200_DEBUG & 64)
+    cudaMemset(ctx->d_ticket, 0, 16 * sizeof(unsigned long long));
     cudaMallocHost((void**)&ctx->h_errword, sizeof(unsigned long long));
     const unsigned long long init = kNoError;
-    cudaMemcpy(ctx->d_errword, &init, sizeof(init), cudaMemcpyHostToDevice);
+    h2d_copy(ctx, ctx->d_errword, &init, sizeof(init));
     if (cudaGetLastError() != cudaSuccess) {
         fb200_destroy(ctx);
         return FB200_ERR_CUDA;
@@ -313,9 +315,9 @@ fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value) {
         ctx->tune_hex8_tile = value;
         return FB200_OK;
     }
-    if (name && std::strcmp(name, "hex8_flush_rot") == 0) {
-        if (value != 0 && value != 1) return fail(ctx, FB200_ERR_SHAPE, "hex8_flush_rot must be 0 or 1");
-        ctx->tune_flush_rot = value;
+    if (name && std::strcmp(name, "hex8_owner_stores") == 0) {
+        if (value != 0 && value != 1) return fail(ctx, FB200_ERR_SHAPE, "hex8_owner_stores must be 0 or 1");
+        ctx->tune_owner = value;
         return FB200_OK;
     }
     return fail(ctx, FB200_ERR_UNSUPPORTED, "unknown tuning knob");
@@ -382,11 +384,10 @@ fb200_status fb200_connectivity_upload(fb200_ctx* ctx, uint64_t num_nodes, uint6
     if (!ctx) return FB200_ERR_STATE;
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!element_offsets) return fail(ctx, FB200_ERR_SHAPE, "null offsets");
+    if (!offsets_well_formed(element_offsets, num_elements)) return fail(ctx, FB200_ERR_SHAPE, "offsets must start at 0 and be non-decreasing");
     const uint64_t total = element_offsets[num_elements];
     if (num_nodes >= (1ull << 31) || num_elements >= (1ull << 31) || total >= (1ull << 31))
         return fail(ctx, FB200_ERR_UNSUPPORTED, "connectivity too large for 32-bit device indices");
-    for (uint64_t e = 0; e < num_elements; ++e)
-        if (element_offsets[e + 1] < element_offsets[e]) return fail(ctx, FB200_ERR_SHAPE, "offsets must be non-decreasing");
     free_space(ctx);
     ctx->elem_type = 0;
     ctx->ei = {0, 0, 0};

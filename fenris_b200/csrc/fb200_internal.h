@@ -60,29 +60,40 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
-constexpr int kTileKBitsRot = 11;  // ... when the two top bits carry the row rotation of the entry (TileShape::flush_rot)
-constexpr int kTileHdrWords = 8;   // first schedule position, rounds, n_nodes, n_slots(P), node_begin, flush_begin, n_flush, n_elems
+constexpr uint32_t kTileZeroPos = 0x7ffu;  // accumulator position of a flush word that writes 0.0 (owner rows, see below)
+// header of a tile: 0 first schedule position, 1 rounds, 2 n_nodes, 3 n_slots (P), 4 node_begin, 5 flush_begin, 6 n_flush, 7 n_elems,
+// 8 n_store (leading flush entries that are plain stores when the call overwrites), 9 wait_begin, 10 n_wait, 11 flags, 12-15 reserved
+constexpr int kTileHdrWords = 16;
 struct TileShape {
     int tile_bits;    // low Morton bits dropped to name a tile (5: 4 x 4 x 2 elements, 6: 4 x 4 x 4)
     int max_elems;    // elements per tile
     int warps;        // elements per round = warps per compute group
     int max_nodes;    // distinct nodes per tile (<= 128)
     int max_slots;    // accumulator positions per tile (upper-triangle node blocks + padding)
-    int flush_rot = 0;  // 1: flush words carry a per-entry rotation (bits 30-31) of the block row a lane reads first, chosen to spread the
-                        // shared-memory banks of a flush half-warp (opt-in: fb200_set_tuning("hex8_flush_rot"); k narrows to 11 bits)
+    int owner_stores = 1;  // 1: rows shared by several tiles are STORED (all of their entries, zeros included) by the lowest-numbered tile
+                           // that touches the node and reduced into by the others once that tile has published its stores - an
+                           // overwriting assembly then needs no zero-fill of the values.  0: only tile-complete rows are stored, every
+                           // other row is reduced into (the caller zero-fills all values first).
 };
 struct HostTiles {
     std::vector<uint32_t> hdr;        // num_tiles * kTileHdrWords
     std::vector<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
-    std::vector<uint32_t> flush;      // per (row node u, coupled node v) in CSR order: position | transposed << 11 | u << 12 | k << 19
-                                      // (| rotation << 30 with TileShape::flush_rot)
+    std::vector<uint32_t> flush;      // per tile: first the STORE segment, then the REDUCE segment, each per (row node u, coupled node v) in CSR
+                                      // order: position | transposed << 11 | u << 12 | k << 19; position kTileZeroPos = the entry is 0.0
+    std::vector<uint32_t> wait;       // per tile: the (lower-numbered) tiles whose stores its reductions must wait for
+    std::vector<int32_t> zero_nodes;  // owner_stores: nodes whose rows no tile stores (touched by ghost elements, or by no owned element at
+                                      // all): the only rows an overwriting call has to clear beforehand
     std::vector<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
     std::vector<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
     std::vector<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
+    bool owner_stores = false;        // the lists were built with TileShape::owner_stores
+    uint64_t zero_entries = 0;        // flush words with position kTileZeroPos
     double bank_conflict_share = 0;   // diagnostic: share of accumulate accesses that collide in a shared-memory bank
 };
+// blk_off (node-block row offsets, N + 1) is needed for owner_stores only (NULL: built as with owner_stores = 0)
 void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
-                      uint64_t num_elements, uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out);
+                      uint64_t num_elements, uint64_t num_owned, uint64_t num_nodes, const uint16_t* blockmap, const int64_t* blk_off,
+                      HostTiles& out);
 
 struct TileLists {
     bool valid = false;
@@ -90,11 +101,16 @@ struct TileLists {
     uint64_t count = 0;
     const int32_t* ids = nullptr;
     int tile_bits = 0;
-    int flush_rot = 0;
+    int owner_stores = 0;   // what was asked for ...
+    bool owner = false;     // ... and whether the lists carry it (HostTiles::owner_stores)
     uint32_t num_tiles = 0;
     uint32_t* d_hdr = nullptr;
     int32_t* d_nodes = nullptr;
     uint32_t* d_flush = nullptr;
+    uint32_t* d_wait = nullptr;
+    uint32_t* d_flag = nullptr;        // per tile: epoch of the launch whose stores of this tile are published
+    int32_t* d_zero_nodes = nullptr;   // rows to clear before an overwriting launch (owner lists)
+    uint64_t zero_node_count = 0;
     uint8_t* d_lnodes = nullptr;
     uint16_t* d_emap = nullptr;
     int32_t* d_elem = nullptr;
@@ -150,8 +166,10 @@ struct fb200_ctx {
     fb200::ChunkLists chunks;
     fb200::TileLists tiles;
     int tune_hex8_tile = -1;  // fb200_set_tuning("hex8_tile"); -1 = FB200_HEX8_TILE from the environment, else 64
-    int tune_flush_rot = -1;  // fb200_set_tuning("hex8_flush_rot"): rotated flush reads (see TileShape::flush_rot); -1 = FB200_HEX8_FLUSH_ROT
-                              // from the environment, else off
+    int tune_owner = -1;      // fb200_set_tuning("hex8_owner_stores"): first-writer stores instead of zero-fill + reductions (TileShape::owner_stores);
+                              // -1 = FB200_HEX8_OWNER from the environment, else on
+    uint32_t tile_epoch = 0;  // launch counter of the owner-store flags (TileLists::d_flag)
+    bool pending_zero = false;  // an overwriting assembly was requested and no kernel has cleared / overwritten the values yet
     // fused zero-fill lists of the Hex8 atomic kernel (see assemble.cu::ensure_zero_lists)
     int64_t* d_zero_off = nullptr;
     int32_t* d_zero_nodes = nullptr;
@@ -218,6 +236,22 @@ struct fb200_ctx {
     int64_t* d_peer_offsets = nullptr;
     double* d_peer_send = nullptr;
     double* d_peer_recv = nullptr;
+    std::vector<int32_t> h_peer_nodes;    // the nodes of all segments (host copy, for fb200_interface_enable_p2p)
+    std::vector<uint64_t> h_peer_begin;   // num_peers + 1, in nodes
+
+    // fused exchange over peer memory (fb200_interface_enable_p2p, comm.cu): the tile kernel's flush reduces interface rows straight
+    // into the neighbouring ranks' values through pointers mapped with CUDA IPC; neighbours synchronise through signal words
+    struct P2P {
+        bool enabled = false;
+        bool pending = false;             // a fused assembly was launched and its closing neighbour barrier has not run yet
+        int num_peers = 0;
+        int32_t peer_rank[2] = {-1, -1};
+        double* values[2] = {nullptr, nullptr};                  // peers' d_values (IPC mappings)
+        unsigned long long* signal[2] = {nullptr, nullptr};      // peers' signal words (IPC mappings), one slot per rank
+        unsigned long long* d_signal = nullptr;                  // my signal words [nranks]
+        uint32_t* d_peer_row = nullptr;                          // [N]: 0, or (block-row offset on the peer + 1) | peer slot << 31
+        unsigned long long seq = 0;                              // barrier sequence number
+    } p2p;
 };
 
 namespace fb200 {
@@ -251,6 +285,14 @@ void dev_free(T*& p) {
     p = nullptr;
 }
 
+// H2D copy of a (pageable) host array that kernels on ctx->stream read next.  ctx->stream is cudaStreamNonBlocking, so a blocking
+// cudaMemcpy on the legacy stream is NOT ordered before those kernels (it may return while the DMA from the staging buffer is still
+// in flight): copy on the context's own stream and wait for it.
+inline cudaError_t h2d_copy(fb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+}
+
 // after a kernel launch
 fb200_status check_launch(fb200_ctx* ctx, const char* name);
 
@@ -263,6 +305,10 @@ fb200_status exclusive_scan_i64(fb200_ctx* ctx, int64_t* d_data, uint64_t count)
 // context.cu: locality-preserving (Morton) processing order of the elements and the codes it was sorted by
 void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const uint64_t* conn, std::vector<int32_t>& order,
                   std::vector<uint64_t>& codes);
+
+// comm.cu: neighbour barrier of the fused exchange (no-op unless p2p is enabled); closes a pending fused assembly
+fb200_status p2p_neighbour_barrier(fb200_ctx* ctx);
+void p2p_disable(fb200_ctx* ctx);
 
 // assemble.cu
 void free_ordered(fb200_ctx* ctx);
@@ -278,5 +324,13 @@ fb200_status assemble_state_dependent_list(fb200_ctx* ctx, const fb200_operator*
                                            const int32_t* d_list, uint64_t count, int plain);
 
 inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
+
+// offsets[0 .. count] of a caller's CSR-like structure: starts at 0, never decreases (checked on the host before any kernel indexes with it)
+inline bool offsets_well_formed(const uint64_t* offsets, uint64_t count) {
+    if (offsets[0] != 0) return false;
+    for (uint64_t i = 0; i < count; ++i)
+        if (offsets[i + 1] < offsets[i]) return false;
+    return true;
+}
 
 }  // namespace fb200

@@ -24,7 +24,16 @@
 //                    neighbouring node blocks (72 B each); blocks below the diagonal are read transposed from the (v, u)
 //                    accumulator.  Rows of nodes whose elements all lie in the tile are complete: they are written with plain
 //                    stores (no reduction, no DRAM read of the line) when the call overwrites.
-// On the structured C3 mesh this is 1.27 CSR updates per value instead of 2.4, 42 % of them plain stores.  Sums differ from the
+//            ownership  an overwriting call does not zero-fill the values first (the reference's assemble() starts from a zeroed
+//                    CsrMatrix, global.rs:124-131 - here that would be a 3.9 GB pass of its own): the flush list of a tile has a
+//                    STORE segment (rows complete in the tile, and all entries - zeros included - of shared rows this tile OWNS,
+//                    being the lowest-numbered tile that touches the node) and a REDUCE segment.  After its stores a tile publishes
+//                    flag[tile] = launch epoch (barrier, fence, release store); before its reductions it waits for the flags of the
+//                    owners of the rows it adds to (tiles.cpp `wait`).  Tickets are handed out in tile order, so every tile waited
+//                    for is already running: no deadlock.
+//            peers   (PEER, multi-GPU) rows of partition-interface nodes are also reduced straight into the neighbouring rank's copy
+//                    of the row through a peer-mapped pointer (NVLink): the interface exchange is part of the flush (comm.cu).
+// On the structured C3 mesh this is 1.27 CSR updates per value instead of 2.4, 65 % of them plain stores.  Sums differ from the
 // per-element kernels by fp reassociation only; (u, v) and (v, u) receive identical per-tile partial sums.
 //
 // Reference gradients: for the trilinear hexahedron (hexahedron.rs:50-83) d phi_a / d xi = sx_a (1 + sy_a eta)(1 + sz_a zeta) / 8
@@ -57,6 +66,10 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// reduction into a peer GPU's memory (NVLink): system scope
+__device__ __forceinline__ void red_add_f64_sys(double* addr, double v) {
+    asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 constexpr int kTileGroupWarps = 8;   // warps per compute group = elements per round (tiles.cpp: TileShape::warps)
@@ -72,7 +85,7 @@ struct Hex8TileSmem {
     static constexpr int WARP_DOUBLES = 24 + 8 * GS;
     static constexpr int ACC = (MAXP * BS + 1) & ~1;    // one accumulator buffer
     static constexpr int BIG_BYTES = MAXN * 3 * 8 + MAXN * 2 * 8;  // X[MAXN][3] doubles, off[MAXN][2] int64 (ring of 3 tiles)
-    static constexpr int SMALL_BYTES = 32 + MAXN * 4;              // header 8 x uint32, ids[MAXN] int32 (ring of 8 tiles)
+    static constexpr int SMALL_BYTES = kTileHdrWords * 4 + MAXN * 4;  // header, ids[MAXN] int32 (ring of 8 tiles)
     static constexpr int FROW_BYTES = MAXN * 2 * 8;                // flush row table of one tile
     static constexpr size_t bytes =
         sizeof(double) * (size_t)(2 * ACC + WARPS * WARP_DOUBLES) + 3 * (size_t)BIG_BYTES + 8 * (size_t)SMALL_BYTES + 2 * (size_t)FROW_BYTES + 32;
@@ -81,8 +94,8 @@ struct Hex8TileSmem {
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// ROT: the flush words carry a per-entry rotation of the block row a lane reads first (TileShape::flush_rot, tiles.cpp) - opt-in
-template <int OP, int MAXN, int MAXP, bool ROT = false>
+// PEER: rows of partition-interface nodes are also reduced into the neighbouring ranks' values (p.peer_row / p.peer_values)
+template <int OP, int MAXN, int MAXP, bool PEER = false>
 __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32, 1) assemble_hex8_tile_kernel(const AssembleParams p) {
     using L = Hex8TileSmem<OP, MAXN, MAXP>;
     constexpr int N = 8, D = 3, S = L::S, BS = L::BS, GS = L::GS, WARPS = L::WARPS, GW = kTileGroupWarps;
@@ -100,12 +113,12 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     auto big_off = [&](int b) { return reinterpret_cast<long long*>(bufbase + b * L::BIG_BYTES + MAXN * 24); };
     unsigned char* smallbase = bufbase + 3 * L::BIG_BYTES;
     auto small_hdr = [&](int sl) { return reinterpret_cast<uint32_t*>(smallbase + sl * L::SMALL_BYTES); };
-    auto small_ids = [&](int sl) { return reinterpret_cast<int*>(smallbase + sl * L::SMALL_BYTES + 32); };
+    auto small_ids = [&](int sl) { return reinterpret_cast<int*>(smallbase + sl * L::SMALL_BYTES + kTileHdrWords * 4); };
     unsigned char* frowbase = smallbase + 8 * L::SMALL_BYTES;
     auto buf_frow = [&](int b) { return reinterpret_cast<long long*>(frowbase + b * L::FROW_BYTES); };
     uint32_t* s_tick = reinterpret_cast<uint32_t*>(frowbase + 2 * L::FROW_BYTES);  // [8]: tile number held by each ring slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int dbg = p.debug;  // measurement knobs (results are wrong when set): 1 skip compute, 2 skip the global writes, 4 skip accumulate
+    const int dbg = p.debug;  // measurement knobs (results are wrong when set): 1 skip compute, 2 skip the global writes, 4 skip accumulate, 8 / 16 / 32 see the flush
     const bool overwrite = p.accumulate == 0;
 
     for (int i = tid; i < 2 * L::ACC; i += TC + TH) smem[i] = 0.0;
@@ -115,11 +128,20 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTileHelperRegs));
         const int ht = tid - TC;
         const uint64_t pol_keep = l2_policy_evict_last();
+        // flush lane mapping: a warp handles 32 list entries = SUB x 32 items per step; item 32 m + lane = (entry fe[m], column fj[m])
+        constexpr int SUB = S == 1 ? 1 : 3;
+        uint32_t fe[SUB];
+        int fj[SUB];
+#pragma unroll
+        for (int m = 0; m < SUB; ++m) {
+            fe[m] = S == 1 ? (uint32_t)lane : (uint32_t)(32 * m + lane) / 3u;
+            fj[m] = S == 1 ? 0 : (32 * m + lane) % 3;
+        }
         // the table pipeline: stage 0 header, stage 1 node ids, stage 2 coordinates + block-row offsets.  A stage reads what the
         // previous one left in shared memory; consecutive stages of a tile run in consecutive iterations (tables_done() between).
         auto stage0 = [&](int sl) {
             const uint32_t tn = s_tick[sl];
-            if (tn < p.num_tiles && ht < 2) cp_async_16(small_hdr(sl) + 4 * ht, p.tile_hdr + (size_t)tn * 8 + 4 * ht);
+            if (tn < p.num_tiles && ht < kTileHdrWords / 4) cp_async_16(small_hdr(sl) + 4 * ht, p.tile_hdr + (size_t)tn * kTileHdrWords + 4 * ht);
         };
         auto stage1 = [&](int sl) {
             if (s_tick[sl] < p.num_tiles) {
@@ -142,10 +164,20 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             named_barrier(BAR_HELPER, TH);
         };
         unsigned int tick_next = 0;
+        // tiles are handed out by an atomic ticket (dynamic) or round-robin over the CTAs (p.tile_static: tile = CTA + k * CTAs)
+        unsigned int static_next = blockIdx.x;
+        auto next_ticket = [&]() -> unsigned int {
+            if (p.tile_static) {
+                const unsigned int t = static_next;
+                static_next += gridDim.x;
+                return t;
+            }
+            return atomicAdd(p.ticket32, 1u);
+        };
         if (ht == 0) {
 #pragma unroll
-            for (int k = 0; k < 5; ++k) s_tick[k] = atomicAdd(p.ticket32, 1u);
-            tick_next = atomicAdd(p.ticket32, 1u);
+            for (int k = 0; k < 5; ++k) s_tick[k] = next_ticket();
+            tick_next = next_ticket();
         }
         named_barrier(BAR_HELPER, TH);
 #pragma unroll
@@ -160,8 +192,10 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         __syncthreads();  // (A) prologue done: tables of tiles 0 and 1 are there, both accumulator buffers are clear
         if (s_tick[0] < p.num_tiles) named_barrier_arrive(BAR_READY + 0, TC + TH);
 
-        uint32_t pf_begin = 0, pf_items = 0;  // previous tile: first list word, S * entries
-        int pf_P = 0;                         // ... accumulator positions in use
+        // owner stores (see the header comment): flags are compared with this launch's epoch; 0 = the lists carry no ownership or the
+        // call accumulates (then every entry is a reduction and nothing is published or waited for)
+        const uint32_t epoch = overwrite ? p.tile_epoch : 0u;
+        int pf_P = 0;  // previous tile: accumulator positions in use
         // iteration `it`: tables of tiles it + 2 .. it + 4, flush of tile it - 1 (after the compute warps have finished it)
         for (uint32_t it = 0;; ++it) {
             const int sl = (int)(it & 7u), b = (int)(it & 1u), nb = b ^ 1;
@@ -174,19 +208,21 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             const bool valid = s_tick[sl] < p.num_tiles;
             const uint32_t* hdr = small_hdr(sl);
             const int nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
-            const uint32_t flush_begin = valid ? hdr[5] : 0u, nflush = valid ? hdr[6] : 0u;
             if (valid) {
-                // row table of this tile's flush (used in the next iteration): first value of node u's rows, row length | complete << 31
+                // row table of this tile's flush (used in the next iteration): address of the first value of node u's rows; row length, and for a
+                // partition-interface node (PEER) its block-row offset on the neighbouring rank + 1 | neighbour slot << 31 in the high word
                 if (ht < nn) {
                     const long long* off = big_off((int)(it % 3u));
                     const long long o0 = off[2 * ht], o1 = off[2 * ht + 1];
                     long long* fr = buf_frow(b);
-                    fr[2 * ht] = (long long)BS * o0;
-                    fr[2 * ht + 1] = (long long)(((int)(o1 - o0) * S) | ((small_ids(sl)[ht] < 0 && overwrite) ? (int)0x80000000 : 0));
+                    fr[2 * ht] = (long long)(p.values + (long long)BS * o0);
+                    unsigned long long w1 = (unsigned long long)(unsigned int)((int)(o1 - o0) * S);
+                    if constexpr (PEER) w1 |= (unsigned long long)p.peer_row[small_ids(sl)[ht] & 0x7fffffff] << 32;
+                    fr[2 * ht + 1] = (long long)w1;
                 }
                 // pull this tile's flush list into L2 (it is read in the next iteration)
-                const char* f0 = reinterpret_cast<const char*>(p.tile_flush + flush_begin);
-                const uint32_t bytes = nflush * 4u;
+                const char* f0 = reinterpret_cast<const char*>(p.tile_flush + hdr[5]);
+                const uint32_t bytes = hdr[6] * 4u;
                 for (uint32_t o = (uint32_t)ht * 128u; o < bytes; o += (uint32_t)TH * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(f0 + o));
             }
             // ---- one stage for each of three coming tiles; the ring slot of tile it - 3 receives the ticket of tile it + 5
@@ -195,71 +231,107 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             stage0((int)((it + 4) & 7u));
             if (ht == 0) {
                 s_tick[(it + 5) & 7u] = tick_next;
-                tick_next = atomicAdd(p.ticket32, 1u);
+                tick_next = next_ticket();
             }
-            // ---- flush of the previous tile: every node block goes to the CSR once.  A warp whose 32 items all belong to complete
-            // rows uses plain stores; a reduction onto the zero-filled row is equally correct, so mixed warps simply reduce.
-            {
-                const uint32_t* fl = p.tile_flush + pf_begin;
+            // ---- flush of the previous tile (its header is still in ring slot it - 1): every node block goes to the CSR once
+            if (it > 0) {
+                const uint32_t* ph = small_hdr((int)((it - 1) & 7u));
+                const uint32_t* fl = p.tile_flush + ph[5];
+                const uint32_t items = ph[6], store_items = ph[8];  // (entries)
                 const double* pacc = smem + nb * L::ACC;
-                const long long* prow = buf_frow(nb);
-                constexpr int FB = 8;
-                const uint32_t wbase_t = (uint32_t)(ht - lane);
-                auto load_words = [&](uint32_t tb, uint32_t (&w)[FB]) {
+                const longlong2* prow = reinterpret_cast<const longlong2*>(buf_frow(nb));
+                // entries [e0, e1) of the list.  A warp takes blocks of 32 entries = SUB * 32 items; in sub-iteration m lane l handles
+                // item 32 m + l of the block = entry fe[m], column fj[m] (per-lane constants: no division in the loop), so that an
+                // instruction covers 32 consecutive doubles of a run of neighbouring node blocks.  STORE: plain stores; else reductions
+                auto flush_range = [&](const uint32_t e0, const uint32_t e1, auto store_tag) {
+                    constexpr bool STORE = decltype(store_tag)::value;
+                    constexpr uint32_t STEP = 32u * kTileHelperWarps;
+                    uint32_t eb = e0 + 32u * (uint32_t)(ht >> 5);
+                    uint32_t w[SUB], wn[SUB];
 #pragma unroll
-                    for (int q = 0; q < FB; ++q) {
-                        const uint32_t t = tb + q * TH + lane;
-                        w[q] = t < pf_items ? fl[S == 1 ? t : t / 3u] : 0u;
+                    for (int m = 0; m < SUB; ++m) w[m] = eb + fe[m] < e1 ? __ldg(fl + eb + fe[m]) : 0xffffffffu;
+                    while (eb < e1) {  // warp-uniform
+                        const uint32_t en = eb + STEP;
+#pragma unroll
+                        for (int m = 0; m < SUB; ++m) wn[m] = en + fe[m] < e1 ? __ldg(fl + en + fe[m]) : 0xffffffffu;  // (next block, in flight)
+#pragma unroll
+                        for (int m = 0; m < SUB; ++m) {
+                            const uint32_t a = w[m];
+                            if (a == 0xffffffffu) continue;  // past the end of the range (no list word is all ones: u <= 124)
+                            const int j = fj[m];
+                            const longlong2 rt = prow[(a >> 12) & 0x7fu];
+                            const int rl = (int)(unsigned int)(unsigned long long)rt.y;
+                            const bool tr = (a & 0x800u) != 0u;
+                            const uint32_t apos = a & 0x7ffu;
+                            const bool zero = apos == kTileZeroPos;  // an owner writes 0.0 where it has no contribution
+                            const double* src = pacc + (int)(zero ? 0u : apos) * BS + (tr ? j * S : j);
+                            const int sstride = tr ? 1 : S;
+                            const int col = S * (int)(a >> 19) + j;
+                            double* dst = reinterpret_cast<double*>(rt.x) + col;
+                            double v[S];
+#pragma unroll
+                            for (int i = 0; i < S; ++i) v[i] = zero ? 0.0 : src[i * sstride];
+                            if (dbg & 2) continue;
+                            if constexpr (STORE) {
+#pragma unroll
+                                for (int i = 0; i < S; ++i) dst[(long long)i * rl] = v[i];
+                            } else {
+                                if (zero) continue;  // (a STORE segment flushed by an accumulating call)
+#pragma unroll
+                                for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
+                                if constexpr (PEER) {
+                                    const uint32_t pw = (uint32_t)((unsigned long long)rt.y >> 32);
+                                    if (pw) {
+                                        double* pd = p.peer_values[pw >> 31] + ((long long)BS * (long long)((pw & 0x7fffffffu) - 1u) + (long long)col);
+#pragma unroll
+                                        for (int i = 0; i < S; ++i) red_add_f64_sys(pd + (long long)i * rl, v[i]);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int m = 0; m < SUB; ++m) w[m] = wn[m];
+                        eb = en;
                     }
                 };
-                auto send_words = [&](uint32_t tb, const uint32_t (&w)[FB]) {
-#pragma unroll
-                    for (int q = 0; q < FB; ++q) {
-                        if (tb + q * TH >= pf_items) break;  // warp-uniform
-                        const uint32_t t = tb + q * TH + lane;
-                        const bool ok = t < pf_items;
-                        const uint32_t a = w[q];
-                        const int u = (int)((a >> 12) & 0x7fu);
-                        const int j = S == 1 ? 0 : (int)(t % 3u);
-                        const long long base = prow[2 * u];
-                        const int rlf = (int)prow[2 * u + 1];
-                        const int rl = rlf & 0x7fffffff;
-                        const bool tr = (a >> 11) & 1u;
-                        const double* src = pacc + (int)(a & 0x7ffu) * BS + (tr ? j * S : j);
-                        const int sstride = tr ? 1 : S;
-                        const int kcol = ROT ? (int)((a >> 19) & ((1u << kTileKBitsRot) - 1u)) : (int)(a >> 19);
-                        const int rot = (ROT && S == 3) ? (int)(a >> 30) : 0;
-                        // row read by load i (and written by store i): i, or rotated per entry so that a half-warp spreads over the banks
-                        auto row_of = [&](int i) { return ROT ? (i + rot >= S ? i + rot - S : i + rot) : i; };
-                        double* dst = p.values + (base + (long long)(S * kcol + j));
-                        double v[S];
-#pragma unroll
-                        for (int i = 0; i < S; ++i) v[i] = src[row_of(i) * sstride];
-                        if (dbg & 2) continue;
-                        if (__all_sync(FULL, rlf < 0 || !ok)) {
-                            if (ok) {
-#pragma unroll
-                                for (int i = 0; i < S; ++i) dst[(long long)row_of(i) * rl] = v[i];
+                if (!overwrite) {
+                    flush_range(0u, items, std::false_type{});
+                } else {
+                    flush_range(0u, store_items, std::true_type{});
+                    if (epoch) {
+                        // publish this tile's stores, then wait for the owners of the rows the REDUCE segment adds to
+                        // (measurement knobs, results wrong: 8 no publish / no wait, 16 no wait, 32 publish without the barrier)
+                        if (!(dbg & 32)) named_barrier(BAR_HELPER, TH);
+                        if (ht == 0 && !(dbg & 8)) st_release_u32(p.tile_flag + s_tick[(it - 1) & 7u], epoch);
+                        const uint32_t nwait = (dbg & 24) ? 0u : ph[10];
+                        if (nwait) {
+                            const uint32_t* wl = p.tile_wait + ph[9];
+                            for (uint32_t w = (uint32_t)ht; w < nwait; w += (uint32_t)TH) {
+                                const uint32_t* fp = p.tile_flag + wl[w];
+                                unsigned int spins = 0;
+                                while (ld_acquire_u32(fp) != epoch) {
+                                    __nanosleep(64);
+                                    if (++spins > (1u << 24)) {  // > 1 s: never on a healthy launch; report instead of hanging
+                                        flag_error(p.errword, (uint64_t)s_tick[(it - 1) & 7u], FB200_ERR_CUDA);
+                                        break;
+                                    }
+                                }
+                                if ((dbg & 64) && spins) {  // diagnostics: blocked waits, their spins, how far back the owner tile is
+                                    unsigned long long* dc = reinterpret_cast<unsigned long long*>(p.ticket32) + 2;
+                                    const unsigned long long dist = s_tick[(it - 1) & 7u] - wl[w];
+                                    atomicAdd(dc + 0, 1ull);
+                                    atomicAdd(dc + 1, (unsigned long long)spins);
+                                    atomicMax(dc + 2, (unsigned long long)spins);
+                                    atomicAdd(dc + 3, dist);
+                                    atomicMax(dc + 4, dist);
+                                    atomicAdd(dc + (dist < 8 ? 5 : dist < 64 ? 6 : dist < 512 ? 7 : 8), 1ull);
+                                    atomicAdd(dc + (dist < 8 ? 9 : dist < 64 ? 10 : dist < 512 ? 11 : 12), (unsigned long long)spins);
+                                }
                             }
-                        } else if (ok) {
-#pragma unroll
-                            for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)row_of(i) * rl, v[i], pol_keep);
+                            named_barrier(BAR_HELPER, TH);
                         }
                     }
-                };
-                // two batches in flight: the list words of batch k + 1 are loaded before batch k is sent
-                uint32_t wa[FB], wb[FB];
-                uint32_t tb = wbase_t;
-                if (tb < pf_items) load_words(tb, wa);
-                while (tb < pf_items) {  // warp-uniform
-                    const uint32_t tb1 = tb + FB * TH;
-                    if (tb1 < pf_items) load_words(tb1, wb);
-                    send_words(tb, wa);
-                    if (tb1 >= pf_items) break;
-                    const uint32_t tb2 = tb1 + FB * TH;
-                    if (tb2 < pf_items) load_words(tb2, wa);
-                    send_words(tb1, wb);
-                    tb = tb2;
+                    flush_range(store_items, items, std::false_type{});
                 }
             }
             tables_done();  // the stages have landed, and every helper has read its accumulators
@@ -267,8 +339,6 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                 double* old = smem + nb * L::ACC;
                 for (int i = ht; i < pf_P * BS; i += TH) old[i] = 0.0;
             }
-            pf_begin = flush_begin;
-            pf_items = nflush * S;
             pf_P = P;
             // accumulator buffer nb is clear (again) and the tables of tile it + 2 are there: release tile it + 1
             if (s_tick[(it + 1) & 7u] < p.num_tiles) {

@@ -446,7 +446,7 @@ static fb200_status upload_colors(fb200_ctx* ctx) {
     FB200_TRY(dev_alloc(ctx, &ctx->d_color_elems, total));
     std::vector<int32_t> tmp(total);
     for (uint64_t i = 0; i < total; ++i) tmp[i] = (int32_t)ctx->h_color_elems[i];
-    if (total) FB200_CUDA(ctx, cudaMemcpy(ctx->d_color_elems, tmp.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (total) FB200_CUDA(ctx, h2d_copy(ctx, ctx->d_color_elems, tmp.data(), total * sizeof(int32_t)));
     return FB200_OK;
 }
 
@@ -578,6 +578,8 @@ fb200_status fb200_pattern_adopt(fb200_ctx* ctx, int32_t sdim, uint64_t num_rows
     if (sdim < 1 || sdim > 3) return fail(ctx, FB200_ERR_SHAPE, "solution_dim must be 1, 2 or 3");
     if (num_rows != (uint64_t)sdim * ctx->N) return fail(ctx, FB200_ERR_SHAPE, "num_rows != solution_dim * num_nodes");
     if (!row_offsets) return fail(ctx, FB200_ERR_SHAPE, "null row_offsets");
+    // a malformed offset array would send the adopt kernels out of bounds: check it on the host first
+    if (!offsets_well_formed(row_offsets, num_rows)) return fail(ctx, FB200_ERR_SHAPE, "row_offsets must start at 0 and be non-decreasing");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
     free_pattern(ctx);
     const uint64_t N = ctx->N, nnz = row_offsets[num_rows];
@@ -686,9 +688,9 @@ fb200_status fb200_colors_adopt(fb200_ctx* ctx, uint64_t num_colors, const uint6
     if (!ctx || !ctx->has_connectivity) return fail(ctx, FB200_ERR_STATE, "colors_adopt needs a space or connectivity");
     if (!color_offsets) return fail(ctx, FB200_ERR_SHAPE, "null colour offsets");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!offsets_well_formed(color_offsets, num_colors)) return fail(ctx, FB200_ERR_SHAPE, "colour offsets must start at 0 and be non-decreasing");
     const uint64_t total = color_offsets[num_colors];
-    for (uint64_t c = 0; c < num_colors; ++c)
-        if (color_offsets[c + 1] < color_offsets[c]) return fail(ctx, FB200_ERR_SHAPE, "colour offsets must be non-decreasing");
+    if (total && !element_ids) return fail(ctx, FB200_ERR_SHAPE, "null colour element list");
     for (uint64_t k = 0; k < total; ++k)
         if (element_ids[k] >= ctx->E_owned) return fail(ctx, FB200_ERR_INDEX_OOB, "colour lists an element that is not owned", (int64_t)element_ids[k]);
     ctx->h_color_off.assign(color_offsets, color_offsets + num_colors + 1);

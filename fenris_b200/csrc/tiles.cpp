@@ -21,13 +21,24 @@
 //              (greedy; on structured meshes they are the coordinate parities), and rot(u) balances the 16 residue classes
 //   flush      per (u, v) in CSR order of row u, one word: accumulator position (11 bits) | transposed << 11 | u << 12 | k << 19,
 //              k = position of v in the block row of u (from the node-block map; meshes with block rows >= 8192 keep the
-//              per-element kernel)
+//              per-element kernel).  The list has two segments: STORE (rows this tile writes with plain stores when the call
+//              overwrites) and REDUCE (rows it adds to with reductions).
+//   ownership  (TileShape::owner_stores) the reference's assemble() starts from zeroed values (global.rs:124-131); zero-filling 3.9 GB
+//              and then reducing into it costs a full extra pass over HBM.  Instead every row has exactly one STORING tile: a node
+//              whose elements all lie in one tile is complete there; a node shared by several tiles is owned by the lowest-numbered
+//              one, which stores ALL entries of its rows (those it has no contribution for as 0.0: position kTileZeroPos) and
+//              publishes a per-tile flag; the other tiles list the owners they depend on (`wait`) and reduce once those flags are
+//              up.  Tiles are handed out in index order, so a tile only ever waits for tiles that are already running: no
+//              deadlock, no co-residency requirement.  Rows of nodes that ghost elements of a partition touch are never stored
+//              (another rank adds to them as well): they and the rows no owned element touches are the `zero_nodes` the caller
+//              clears - a fraction of a percent of the values.
 //   schedule   the tile's elements ordered by a greedy node-disjoint colouring (fenris-paradis' idea, coloring.rs:6-70, applied
 //              inside the tile) and cut into ROUNDS of at most `warps` elements of one colour (padded to `warps` schedule
 //              positions).  The kernel's two groups of compute warps take the rounds alternately and add their blocks strictly
 //              in round order (named-barrier hand-over), so no two warps ever update the same accumulator concurrently
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <thread>
 
 #include "fb200_internal.h"
@@ -41,7 +52,9 @@ struct TileOut {
     int ne = 0;
     uint32_t P = 0, rounds = 0;
     std::vector<int32_t> nodes;
-    std::vector<uint32_t> flush;
+    std::vector<uint32_t> flush;   // pass 1: CSR order; pass 2 (finish_flush): STORE segment, then REDUCE segment
+    std::vector<uint32_t> wait;    // pass 2
+    uint32_t n_store = 0, flags = 0, zero_entries = 0;
     std::vector<uint8_t> lnodes;   // rounds * warps * 8
     std::vector<uint16_t> emap;    // rounds * warps * 64
     std::vector<int32_t> elem;     // rounds * warps
@@ -92,58 +105,6 @@ struct Builder {
             lab[u] = (uint8_t)best;
         }
         (void)ne;
-    }
-
-    // Flush reads (hex8_tile_kernel.cuh): item 3 e + j of the list is lane (entry e, column j); it reads the words 9 pos + 3 i + j
-    // (transposed: 9 pos + 3 j + i) for i = 0, 1, 2 in three loads, 16 lanes = 16 eight-byte banks per half-warp.  Entries of one row
-    // share few bank classes (pos mod 16 = 4 alpha(u) + ...), so consecutive entries collide.  With a rotation r_e the lane reads row
-    // (i + r_e) mod 3 in load i: chosen greedily, entry by entry, to minimise the bank maxima of the half-warps the entry touches.
-    static void rotate_flush_rows(std::vector<uint32_t>& flush) {
-        const size_t nf = flush.size();
-        const size_t halves = (3 * nf + 15) / 16;
-        std::vector<uint8_t> count(halves * 3 * 16, 0);  // [half-warp][load][bank]
-        std::vector<uint8_t> peak(halves * 3, 0);
-        for (size_t e = 0; e < nf; ++e) {
-            const uint32_t a = flush[e];
-            const int pos = (int)(a & 0x7ffu);
-            const bool tr = (a >> 11) & 1u;
-            int best = 0, best_cost = 1 << 30;
-            for (int r = 0; r < 3; ++r) {
-                int cost = 0;
-                for (int i = 0; i < 3; ++i) {
-                    const int ii = (i + r) % 3;
-                    uint8_t add[2][16] = {{0}};  // the entry's lanes may straddle two half-warps
-                    const size_t h0 = (3 * e) / 16;
-                    for (int j = 0; j < 3; ++j) {
-                        const size_t h = (3 * e + j) / 16;
-                        const int word = pos * 9 + (tr ? j * 3 + ii : ii * 3 + j);
-                        ++add[h - h0][word & 15];
-                    }
-                    for (int hh = 0; hh < 2; ++hh) {
-                        if (h0 + hh >= halves) continue;
-                        int m = peak[(h0 + hh) * 3 + i];
-                        for (int b = 0; b < 16; ++b)
-                            if (add[hh][b]) m = std::max<int>(m, count[((h0 + hh) * 3 + i) * 16 + b] + add[hh][b]);
-                        cost += m - peak[(h0 + hh) * 3 + i];
-                    }
-                }
-                if (cost < best_cost) {
-                    best_cost = cost;
-                    best = r;
-                }
-            }
-            for (int i = 0; i < 3; ++i) {
-                const int ii = (i + best) % 3;
-                for (int j = 0; j < 3; ++j) {
-                    const size_t h = (3 * e + j) / 16;
-                    const int word = pos * 9 + (tr ? j * 3 + ii : ii * 3 + j);
-                    uint8_t& c = count[(h * 3 + i) * 16 + (word & 15)];
-                    ++c;
-                    peak[h * 3 + i] = std::max(peak[h * 3 + i], c);
-                }
-            }
-            flush[e] = a | ((uint32_t)best << 30);
-        }
     }
 
     bool build_one(uint64_t p0, int ne, TileOut& t) {
@@ -257,10 +218,9 @@ struct Builder {
                         }
                     tr = 1;
                 }
-                if (x.k >= (1u << (shape.flush_rot ? kTileKBitsRot : kTileKBits))) degenerate = true;
+                if (x.k >= (1u << kTileKBits)) degenerate = true;
                 t.flush.push_back(pos | (tr << 11) | ((uint32_t)u << 12) | ((uint32_t)x.k << 19));
             }
-        if (shape.flush_rot) rotate_flush_rows(t.flush);
         // ---- schedule: greedy node-disjoint colouring inside the tile; every colour class is cut into rounds of at most
         // `warps` elements; rounds are padded to `warps` schedule positions (padding: node byte 0 = 0xff, no accumulators)
         std::vector<uint64_t> node_mask(nn, 0);
@@ -269,7 +229,8 @@ struct Builder {
             uint64_t used = 0;
             for (int a = 0; a < n; ++a) used |= node_mask[ln[el * n + a]];
             int c = 0;
-            while (c < 63 && ((used >> c) & 1)) ++c;
+            while (c < 64 && ((used >> c) & 1)) ++c;
+            if (c == 64) return false;  // 64 mutually conflicting elements: no free colour - the caller halves the tile
             colour[el] = c;
             for (int a = 0; a < n; ++a) node_mask[ln[el * n + a]] |= 1ull << c;
         }
@@ -317,28 +278,97 @@ struct Builder {
         }
         pad_round();
         t.rounds = (uint32_t)(t.elem.size() / gw);
+        if (t.rounds > 255) return false;  // bound asserted by the self test (cannot happen with <= 64 elements per tile)
         return true;
     }
 };
 
 }  // namespace
 
+// pass 2 of a tile: split the CSR-ordered flush list into the STORE and the REDUCE segment (see "ownership" in the header comment)
+static void finish_flush(TileOut& t, uint32_t tile, bool owner, const uint32_t* owner_tile, const int32_t* degree, const int32_t* degree_owned,
+                         const int64_t* blk_off) {
+    const int nn = (int)t.nodes.size();
+    // class of every tile node: 0 reduce, 1 store (complete), 2 store all entries of the rows (owner of a shared node)
+    uint8_t cls[128];
+    t.wait.clear();
+    t.flags = 0;
+    for (int u = 0; u < nn; ++u) {
+        const int32_t id = t.nodes[u] & 0x7fffffff;
+        if (t.nodes[u] < 0) {
+            cls[u] = 1;
+        } else if (!owner) {
+            cls[u] = 0;
+        } else if (degree[id] != degree_owned[id]) {
+            cls[u] = 0;  // ghost elements touch the node: other ranks add to its rows too; cleared by the caller, never stored
+            t.flags |= 1u;
+        } else if (owner_tile[id] == tile) {
+            cls[u] = 2;
+        } else {
+            cls[u] = 0;
+            t.wait.push_back(owner_tile[id]);
+        }
+    }
+    std::sort(t.wait.begin(), t.wait.end());
+    t.wait.erase(std::unique(t.wait.begin(), t.wait.end()), t.wait.end());
+    std::vector<uint32_t> store, reduce;
+    store.reserve(t.flush.size() + 256);
+    reduce.reserve(t.flush.size());
+    t.zero_entries = 0;
+    size_t f = 0;
+    const size_t nf = t.flush.size();
+    while (f < nf) {
+        const uint32_t u = (t.flush[f] >> 12) & 0x7fu;
+        size_t g = f;
+        while (g < nf && ((t.flush[g] >> 12) & 0x7fu) == u) ++g;
+        if (cls[u] == 0) {
+            reduce.insert(reduce.end(), t.flush.begin() + f, t.flush.begin() + g);
+        } else if (cls[u] == 1) {
+            store.insert(store.end(), t.flush.begin() + f, t.flush.begin() + g);
+        } else {
+            const int32_t id = t.nodes[u] & 0x7fffffff;
+            const uint32_t cnt = (uint32_t)(blk_off[id + 1] - blk_off[id]);
+            size_t h = f;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                if (h < g && (t.flush[h] >> 19) == k) {
+                    store.push_back(t.flush[h++]);
+                } else {
+                    store.push_back(kTileZeroPos | (u << 12) | (k << 19));
+                    ++t.zero_entries;
+                }
+            }
+        }
+        f = g;
+    }
+    t.n_store = (uint32_t)store.size();
+    store.insert(store.end(), reduce.begin(), reduce.end());
+    t.flush.swap(store);
+}
+
 void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* order, const uint64_t* codes, const int32_t* conn,
-                      uint64_t num_elements, uint64_t num_nodes, const uint16_t* blockmap, HostTiles& out) {
+                      uint64_t num_elements, uint64_t num_owned, uint64_t num_nodes, const uint16_t* blockmap, const int64_t* blk_off,
+                      HostTiles& out) {
     constexpr int n = 8;
     // incidences of every node over ALL elements of the space - also the ghost elements of a partition, which are in the pattern
     // but are not assembled here: a node is complete only if every element it belongs to is processed inside one tile (then
     // the flush writes every entry of its rows)
-    std::vector<int32_t> degree(num_nodes, 0);
+    std::vector<int32_t> degree(num_nodes, 0), degree_owned(num_nodes, 0);
     for (uint64_t e = 0; e < num_elements; ++e)
-        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
+        for (int a = 0; a < n; ++a) {
+            ++degree[conn[e * n + a]];
+            if (e < num_owned) ++degree_owned[conn[e * n + a]];
+        }
     out.hdr.clear();
     out.nodes.clear();
     out.flush.clear();
+    out.wait.clear();
+    out.zero_nodes.clear();
     out.lnodes.clear();
     out.emap.clear();
     out.elem.clear();
     out.bank_conflict_share = 0;
+    out.zero_entries = 0;
+    out.owner_stores = shape.owner_stores != 0 && blk_off != nullptr;
     // candidate tiles: runs with a common Morton prefix
     std::vector<std::pair<uint64_t, int>> cand;
     for (uint64_t p0 = 0; p0 < count;) {
@@ -382,27 +412,73 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         accesses += b.accesses;
     };
     const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-    const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, cand.size() / 64));
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
-    worker();
-    for (auto& th : pool) th.join();
+    auto run_pool = [&](uint64_t work_items, const std::function<void()>& fn) {
+        const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, work_items / 64));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(fn);
+        fn();
+        for (auto& th : pool) th.join();
+    };
+    run_pool(cand.size(), worker);
     if (degenerate.load()) {  // elements with repeated nodes (or huge block rows): the caller keeps the per-element kernel
         out.hdr.clear();
         out.bank_conflict_share = -1.0;
         return;
     }
+    // ---- pass 2: tile numbers are final now (the order of `results`); owner of every node = the lowest tile that touches it
+    std::vector<TileOut*> tiles;
     for (auto& rs : results)
-        for (TileOut& t : rs) {
-            const uint32_t hdr[kTileHdrWords] = {(uint32_t)out.elem.size(), t.rounds,                    (uint32_t)t.nodes.size(),   t.P,
-                                                 (uint32_t)out.nodes.size(), (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), (uint32_t)t.ne};
-            out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
-            out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
-            out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
-            out.lnodes.insert(out.lnodes.end(), t.lnodes.begin(), t.lnodes.end());
-            out.emap.insert(out.emap.end(), t.emap.begin(), t.emap.end());
-            out.elem.insert(out.elem.end(), t.elem.begin(), t.elem.end());
+        for (TileOut& t : rs) tiles.push_back(&t);
+    std::vector<uint32_t> owner_tile;
+    if (out.owner_stores) {
+        owner_tile.assign(num_nodes, 0xffffffffu);
+        for (size_t ti = 0; ti < tiles.size(); ++ti)
+            for (int32_t nd : tiles[ti]->nodes) {
+                uint32_t& o = owner_tile[nd & 0x7fffffff];
+                if (o == 0xffffffffu) o = (uint32_t)ti;
+            }
+        for (uint64_t i = 0; i < num_nodes; ++i)
+            if (owner_tile[i] == 0xffffffffu || degree[i] != degree_owned[i]) out.zero_nodes.push_back((int32_t)i);
+    }
+    next.store(0);
+    auto finisher = [&]() {
+        for (;;) {
+            const uint64_t t0 = next.fetch_add(64);
+            if (t0 >= tiles.size()) break;
+            for (uint64_t ti = t0; ti < std::min<uint64_t>(tiles.size(), t0 + 64); ++ti)
+                finish_flush(*tiles[ti], (uint32_t)ti, out.owner_stores, owner_tile.data(), degree.data(), degree_owned.data(), blk_off);
         }
+    };
+    run_pool(tiles.size(), finisher);
+    // ---- concatenate
+    uint64_t tot_nodes = 0, tot_flush = 0, tot_wait = 0, tot_pos = 0;
+    for (const TileOut* t : tiles) {
+        tot_nodes += t->nodes.size();
+        tot_flush += t->flush.size();
+        tot_wait += t->wait.size();
+        tot_pos += t->elem.size();
+    }
+    out.hdr.reserve(tiles.size() * kTileHdrWords);
+    out.nodes.reserve(tot_nodes);
+    out.flush.reserve(tot_flush);
+    out.wait.reserve(tot_wait);
+    out.lnodes.reserve(tot_pos * n);
+    out.emap.reserve(tot_pos * n * n);
+    out.elem.reserve(tot_pos);
+    for (const TileOut* tp : tiles) {
+        const TileOut& t = *tp;
+        const uint32_t hdr[kTileHdrWords] = {(uint32_t)out.elem.size(),  t.rounds, (uint32_t)t.nodes.size(), t.P, (uint32_t)out.nodes.size(),
+                                             (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), (uint32_t)t.ne, t.n_store,
+                                             (uint32_t)out.wait.size(),  (uint32_t)t.wait.size(), t.flags, 0u, 0u, 0u, 0u};
+        out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
+        out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
+        out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
+        out.wait.insert(out.wait.end(), t.wait.begin(), t.wait.end());
+        out.lnodes.insert(out.lnodes.end(), t.lnodes.begin(), t.lnodes.end());
+        out.emap.insert(out.emap.end(), t.emap.begin(), t.emap.end());
+        out.elem.insert(out.elem.end(), t.elem.begin(), t.elem.end());
+        out.zero_entries += t.zero_entries;
+    }
     out.bank_conflict_share = accesses.load() ? (double)conflicts.load() / (double)accesses.load() : 0.0;
 }
 
@@ -412,13 +488,13 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
 extern "C" fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
                                                   uint64_t num_owned, uint64_t stats[8], int32_t* failed_check) {
     uint64_t st[10];
-    const fb200_status s = fb200_tile_lists_selftest_ex(num_nodes, vertices, num_elements, connectivity, num_owned, 0, st, failed_check);
+    const fb200_status s = fb200_tile_lists_selftest_ex(num_nodes, vertices, num_elements, connectivity, num_owned, 1, st, failed_check);
     if (s == FB200_OK && stats) std::copy(st, st + 8, stats);
     return s;
 }
 
 extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const double* vertices, uint64_t num_elements,
-                                                     const uint64_t* connectivity, uint64_t num_owned, int32_t flush_rot, uint64_t stats[10],
+                                                     const uint64_t* connectivity, uint64_t num_owned, int32_t owner_stores, uint64_t stats[10],
                                                      int32_t* failed_check) {
     using namespace fb200;
     constexpr int n = 8, n2 = 64;
@@ -459,19 +535,34 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
             codes.push_back(codes_all[i]);
         }
     TileShape shape{6, 64, 8, 128, 1216};
-    shape.flush_rot = flush_rot ? 1 : 0;
-    const int kbits = shape.flush_rot ? kTileKBitsRot : kTileKBits;
-    uint64_t flush_loads = 0, flush_wavefronts = 0;  // model of the flush's shared-memory reads (see Builder::rotate_flush_rows)
+    shape.owner_stores = owner_stores ? 1 : 0;
+    std::vector<int64_t> blk_off(num_nodes + 1, 0);
+    for (uint64_t i = 0; i < num_nodes; ++i) blk_off[i + 1] = blk_off[i] + (int64_t)rows[i].size();
     HostTiles ht;
-    build_tile_lists(shape, order.size(), order.data(), codes.data(), conn.data(), num_elements, num_nodes, map.data(), ht);
+    build_tile_lists(shape, order.size(), order.data(), codes.data(), conn.data(), num_elements, num_owned, num_nodes, map.data(), blk_off.data(), ht);
     if (ht.bank_conflict_share < 0.0) return FB200_ERR_UNSUPPORTED;
+    if (ht.owner_stores != (owner_stores != 0)) return fail_check(22);
     // ---- checks
-    std::vector<int32_t> degree(num_nodes, 0);
+    std::vector<int32_t> degree(num_nodes, 0), degree_owned(num_nodes, 0);
     for (uint64_t e = 0; e < num_elements; ++e)
-        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
+        for (int a = 0; a < n; ++a) {
+            ++degree[conn[e * n + a]];
+            if (e < num_owned) ++degree_owned[conn[e * n + a]];
+        }
     std::vector<uint8_t> seen(num_elements, 0);
     const size_t ntiles = ht.hdr.size() / kTileHdrWords;
-    uint64_t max_nodes = 0, max_P = 0, complete = 0, max_rounds = 0, scheduled = 0;
+    uint64_t max_nodes = 0, max_P = 0, complete = 0, max_rounds = 0, scheduled = 0, store_entries = 0, zero_entries = 0;
+    // ownership: the lowest tile that touches a node; how many tiles store the node's rows (must be exactly one per storable node)
+    std::vector<uint32_t> first_tile(num_nodes, 0xffffffffu);
+    std::vector<uint8_t> stored_by(num_nodes, 0);
+    for (size_t t = 0; t < ntiles; ++t) {
+        const uint32_t* h = &ht.hdr[t * kTileHdrWords];
+        if ((uint64_t)h[4] + h[2] > ht.nodes.size()) return fail_check(2);
+        for (uint32_t u = 0; u < h[2]; ++u) {
+            uint32_t& o = first_tile[ht.nodes[h[4] + u] & 0x7fffffff];
+            if (o == 0xffffffffu) o = (uint32_t)t;
+        }
+    }
     for (size_t t = 0; t < ntiles; ++t) {
         const uint32_t* h = &ht.hdr[t * kTileHdrWords];
         const uint32_t p0 = h[0], R = h[1], nn = h[2], P = h[3], nb = h[4], fb = h[5], nf = h[6], ne = h[7];
@@ -534,49 +625,65 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
             if (taken[pairs[i].second]) return fail_check(11);
             taken[pairs[i].second] = 1;
         }
-        // flush list: every coupled ordered pair (u, v) exactly once, in CSR order of row u, with the position of v in u's block row
-        if (nf != 2 * pairs.size() - [&] { size_t d = 0; for (auto& pr : pairs) d += (pr.first >> 8) == (pr.first & 0xffu); return d; }()) return fail_check(12);
-        uint32_t last_u = 0, last_k = 0;
+        // flush list: every coupled ordered pair (u, v) exactly once with the position of v in u's block row; two segments (STORE, then
+        // REDUCE), each in CSR order of its rows; zero words only in the STORE segment of a shared node's owner, completing its rows
+        const uint32_t nstore = h[8], wb = h[9], nw = h[10];
+        if (nstore > nf || (uint64_t)wb + nw > ht.wait.size()) return fail_check(2);
+        store_entries += nstore;
+        const size_t diag = [&] { size_t d = 0; for (auto& pr : pairs) d += (pr.first >> 8) == (pr.first & 0xffu); return d; }();
+        uint32_t last_u = 0, last_k = 0, zeros = 0;
+        std::vector<uint8_t> row_seg(nn, 0);       // 1 = row seen in the STORE segment, 2 = in the REDUCE segment
+        std::vector<uint32_t> row_entries(nn, 0);
         for (uint32_t f = 0; f < nf; ++f) {
             const uint32_t w = ht.flush[fb + f];
-            const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = (w >> 19) & ((1u << kbits) - 1u);
+            const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = w >> 19;
+            const uint32_t seg = f < nstore ? 1u : 2u;
             if (u >= nn) return fail_check(13);
-            if ((w >> 19) >> kbits >= 3u || (!shape.flush_rot && (w >> 19) >> kbits)) return fail_check(21);  // rotation 0..2, none without the flag
-            if (f && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
+            if (f && f != nstore && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
             last_u = u;
             last_k = k;
+            if (row_seg[u] && row_seg[u] != seg) return fail_check(23);  // a row lives in one segment only
+            row_seg[u] = (uint8_t)seg;
+            ++row_entries[u];
             const auto& r = rows[ht.nodes[nb + u] & 0x7fffffff];
             if (k >= r.size()) return fail_check(15);
             const int32_t vg = r[k];
             const auto it = std::lower_bound(ht.nodes.begin() + nb, ht.nodes.begin() + nb + nn, vg, [](int32_t x, int32_t y) { return (x & 0x7fffffff) < y; });
-            if (it == ht.nodes.begin() + nb + nn || (*it & 0x7fffffff) != vg) return fail_check(16);
+            const bool v_in_tile = it != ht.nodes.begin() + nb + nn && (*it & 0x7fffffff) == vg;
             const uint32_t v = (uint32_t)(it - (ht.nodes.begin() + nb));
-            if (tr != (u > v ? 1u : 0u)) return fail_check(17);
-            const uint32_t key = ((std::min(u, v)) << 8) | std::max(u, v);
+            const uint32_t key = v_in_tile ? ((std::min(u, v)) << 8) | std::max(u, v) : 0xffffffffu;
             const auto pit = std::lower_bound(pairs.begin(), pairs.end(), std::make_pair(key, 0u));
-            if (pit == pairs.end() || pit->first != key || pit->second != ps) return fail_check(18);
-        }
-        // the three 64-bit loads of every 32-item group: two half-warps each, max distinct words per 8-byte bank
-        for (uint32_t g = 0; g < 3 * nf; g += 16)
-            for (int i = 0; i < 3; ++i) {
-                int words[16], cnt = 0, worst = 0;
-                for (uint32_t it = g; it < std::min(g + 16, 3 * nf); ++it) {
-                    const uint32_t w = ht.flush[fb + it / 3];
-                    const int j = (int)(it % 3), ii = (i + (int)(shape.flush_rot ? w >> 30 : 0)) % 3;
-                    words[cnt++] = (int)(w & 0x7ffu) * 9 + (((w >> 11) & 1u) ? j * 3 + ii : ii * 3 + j);
-                }
-                for (int b = 0; b < 16; ++b) {
-                    int m = 0;
-                    for (int x = 0; x < cnt; ++x) {
-                        bool first = (words[x] & 15) == b;
-                        for (int y = 0; first && y < x; ++y) first = words[y] != words[x];
-                        m += first;
-                    }
-                    worst = std::max(worst, m);
-                }
-                flush_wavefronts += worst;
-                flush_loads += (g % 32 == 0);
+            const bool coupled = v_in_tile && pit != pairs.end() && pit->first == key;
+            if (ps == kTileZeroPos) {
+                // a zero word: only where the tile has no contribution, only in the STORE segment, only with ownership
+                if (!ht.owner_stores || seg != 1 || tr || coupled) return fail_check(24);
+                ++zeros;
+                continue;
             }
+            if (!v_in_tile) return fail_check(16);
+            if (tr != (u > v ? 1u : 0u)) return fail_check(17);
+            if (!coupled || pit->second != ps) return fail_check(18);
+        }
+        if (nf - zeros != 2 * pairs.size() - diag) return fail_check(12);
+        zero_entries += zeros;
+        for (uint32_t u = 0; u < nn; ++u) {
+            const int32_t id = ht.nodes[nb + u] & 0x7fffffff;
+            const bool is_complete = ht.nodes[nb + u] < 0, ghosted = degree[id] != degree_owned[id];
+            const bool owner_here = ht.owner_stores && !ghosted && first_tile[id] == (uint32_t)t;
+            const bool must_store = is_complete || owner_here;
+            if (row_seg[u] != (must_store ? 1 : 2)) return fail_check(25);
+            if (must_store) {
+                if (row_entries[u] != rows[id].size()) return fail_check(26);  // a stored row is written completely
+                if (++stored_by[id] != 1) return fail_check(27);
+            } else if (ht.owner_stores && !ghosted) {
+                // reductions into a row another tile stores: that tile is lower-numbered and in the wait list
+                const uint32_t o = first_tile[id];
+                if (o >= (uint32_t)t || !std::binary_search(ht.wait.begin() + wb, ht.wait.begin() + wb + nw, o)) return fail_check(28);
+            }
+        }
+        for (uint32_t k = 0; k < nw; ++k)
+            if (ht.wait[wb + k] >= (uint32_t)t || (k && ht.wait[wb + k] <= ht.wait[wb + k - 1])) return fail_check(29);
+        if (!ht.owner_stores && (nw || zeros)) return fail_check(30);
         for (uint32_t u = 0; u < nn; ++u) {
             const bool flag = ht.nodes[nb + u] < 0;
             if (flag != (inc[u] == degree[ht.nodes[nb + u] & 0x7fffffff])) return fail_check(19);
@@ -585,6 +692,20 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
     }
     for (uint64_t e = 0; e < num_owned; ++e)
         if (!seen[e]) return fail_check(20);
+    // with ownership every row is either stored by exactly one tile or listed for the caller to clear
+    if (ht.owner_stores) {
+        size_t z = 0;
+        for (uint64_t i = 0; i < num_nodes; ++i) {
+            const bool listed = z < ht.zero_nodes.size() && (uint64_t)ht.zero_nodes[z] == i;
+            z += listed;
+            if (listed == (stored_by[i] == 1)) return fail_check(31);
+            if (listed != (first_tile[i] == 0xffffffffu || degree[i] != degree_owned[i])) return fail_check(31);
+        }
+        if (z != ht.zero_nodes.size()) return fail_check(31);
+        if (zero_entries != ht.zero_entries) return fail_check(32);
+    } else if (!ht.zero_nodes.empty()) {
+        return fail_check(31);
+    }
     stats[0] = ntiles;
     stats[1] = max_nodes;
     stats[2] = max_P;
@@ -593,7 +714,7 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
     stats[5] = (uint64_t)(ht.bank_conflict_share * 1e6);
     stats[6] = scheduled;
     stats[7] = max_rounds;
-    stats[8] = flush_loads;
-    stats[9] = flush_wavefronts;
+    stats[8] = store_entries;
+    stats[9] = zero_entries;
     return FB200_OK;
 }

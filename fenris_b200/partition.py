@@ -135,3 +135,67 @@ def localize(vertices: np.ndarray, connectivity: np.ndarray, owned: np.ndarray, 
     lookup = np.full(int(conn.max()) + 1 if conn.size else 1, -1, dtype=np.int64)
     lookup[gids] = np.arange(len(gids))
     return np.ascontiguousarray(vertices[gids]), lookup[sub].astype(np.uint64), gids
+
+
+def element_range_partition(vertices: np.ndarray, connectivity: np.ndarray, starts, rank: int):
+    """Partition by CONTIGUOUS ELEMENT RANGES of any uniform mesh: rank r owns elements [starts[r], starts[r+1]).
+
+    The reference's generators emit cells layer by layer (procedural.rs:216-403), so ranges of element ids are z-slabs of the
+    structured hex and BCC tet meshes (config C5: 50 M tets over 8 ranks); for any other mesh the ranges are whatever the caller's
+    ordering makes them.  Returns a dict for `rank`:
+      vertices, connectivity  rank-local mesh: owned elements first, then the GHOST elements = elements of other ranks that touch a node
+                              of an owned element (pattern only: they make the rows of interface nodes identical on all sharing ranks)
+      num_owned               owned elements
+      global_nodes            global id of every local node (ascending, so local order = global order)
+      peers                   [(peer rank, local ids of the nodes shared with it, ascending global id - the same order on both sides)]
+    Only O(own slab) memory beyond the global arrays passed in."""
+    conn = np.asarray(connectivity)
+    starts = np.asarray(starts, dtype=np.int64)
+    nranks = len(starts) - 1
+    e0, e1 = int(starts[rank]), int(starts[rank + 1])
+    num_nodes = len(vertices)
+    mine = np.zeros(num_nodes, dtype=bool)
+    mine[conn[e0:e1].ravel().astype(np.int64)] = True
+    # elements of other ranks that touch one of my nodes (chunked: the gather mine[conn] is the only O(E) temporary)
+    ghost_ids = []
+    chunk = 1 << 22
+    for a in range(0, len(conn), chunk):
+        b = min(a + chunk, len(conn))
+        hit = mine[conn[a:b].astype(np.int64)].any(axis=1)
+        lo, hi = max(a, e0), min(b, e1)
+        if lo < hi:
+            hit[lo - a:hi - a] = False
+        ghost_ids.append(np.nonzero(hit)[0] + a)
+    ghosts = np.concatenate(ghost_ids) if ghost_ids else np.zeros(0, dtype=np.int64)
+    owner_of_ghost = np.searchsorted(starts, ghosts, side="right") - 1
+    owned = np.arange(e0, e1, dtype=np.int64)
+    lverts, lconn, gids = localize(vertices, conn, owned, ghosts)
+    peers = []
+    for q in np.unique(owner_of_ghost):
+        assert 0 <= q < nranks and q != rank
+        touched_by_q = np.unique(conn[ghosts[owner_of_ghost == q]].ravel().astype(np.int64))
+        shared = touched_by_q[mine[touched_by_q]]  # ascending global ids: nodes of my owned elements that q's elements touch too
+        peers.append((int(q), np.searchsorted(gids, shared).astype(np.uint64)))
+    return {"vertices": lverts, "connectivity": lconn, "num_owned": e1 - e0, "global_nodes": gids, "peers": peers}
+
+
+def tet_box_layer_starts(cx: int, cy: int, cz: int) -> np.ndarray:
+    """First element id of every z-layer of cells of the reference's BCC tet box mesh (create_rectangular_uniform_tet_mesh,
+    procedural.rs:286-403), as fb200_gen_tet_mesh / the oracle emit it: cells in k-major order, a cell emits 4 tets per face shared with
+    its +axis neighbour and 2 per face on the box boundary.  Returns cz + 1 offsets."""
+    def per_axis(n):
+        c = np.full(n, 4, dtype=np.int64)   # interior +face octahedron
+        c[-1] = 0
+        c[0] += 2                           # low boundary pyramid
+        c[-1] += 2                          # high boundary pyramid
+        return c
+    ax, ay, az = per_axis(cx), per_axis(cy), per_axis(cz)
+    per_layer = cy * ax.sum() + cx * ay.sum() + cx * cy * az  # [cz]
+    return np.concatenate([[0], np.cumsum(per_layer)]).astype(np.int64)
+
+
+def split_layers(num_layers: int, nranks: int) -> np.ndarray:
+    """Layer boundaries of nranks slabs, as even as possible (the first num_layers % nranks slabs get one more)."""
+    base, extra = divmod(num_layers, nranks)
+    sizes = np.array([base + (1 if r < extra else 0) for r in range(nranks)], dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(sizes)])

@@ -111,8 +111,9 @@ fb200_status fb200_timer_end(fb200_ctx* ctx, float* milliseconds); /* synchroniz
 uint64_t fb200_launch_count(fb200_ctx* ctx);
 /* Kernel-selection knobs (no reference counterpart; results never depend on them beyond fp reassociation).
  * "hex8_tile": elements per shared-memory tile of the Hex8 atomic scatter - 64 (default) or 0 = per-element kernel.
- * "hex8_flush_rot": 1 = the tile kernel's flush reads its accumulator rows in a per-entry rotated order chosen on the host to spread the
- *   shared-memory banks (same sums; block rows limited to 2048 coupled nodes); 0 (default) = rows in order. */
+ * "hex8_owner_stores": 1 (default) = an overwriting Hex8 tile assembly needs no zero-fill of the values: every CSR row is stored by exactly
+ *   one tile (the lowest-numbered one that touches the node, which also writes the row's zeros) and the other tiles reduce into it after
+ *   that tile has published its stores; 0 = zero-fill all values, store tile-complete rows only, reduce into the rest. */
 fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value);
 
 /* ---- the space: Mesh<f64, D, C>  (src/mesh.rs:23-40) --------------------------------------- */
@@ -244,6 +245,14 @@ fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const
 /* Sum the interface rows over the ranks that share them.  Peers set: pack per peer -> ncclSend/ncclRecv (one group) -> add the
  * received blocks; otherwise pack -> ncclAllReduce(sum, f64) -> unpack.  Over NVLink, enqueued on the ctx stream. */
 fb200_status fb200_interface_allreduce(fb200_ctx* ctx);
+/* Optional, after fb200_comm_init + fb200_interface_set_peers (collective over the neighbours): fuse the interface exchange into the
+ * assembly kernel.  Every rank maps its neighbours' value arrays (CUDA IPC over NVLink) and learns where their copies of the shared rows
+ * start; the Hex8 tile kernel's flush then adds this rank's partial sums of an interface row to the neighbour's copy as well
+ * (red.global.add.f64 on the peer pointer), and fb200_interface_allreduce shrinks to a neighbour barrier - no pack, no ncclSend/ncclRecv,
+ * no add pass.  Needs one neighbour per interface node and at most two neighbours per rank (slab-like partitions); otherwise
+ * FB200_ERR_UNSUPPORTED and the packed exchange stays in use.  Assemblies that do not run the tile kernel keep the packed exchange too.
+ * The mapping belongs to the current pattern: call again after a new pattern (on every rank). */
+fb200_status fb200_interface_enable_p2p(fb200_ctx* ctx);
 
 /* ---- host-side helpers restating the reference's generators (no GPU needed) ----------------- */
 /* src/mesh/procedural.rs:216-277 / 286-403 / 46-93.  Call with vertices == NULL to query sizes. */
@@ -272,11 +281,12 @@ void fb200_lame_from_young_poisson(double young, double poisson, double* mu, dou
  * coupled pair of the tile exactly once with the right position in the CSR block row, complete flags, size limits.
  * stats[0..7] = tiles, max nodes, max accumulator positions, flush entries, complete nodes, bank-conflict share * 1e6, schedule positions,
  * max rounds.  Returns FB200_OK, FB200_ERR_UNSUPPORTED when the mesh cannot use tiles (repeated nodes), FB200_ERR_STATE + (*failed_check = id)
- * when a check fails.  The _ex form also builds the lists with the rotated flush reads (flush_rot != 0, see fb200_set_tuning
- * "hex8_flush_rot") and reports a model of the flush's shared-memory reads: stats[8] = 64-bit loads per warp, stats[9] = their wavefronts
- * (two half-warps per load, max distinct words per 8-byte bank; 2 per load is conflict free). */
+ * when a check fails.  The plain form builds the lists with first-writer ownership (fb200_set_tuning "hex8_owner_stores" = 1); the _ex form
+ * takes the setting and also reports stats[8] = flush entries in the STORE segments, stats[9] = zero entries written by the owners of
+ * shared rows.  Ownership checks: every row is stored completely by exactly one tile or listed for clearing (rows that ghost elements touch),
+ * and a tile that reduces into a stored row waits for a lower-numbered tile. */
 fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
-                                          uint64_t num_owned, int32_t flush_rot, uint64_t stats[10], int32_t* failed_check);
+                                          uint64_t num_owned, int32_t owner_stores, uint64_t stats[10], int32_t* failed_check);
 fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
                                        uint64_t num_owned, uint64_t stats[8], int32_t* failed_check);
 

@@ -156,3 +156,86 @@ def test_general_partition_layout_is_consistent():
             assert int(loc_ro[li + 1] - loc_ro[li]) == int(blocks[g]), "ghosts must complete interface rows"
             assert seen.setdefault(g, off) == off, "all sharing ranks use the same packed offset"
     assert len(seen) > 0
+
+
+# ------------------------------------------------------------------------------------------------ element-range partitions (C5: Tet4 slabs)
+def _range_mesh(kind):
+    if kind == "tet4":
+        v, c = fo.create_unit_box_uniform_tet_mesh_3d(3)
+        layers = partition.tet_box_layer_starts(3, 3, 3)
+        return fo.TET4, v, np.asarray(c, dtype=np.int64), layers
+    v8, c8 = fo.create_unit_box_uniform_hex_mesh_3d(3)
+    v, c = fo.hex27_mesh_from_hex8(v8, np.asarray(c8, dtype=np.int64))
+    return fo.HEX27, np.asarray(v), np.asarray(c, dtype=np.int64), np.arange(4, dtype=np.int64) * 9  # 9 cells per z-layer
+
+
+def _range_worker(rank, world, port, kind, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        et, v, c, layer_starts = _range_mesh(kind)
+        starts = layer_starts[partition.split_layers(len(layer_starts) - 1, world)]
+        part = partition.element_range_partition(v, c, starts, rank)
+        lv, lc, n_owned, gids = part["vertices"], part["connectivity"].astype(np.int64), part["num_owned"], part["global_nodes"]
+        prob = fo.Problem(et, lv, lc, fo.LINEAR_ELASTIC, params=(MU, LAM))
+        s = prob.sdim
+        ro, ci = fo.assemble_pattern_fast(s, len(lv), lc)  # ghosts complete the pattern
+        values = np.zeros(len(ci))
+        K = fo.element_matrices_fast(prob)
+        for e in range(n_owned):  # ghosts are NOT assembled
+            fo.scatter_element(values, ro, ci, s, lc[e].tolist(), K[e])
+        # neighbour exchange exactly as fb200_interface_set_peers / interface_exchange_peers order the rows
+        sends, recvs, reqs = [], [], []
+        for peer, nodes in part["peers"]:
+            seg = np.concatenate([values[int(ro[s * n]):int(ro[s * n + s])] for n in nodes.astype(np.int64)])
+            sends.append(torch.from_numpy(seg.copy()))
+            recvs.append(torch.zeros(len(seg), dtype=torch.float64))
+            reqs.append(dist.isend(sends[-1], dst=peer))
+            reqs.append(dist.irecv(recvs[-1], src=peer))
+        for r in reqs:
+            r.wait()
+        for (peer, nodes), got in zip(part["peers"], recvs):
+            got, o = got.numpy(), 0
+            for n in nodes.astype(np.int64):
+                b, e = int(ro[s * n]), int(ro[s * n + s])
+                values[b:e] += got[o:o + (e - b)]
+                o += e - b
+        # rows of the nodes of this rank's OWNED elements, with global column ids
+        rows = {}
+        for l in np.unique(lc[:n_owned]).tolist():
+            for i in range(s):
+                b, e = int(ro[s * l + i]), int(ro[s * l + i + 1])
+                cols = ci[b:e].astype(np.int64)
+                rows[s * int(gids[l]) + i] = (s * gids[cols // s] + cols % s, values[b:e].copy())
+        q.put((rank, rows, int(n_owned)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world", [("tet4", 2), ("tet4", 3), ("hex27", 2)])
+def test_element_range_partition_equals_global(kind, world):
+    """partition.element_range_partition (config C5's slabs of the BCC tet mesh; Hex27 slabs): owned + ghost elements, neighbour lists in
+    the same order on both sides; the exchanged rows equal a single-process assembly of the whole mesh."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_range_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    et, v, c, _ = _range_mesh(kind)
+    prob = fo.Problem(et, v, c, fo.LINEAR_ELASTIC, params=(MU, LAM))
+    ro, ci, vals = fo.assemble_fast(prob)
+    assert sum(r[2] for r in results) == len(c)
+    covered = set()
+    for rank, rows, _ in results:
+        for grow, (cols, val) in rows.items():
+            b, e = int(ro[grow]), int(ro[grow + 1])
+            assert np.array_equal(cols, ci[b:e].astype(np.int64)), (rank, grow)
+            assert np.allclose(val, vals[b:e], rtol=1e-13, atol=1e-9 * np.abs(vals).max()), (rank, grow)
+            covered.add(grow)
+    assert len(covered) == len(ro) - 1

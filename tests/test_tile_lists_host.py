@@ -21,12 +21,12 @@ def _selftest(v, c, owned=None):
     return st, failed.value, list(stats)
 
 
-def _selftest_ex(v, c, flush_rot, owned=None):
+def _selftest_ex(v, c, owner_stores, owned=None):
     v = np.ascontiguousarray(v, dtype=np.float64)
     c = np.ascontiguousarray(c, dtype=np.uint64)
     stats = (C.c_uint64 * 10)()
     failed = C.c_int32(0)
-    st = nat.lib().fb200_tile_lists_selftest_ex(len(v), nat.ptr(v), len(c), nat.ptr(c), len(c) if owned is None else owned, flush_rot, stats,
+    st = nat.lib().fb200_tile_lists_selftest_ex(len(v), nat.ptr(v), len(c), nat.ptr(c), len(c) if owned is None else owned, owner_stores, stats,
                                                 C.byref(failed))
     return st, failed.value, list(stats)
 
@@ -38,9 +38,19 @@ def test_structured_cubes(n):
     assert st == nat.OK, f"check {failed} failed"
     tiles, max_nodes, max_pos, flush, complete, conflict_ppm, positions, max_rounds = s
     assert tiles == ((n + 3) // 4) ** 3 and max_nodes <= 125 and max_pos <= 1216
-    if n % 4 == 0:
-        # 4 x 4 x 4 tiles: 125 nodes and 2197 node blocks each, 8 colours of 8 elements; complete = nodes off the inner tile faces
-        assert flush == tiles * 2197 and complete == (n + 2 - n // 4) ** 3 and max_rounds == 8 and positions == n ** 3
+    for owner in (0, 1):
+        st, failed, sx = _selftest_ex(m.vertices(), m.connectivity(), owner)
+        assert st == nat.OK, f"owner_stores={owner}: check {failed} failed"
+        flush, store, zeros = sx[3], sx[8], sx[9]
+        if n % 4 == 0:
+            # 4 x 4 x 4 tiles: 125 nodes and 2197 node blocks each, 8 colours of 8 elements; complete = nodes off the inner tile faces
+            assert flush == tiles * 2197 + zeros and complete == (n + 2 - n // 4) ** 3 and max_rounds == 8 and positions == n ** 3
+        nnz_blocks = (3 * n + 1) ** 3  # node-block pattern of the structured mesh: (3n + 1)^3 coupled pairs
+        if owner:
+            # every row is stored exactly once, zeros included: the STORE segments cover the whole block pattern
+            assert store == nnz_blocks and (zeros > 0) == (tiles > 1)
+        else:
+            assert zeros == 0 and store < nnz_blocks or tiles == 1
     assert conflict_ppm < 30000  # the bank-aware accumulator positions keep collisions rare
 
 
@@ -81,26 +91,22 @@ def test_index_out_of_bounds():
     assert _selftest(m.vertices(), c)[0] == nat.ERR_INDEX_OOB
 
 
-def test_rotated_flush_lists_keep_every_invariant_and_spread_the_banks():
-    # opt-in fb200_set_tuning("hex8_flush_rot"): the flush words carry a rotation (bits 30-31) of the block row a lane reads first.
-    # Same lists otherwise (all 21 checks), and the modelled shared-memory wavefronts per flush load drop (the model reproduces the
-    # ncu source counters of the shipped order: 6.2 vs 5.6-6.6 measured, profiles/r01/README.md)
+def test_owner_lists_on_unstructured_numbering_and_partitions():
+    # first-writer ownership (fb200_set_tuning "hex8_owner_stores"): every row stored completely by exactly one tile, reducers wait for
+    # a lower-numbered tile, rows that ghost elements touch are listed for clearing instead (checks 22-32 of the self test)
     m = fb.create_unit_box_uniform_hex_mesh_3d(12)
-    st0, failed0, s0 = _selftest_ex(m.vertices(), m.connectivity(), 0)
-    st1, failed1, s1 = _selftest_ex(m.vertices(), m.connectivity(), 1)
-    assert st0 == nat.OK and st1 == nat.OK, (failed0, failed1)
-    assert s0[:8] == s1[:8] and s0[8] == s1[8] > 0
-    per_load0, per_load1 = s0[9] / s0[8], s1[9] / s1[8]
-    assert 5.5 < per_load0 < 6.8 and per_load1 < 0.72 * per_load0 and per_load1 >= 2.0
-    # unstructured numbering, ghosts
     v = fo.jitter_vertices(m.vertices(), 1.0 / 12, amp=0.2)
     rng = np.random.default_rng(5)
     perm = rng.permutation(len(v))
     inv = np.empty_like(perm)
     inv[perm] = np.arange(len(v))
     c = inv[m.connectivity().astype(np.int64)][rng.permutation(m.num_elements())]
-    st, failed, s = _selftest_ex(v[perm], c, 1)
-    assert st == nat.OK, f"check {failed} failed"
-    verts, conn, n_owned, _ = structured_hex_slab(8, 8, 12, 1.0 / 8, 1, 3)
-    st, failed, s = _selftest_ex(verts, conn, 1, owned=n_owned)
-    assert st == nat.OK, f"check {failed} failed"
+    for owner in (0, 1):
+        st, failed, s = _selftest_ex(v[perm], c, owner)
+        assert st == nat.OK, f"check {failed} failed"
+        assert (s[8] == 37 ** 3) == bool(owner)
+    for rank in range(3):
+        verts, conn, n_owned, _ = structured_hex_slab(8, 8, 12, 1.0 / 8, rank, 3)
+        for owner in (0, 1):
+            st, failed, s = _selftest_ex(verts, conn, owner, owned=n_owned)
+            assert st == nat.OK, f"rank {rank}: check {failed} failed"
