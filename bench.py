@@ -1,16 +1,25 @@
 #!/usr/bin/env python3
-"""bench.py - headline benchmark: Hex8 3-D linear-elasticity elements/s assembled into a pre-built global CSR.
+"""bench.py - headline benchmark: elements/s assembled into a pre-built global CSR.
 
 Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W   prints ONE JSON line.
-  * N = 1 workload = BASELINE.json config C3: unit cube, 126^3 Hex8 cells (2 000 376 elements, 6 145 149 dofs,
-    nnz 489 959 451), canonical 2x2x2 Gauss rule, Lame from Young 1e6 / Poisson 0.2, u = 0, fp64.
-  * N > 1 (torchrun, one rank per GPU): weak scaling - every rank owns a 126 x 126 x 126-cell z-slab of a
-    126 x 126 x (126 N) box; rows of the N-1 interface node planes are summed with ncclAllReduce (packed, interface rows only).
-  * a "step" = one assemble_into_csr-equivalent (values zeroed/overwritten + all element contributions + interface exchange),
-    mesh / pattern / scatter map / colours resident in HBM and built outside the timed region, exactly like
-    benches/assembly.rs:131-141 of the reference keeps the pattern outside the timed closure.
+  * --workload c3 (default; BASELINE.json config C3, the one the metric is quoted on): Hex8 3-D linear elasticity, unit cube,
+    126^3 cells per GPU (2 000 376 elements, 6 145 149 dofs, nnz 489 959 451), canonical 2x2x2 Gauss rule, Lame from Young 1e6 /
+    Poisson 0.2, u = 0, fp64.  N > 1 (torchrun, one rank per GPU): WEAK scaling - every rank owns a 126^3-cell z-slab of a
+    126 x 126 x (126 N) box; the rows of the N-1 interface node planes are completed by the interface exchange:
+      --exchange p2p (default)  fused into the tile kernel's flush: reductions straight into the neighbour's rows over NVLink (CUDA IPC
+                                peer memory) + one neighbour barrier - no pack / send / add passes (fenris_b200/csrc/comm.cu)
+      --exchange peers          packed rows, ncclSend / ncclRecv per neighbour, added on arrival
+      --exchange allreduce      one world ncclAllReduce over a packed buffer of all interface rows
+  * --workload c5 (BASELINE.json config C5): Tet4 linear elasticity, create_unit_box_uniform_tet_mesh_3d(161) = 50 079 372 elements,
+    STRONG scaling: the mesh is cut into N z-slabs of element ranges (fenris_b200/partition.py), neighbour exchange of the packed rows.
+  * a "step" = one assemble()-equivalent (values = all element contributions, interface exchange included), mesh / pattern / scatter
+    lists resident in HBM and built outside the timed region, exactly like benches/assembly.rs:131-141 of the reference keeps the
+    pattern outside the timed closure.
+  * "parity": after the timed region every rank compares rows of its assembled matrix - the interface planes (N > 1) and a plane in
+    the middle of its slab - ENTRYWISE with the C restatement of the reference CPU path on the sub-mesh around those rows (the oracle as
+    checker, never as the thing measured).
   * --impl reference: the reference's CPU path (C restatement, OpenMP over colours = fenris-paradis semantics; the Rust
-    original cannot be built in this image) timed on the host cores on a bounded sample of the same workload.
+    original cannot be built in this image) timed on the host cores on the same workload when the host has the memory for it.
 """
 from __future__ import annotations
 
@@ -29,9 +38,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CELLS = 126
+C5_CELLS = 161
 YOUNG, POISSON = 1e6, 0.2
 MODE_NAMES = {"atomic": 0, "colored": 1, "gather": 2}
-SAMPLE_CELLS = 64  # CPU baseline sample: 64^3 Hex8 elasticity cube (262 144 elements)
+SAMPLE_CELLS = 64  # CPU baseline sample inside the GPU arm: 64^3 Hex8 elasticity cube (262 144 elements)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -49,6 +59,14 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_memory_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 0.0
 
 
 class ClockSampler:
@@ -108,67 +126,160 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def slab_local_mesh(cells_xy: int, cells_z_per_rank: int, rank: int, nranks: int, h: float):
-    """Element partition by z-slabs with one ghost cell layer per neighbour (see fenris_b200/partition.py)."""
-    from fenris_b200 import partition
-    return partition.structured_hex_slab(cells_xy, cells_xy, cells_z_per_rank * nranks, h, rank, nranks)
-
-
-def best_thread_count(cr, fo, w, p, data, v, c, ro, ci, vals, colors):
+def best_thread_count(cr, et, op, w, p, data, v, c, ro, ci, vals, colors):
     """All the host threads the CPU path can USE: the coloured loop is memory/NUMA bound and gets slower when
     hyper-threads are oversubscribed, so try max, max/2, max/4 and keep the fastest."""
     mx = cr.max_threads()
     cands = sorted({mx, max(mx // 2, 1), max(mx // 4, 1), min(os.cpu_count() or mx, mx)}, reverse=True)
     best, best_t = mx, None
     for t in cands:
-        dt = None
-        for _ in range(2):
-            vals[:] = 0
-            t0 = time.perf_counter()
-            cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, w, p, data, v, c, ro, ci, values=vals, colors=colors, nthreads=t)
-            d = time.perf_counter() - t0
-            dt = d if dt is None else min(dt, d)
+        vals[:] = 0
+        t0 = time.perf_counter()
+        cr.assemble(et, op, w, p, data, v, c, ro, ci, values=vals, colors=colors, nthreads=t)
+        dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = t, dt
     return best
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
+def cpu_problem(workload, cells):
+    """The CPU arm's problem: mesh, pattern, colours, rule (oracle side only)."""
     from oracle import cpu_ref as cr
     from oracle import fenris_oracle as fo
+    mu, lam = fo.lame_from_young_poisson(YOUNG, POISSON)
+    if workload == "c5":
+        v, c = cr.gen_tet_mesh(cells)
+        et = fo.TET4
+        w, p = fo.tetrahedron_rule(1)
+    else:
+        v, c = cr.gen_hex_mesh(cells)
+        et = fo.HEX8
+        w, p = fo.hexahedron_gauss(2)
+    ro, ci = cr.pattern(3, len(v), c)
+    colors = cr.color_greedy(c, len(v))
+    return cr, et, fo.LINEAR_ELASTIC, w, p, (mu, lam), v, c, ro, ci, colors
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = SAMPLE_CELLS
-    v, c = cr.gen_hex_mesh(n)
-    ro, ci = cr.pattern(3, len(v), c)
-    colors = cr.color_greedy(c, len(v))
-    w, p = fo.hexahedron_gauss(2)
-    mu, lam = fo.lame_from_young_poisson(YOUNG, POISSON)
+    full = C5_CELLS if args.workload == "c5" else CELLS
+    # full size needs the CSR (values + u64 column indices) and the mesh on the host: ~9 GB for C3, ~22 GB for C5
+    need_gb = 30.0 if args.workload == "c5" else 14.0
+    small = 64 if args.workload != "c5" else 40
+    n = full if (host_memory_gb() > need_gb and not args.reference_sample) else small
+    cr, et, op, w, p, data, v, c, ro, ci, colors = cpu_problem(args.workload, n)
     vals = np.zeros(len(ci))
-    cores = best_thread_count(cr, fo, w, p, (mu, lam), v, c, ro, ci, vals, colors)
-    for _ in range(max(args.warmup, 1)):
+    cores = best_thread_count(cr, et, op, w, p, data, v, c, ro, ci, vals, colors)
+    for _ in range(max(min(args.warmup, 3), 1)):
         vals[:] = 0
-        cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, w, p, (mu, lam), v, c, ro, ci, values=vals, colors=colors, nthreads=cores)
-    t0 = time.perf_counter()
+        cr.assemble(et, op, w, p, data, v, c, ro, ci, values=vals, colors=colors, nthreads=cores)
+    times = []
     for _ in range(args.steps):
         vals[:] = 0
-        cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, w, p, (mu, lam), v, c, ro, ci, values=vals, colors=colors, nthreads=cores)
-    dt = (time.perf_counter() - t0) / args.steps
+        t0 = time.perf_counter()
+        cr.assemble(et, op, w, p, data, v, c, ro, ci, values=vals, colors=colors, nthreads=cores)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
     value = len(c) / dt
-    sample = f"Hex8 elasticity {n}^3 cube ({len(c)} elements) per step, coloured OpenMP assembly on {cores} threads"
+    name = "Tet4" if args.workload == "c5" else "Hex8"
+    sample = f"{name} elasticity {n}^3 cells ({len(c)} elements) per step, coloured OpenMP assembly on {cores} threads" + \
+             (" = the full workload" if n == full else f" (sample of the {full}^3 workload: host memory)")
     out = {
-        "impl": "reference", "metric": "elements/sec into global CSR (Hex8 3D linear elasticity, fp64)", "value": value, "unit": "elements/s",
+        "impl": "reference", "metric": f"elements/sec into global CSR ({name} 3D linear elasticity, fp64)", "value": value, "unit": "elements/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3: Hex8 linear elasticity, unit cube 126^3 (reference arm timed on a 64^3 sample of the same problem)",
+        "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, full), "reference_cells": n, "same_config": n == full,
                    "note": "C restatement of CsrParAssembler (fenris-paradis colouring); the Rust reference cannot be built here (no rustc/cargo)"},
         "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def workload_name(workload, cells):
+    if workload == "c5":
+        return f"C5: Tet4 linear elasticity, create_unit_box_uniform_tet_mesh_3d({cells}), one-point rule, Lame(E=1e6, nu=0.2), u=0"
+    return f"C3: Hex8 linear elasticity (fenris-solid), unit cube {cells}^3 cells per GPU, Gauss 2^3, Lame(E=1e6, nu=0.2), u=0"
+
+
+# ------------------------------------------------------------------------------------------------ parity (oracle = checker)
+def parity_c3(ctx, vals, cells, h, rank, world, data):
+    """Rows of whole node planes of this rank's matrix against the C oracle on the two cell layers around each plane: the interface
+    planes (completed by the exchange) and the middle plane of the slab.  K_e is translation invariant, so the sub-mesh may start at z = 0."""
+    from oracle import cpu_ref as cr
+    from oracle import fenris_oracle as fo
+    vx = cells + 1
+    plane = vx * vx
+    g0 = 1 if rank > 0 else 0                      # ghost cell layers below
+    nplanes = cells + 1 + g0 + (1 if rank < world - 1 else 0)
+    cnt1 = np.full(vx, 3)
+    cnt1[[0, -1]] = 2
+    cz = np.full(nplanes, 3)
+    cz[[0, -1]] = 2
+    blocks = (cz[:, None, None] * cnt1[None, :, None] * cnt1[None, None, :]).reshape(-1)  # coupled nodes per node, plane-major
+    row_start = np.concatenate([[0], np.cumsum(np.repeat(3 * blocks, 3))]).astype(np.int64)
+    assert int(row_start[-1]) == len(vals), "row layout of the structured slab"
+    sv, sc = cr.gen_hex_mesh(cells, cz=2, cell_size=h)
+    sro, sci = cr.pattern(3, len(sv), sc)
+    w, p = fo.hexahedron_gauss(2)
+    ref = cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, w, p, data, sv, sc, sro, sci)
+    rb, re = int(sro[3 * plane]), int(sro[3 * 2 * plane])
+    planes = [g0 + cells // 2]
+    if rank > 0:
+        planes.append(g0)
+    if rank < world - 1:
+        planes.append(g0 + cells)
+    worst, rows = 0.0, 0
+    for kp in planes:
+        b, e = int(row_start[3 * plane * kp]), int(row_start[3 * plane * (kp + 1)])
+        assert e - b == re - rb
+        worst = max(worst, float(np.linalg.norm(vals[b:e] - ref[rb:re]) / np.linalg.norm(ref[rb:re])))
+        rows += 3 * plane
+    return worst, rows
+
+
+def parity_sampled_rows(ctx, vals, et, gverts, gconn, part, data, rule, seed):
+    """Unstructured form (C5): sample nodes of this rank's owned elements (half of them on the partition interface when there is one),
+    gather every global element that touches them, assemble that sub-mesh with the C oracle and compare the sampled rows entrywise."""
+    from oracle import cpu_ref as cr
+    from oracle import fenris_oracle as fo
+    rng = np.random.default_rng(seed)
+    gids = part["global_nodes"].astype(np.int64)
+    owned_nodes = np.unique(part["connectivity"][:part["num_owned"]].astype(np.int64))
+    take = [rng.choice(owned_nodes, size=min(4000, len(owned_nodes)), replace=False)]
+    for _, ids in part["peers"]:
+        ids = ids.astype(np.int64)
+        take.append(rng.choice(ids, size=min(2000, len(ids)), replace=False))
+    sample_local = np.unique(np.concatenate(take))
+    sample_global = gids[sample_local]
+    mark = np.zeros(len(gverts), dtype=bool)
+    mark[sample_global] = True
+    hit = []
+    chunk = 1 << 22
+    for a in range(0, len(gconn), chunk):
+        hit.append(np.nonzero(mark[gconn[a:a + chunk].astype(np.int64)].any(axis=1))[0] + a)
+    elems = np.concatenate(hit)
+    sub = gconn[elems].astype(np.int64)
+    sg = np.unique(sub)
+    sconn = np.searchsorted(sg, sub).astype(np.uint64)
+    sverts = np.ascontiguousarray(gverts[sg])
+    sro, sci = cr.pattern(3, len(sverts), sconn)
+    ref = cr.assemble(et, fo.LINEAR_ELASTIC, rule[0], rule[1], data, sverts, sconn, sro, sci)
+    ro = ctx.row_offsets_download().astype(np.int64)
+    spos = np.searchsorted(sg, sample_global)
+    num = den = 0.0
+    for l, sp in zip(sample_local.tolist(), spos.tolist()):
+        b, e = int(ro[3 * l]), int(ro[3 * l + 3])
+        rb, re = int(sro[3 * sp]), int(sro[3 * sp + 3])
+        assert e - b == re - rb, "sampled row has a different length in the sub-mesh"
+        d = vals[b:e] - ref[rb:re]
+        num += float(d @ d)
+        den += float(ref[rb:re] @ ref[rb:re])
+    return float(np.sqrt(num / den)), 3 * len(sample_local)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -178,12 +289,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
     ap.add_argument("--scatter", default=os.environ.get("FB200_SCATTER", "atomic"), choices=list(MODE_NAMES))
-    ap.add_argument("--cells", type=int, default=CELLS, help="cells per edge per GPU (126 = BASELINE config C3)")
-    ap.add_argument("--exchange", default="peers", choices=["peers", "allreduce"],
-                    help="N > 1: interface rows by neighbour ncclSend/ncclRecv (default) or one world ncclAllReduce")
+    ap.add_argument("--cells", type=int, default=0, help="cells per edge (c3: per GPU, default 126; c5: of the whole box, default 161)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "peers", "allreduce"],
+                    help="N > 1: interface rows fused into the kernel over peer memory (default), neighbour ncclSend/ncclRecv, or one world ncclAllReduce")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--reference-sample", action="store_true", help="--impl reference: time the small sample even if the host could hold the full workload")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra JSON field)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -194,6 +308,7 @@ def main():
     import torch.distributed as dist
 
     import fenris_b200 as fb
+    from fenris_b200 import partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,32 +320,59 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    cells = args.cells
+    c5 = args.workload == "c5"
+    cells = args.cells or (C5_CELLS if c5 else CELLS)
     h = 1.0 / cells
     lame = fb.LameParameters.from_young_poisson(fb.YoungPoisson(YOUNG, POISSON))
-    w, p = fb.canonical_stiffness_quadrature(fb.HEX8)
+    et = fb.TET4 if c5 else fb.HEX8
+    n_el_nodes = 4 if c5 else 8
+    w, p = fb.canonical_stiffness_quadrature(et)
     data = (lame.mu, lame.lambda_)
     mode = MODE_NAMES[args.scatter]
 
     ctx = fb.Context(local_rank)
     t_setup = time.perf_counter()
-    if world == 1:
+    part = gverts = gconn = iface = None
+    if c5:
+        gmesh = fb.create_unit_box_uniform_tet_mesh_3d(cells)
+        gverts, gconn = gmesh.vertices(), gmesh.connectivity()
+        layer_starts = partition.tet_box_layer_starts(cells, cells, cells)
+        starts = layer_starts[partition.split_layers(cells, world)]
+        if world == 1:
+            part = {"vertices": gverts, "connectivity": gconn, "num_owned": len(gconn), "global_nodes": np.arange(len(gverts)), "peers": []}
+        else:
+            part = partition.element_range_partition(gverts, gconn, starts, rank)
+        verts, conn, n_owned = part["vertices"], part["connectivity"], part["num_owned"]
+        peers = part["peers"]
+    elif world == 1:
         mesh = fb.create_rectangular_uniform_hex_mesh(1.0, 1, 1, 1, cells)
-        verts, conn, n_owned, iface = mesh.vertices(), mesh.connectivity(), mesh.num_elements(), None
+        verts, conn, n_owned, peers = mesh.vertices(), mesh.connectivity(), mesh.num_elements(), []
     else:
-        verts, conn, n_owned, iface = slab_local_mesh(cells, cells, rank, world, h)
-    ctx.space_upload(fb.HEX8, verts, conn)
+        verts, conn, n_owned, iface = partition.structured_hex_slab(cells, cells, cells * world, h, rank, world)
+        peers = iface["peers"]
+    t_mesh = time.perf_counter() - t_setup
+    ctx.space_upload(et, verts, conn)
     ctx.set_num_owned_elements(n_owned)
     nrows, nnz = ctx.assemble_pattern(3)
-    ctx.color_nodes()
+    if mode == MODE_NAMES["colored"] or args.all_modes:
+        ctx.color_nodes()
+    exchange = args.exchange
     if world > 1:
         uid = [fb.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
-        if args.exchange == "peers":
-            ctx.interface_set_peers(iface["peers"])
-        else:
+        if exchange == "allreduce" and not c5:
             ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
+        else:
+            ctx.interface_set_peers(peers)
+            if exchange == "allreduce":
+                exchange = "peers"
+            if exchange == "p2p" and (c5 or mode != MODE_NAMES["atomic"] or not ctx.interface_enable_p2p()):
+                exchange = "peers"  # the fused exchange lives in the Hex8 tile kernel; everything else uses the packed neighbour exchange
+    # the first assembly builds the scatter lists of the kernel (tile / chunk lists): part of the set-up, like the pattern
+    ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode, accumulate=False)
+    if world > 1:
+        ctx.interface_allreduce()
     ctx.synchronize()
     setup_s = time.perf_counter() - t_setup
 
@@ -271,33 +413,59 @@ def main():
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = ctx.launch_count - launches0
     ms_per_step = ms_total / args.steps
-    total_owned = n_owned * world if world == 1 else None
+    total_owned = n_owned
     if world > 1:
         t = torch.tensor([n_owned], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         total_owned = int(t.item())
     value = total_owned / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (this rank's launch; algorithmic bytes of SURVEY 8d)
+    # ---- parity of what the timed steps left in HBM (every rank; max over ranks)
+    parity = None
+    vals_host = None
+    if not args.no_parity or not args.no_e2e:
+        vals_host = torch.empty(max(nnz, 1), dtype=torch.float64, pin_memory=True).numpy()
+    if not args.no_parity:
+        ctx.values_download(vals_host)
+        if c5:
+            from oracle import fenris_oracle as fo
+            err, rows = parity_sampled_rows(ctx, vals_host[:nnz], fo.TET4, gverts, gconn, part, data, (w, p), 17 + rank)
+        else:
+            err, rows = parity_c3(ctx, vals_host[:nnz], cells, h, rank, world, data)
+        if world > 1:
+            t = torch.tensor([err], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r = torch.tensor([rows], dtype=torch.int64, device="cuda")
+            dist.all_reduce(r)
+            err, rows = float(t.item()), int(r.item())
+        parity = {"rel_frobenius": err, "rows_checked": rows, "tolerance": 1e-12, "ok": bool(err < 1e-12),
+                  "against": "oracle/cpu_ref.c on the sub-mesh around the checked rows" +
+                             ("; interface planes + the middle plane of every rank's slab" if not c5 else "; sampled owned + interface nodes of every rank")}
+
+    # ---- roofline of the dominant kernel (this rank's launch; algorithmic bytes of SURVEY 8d): the step's assembly launch timed alone
     E_loc, N_loc = n_owned, verts.shape[0]
-    b_algo = algorithmic_bytes(8, 3, E_loc, N_loc, nnz)
-    kernel_ms = timed(args.steps, lambda: ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode,
-                                                                      accumulate=(mode != MODE_NAMES["gather"]))) / args.steps
+    b_algo = algorithmic_bytes(n_el_nodes, 3, E_loc, N_loc, nnz)
+    kernel_ms = timed(args.steps, lambda: ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode, accumulate=False)) / args.steps
+    if world > 1:
+        ctx.interface_allreduce()
     peak, peak_src = measured_peak_gbs()
     achieved = b_algo / (kernel_ms * 1e-3) / 1e9
+    kernel_name = {"atomic": ("assemble_tet4_chunk_kernel<LINEAR_ELASTIC>" if c5 else
+                              "assemble_hex8_tile_kernel<LINEAR_ELASTIC> (owner stores: the overwriting launch of the step, no zero-fill pass)"
+                              if os.environ.get("FB200_HEX8_TILE", "64") != "0" else "assemble_hex8_mma_kernel<LINEAR_ELASTIC, ATOMIC>"),
+                   "colored": "element kernel, COLORED, one launch per colour",
+                   "gather": "assemble_gather_kernel"}[args.scatter]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.scatter)
+            traffic = json.load(open(tp)).get(f"{args.workload}:{args.scatter}")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"atomic": "assemble_hex8_tile_kernel<LINEAR_ELASTIC> (accumulate launch: every CSR value read-modify-written)"
-                           if os.environ.get("FB200_HEX8_TILE", "64") != "0" else "assemble_hex8_mma_kernel<LINEAR_ELASTIC, ATOMIC>",
-                           "colored": "assemble_hex8_mma_kernel<LINEAR_ELASTIC, COLORED> x colours",
-                           "gather": "assemble_gather_kernel"}[args.scatter],
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": b_algo, "bytes_per_element": b_algo / max(E_loc, 1), "peak_source": peak_src}
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": b_algo,
+                "bytes_per_element": b_algo / max(E_loc, 1), "peak_source": peak_src,
+                "frac_of_step": (b_algo / (ms_per_step * 1e-3) / 1e9) / peak}
 
     other = None
     if args.all_modes:
@@ -307,58 +475,57 @@ def main():
                 step(m)
             other[name] = total_owned / (timed(max(args.steps // 2, 3), lambda m=m: step(m)) / max(args.steps // 2, 3) * 1e-3)
 
-    # ---- end to end through the host-buffer C-ABI call: H2D of the vertex coordinates + D2H of the CSR values every step
+    # ---- end to end through the host-buffer path: H2D of the vertex coordinates + D2H of the CSR values every step
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 5))
-        vals_host = torch.empty(max(nnz, 1), dtype=torch.float64, pin_memory=True).numpy()
         verts_host = torch.from_numpy(np.ascontiguousarray(verts)).pin_memory().numpy()
 
         def e2e_step():
             ctx.space_update_vertices(verts_host)
-            ctx.assemble_into_csr(fb.LINEAR_ELASTIC, w, p, data, vals_host, scatter_mode=mode, accumulate=False)
-            if world > 1:
+            if world == 1:
+                ctx.assemble_into_csr(fb.LINEAR_ELASTIC, w, p, data, vals_host, scatter_mode=mode, accumulate=False)
+            else:  # the host must receive the COMPLETED rows: exchange before the download
+                ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode, accumulate=False)
                 ctx.interface_allreduce()
+                ctx.values_download(vals_host)
 
         e2e_step()
         ms = timed(e2e_steps, e2e_step) / e2e_steps
         e2e = {"value": total_owned / (ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(verts_host.nbytes), "d2h_bytes_per_step": int(nnz * 8),
                "ms_per_step": ms, "steps": e2e_steps}
-        del vals_host
+    del vals_host
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import cpu_ref as cr
-        from oracle import fenris_oracle as fo
-        n = SAMPLE_CELLS
-        sv, sc = cr.gen_hex_mesh(n)
-        sro, sci = cr.pattern(3, len(sv), sc)
-        colors = cr.color_greedy(sc, len(sv))
-        sw, sp_ = fo.hexahedron_gauss(2)
+        n = 40 if c5 else SAMPLE_CELLS
+        cr, oet, oop, sw, sp_, sdata, sv, sc, sro, sci, colors = cpu_problem(args.workload, n)
         vals = np.zeros(len(sci))
-        cores = best_thread_count(cr, fo, sw, sp_, data, sv, sc, sro, sci, vals, colors)
-        cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, sw, sp_, data, sv, sc, sro, sci, values=vals, colors=colors, nthreads=cores)
+        cores = best_thread_count(cr, oet, oop, sw, sp_, sdata, sv, sc, sro, sci, vals, colors)
+        cr.assemble(oet, oop, sw, sp_, sdata, sv, sc, sro, sci, values=vals, colors=colors, nthreads=cores)
         reps, t0 = 0, time.perf_counter()
         while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 200):
             vals[:] = 0
-            cr.assemble(fo.HEX8, fo.LINEAR_ELASTIC, sw, sp_, data, sv, sc, sro, sci, values=vals, colors=colors, nthreads=cores)
+            cr.assemble(oet, oop, sw, sp_, sdata, sv, sc, sro, sci, values=vals, colors=colors, nthreads=cores)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
         cpu = {"value": len(sc) / dt, "unit": "elements/s", "cores": cores, "kind": "port",
-               "sample": f"Hex8 elasticity {n}^3 cube ({len(sc)} elements) x {reps} reps, coloured OpenMP C restatement of CsrParAssembler"}
+               "sample": f"{'Tet4' if c5 else 'Hex8'} elasticity {n}^3 cells ({len(sc)} elements) x {reps} reps, coloured OpenMP C restatement of CsrParAssembler"}
 
     if rank == 0:
+        exch = {"p2p": "fused into the tile kernel's flush over NVLink peer memory (red.global.add.f64 on the neighbour's rows) + neighbour barrier",
+                "peers": "neighbour ncclSend/ncclRecv of the packed rows, summed on arrival", "allreduce": "world ncclAllReduce"}[exchange]
         out = {
-            "metric": "elements/sec into global CSR (Hex8 3D linear elasticity, fp64)", "value": value, "unit": "elements/s",
+            "metric": f"elements/sec into global CSR ({'Tet4' if c5 else 'Hex8'} 3D linear elasticity, fp64)", "value": value, "unit": "elements/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3: Hex8 linear elasticity (fenris-solid), unit cube {cells}^3 cells per GPU, Gauss 2^3, Lame(E=1e6, nu=0.2), u=0",
-                       "elements_per_gpu": int(n_owned), "nnz_per_gpu": int(nnz), "scatter": args.scatter,
-                       "parallelism": "1 GPU" if world == 1 else f"z-slab element partition x{world}, interface rows: " +
-                                      ("neighbour ncclSend/ncclRecv, summed on arrival" if args.exchange == "peers" else "world ncclAllReduce"),
-                       "l2": "inputs+outputs >> L2 (values 3.9 GB per GPU); no L2 flush needed", "setup_s": setup_s},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "scaling": "strong" if c5 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, cells),
+                       "elements_total": int(total_owned), "elements_rank0": int(n_owned), "nnz_rank0": int(nnz), "scatter": args.scatter,
+                       "parallelism": "1 GPU" if world == 1 else f"z-slab element partition x{world}, interface rows: {exch}",
+                       "exchange": exchange if world > 1 else None,
+                       "l2": "inputs+outputs >> L2 (values 3.9 - 9 GB per GPU); no L2 flush needed", "setup_s": setup_s, "mesh_s": t_mesh},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
         if other:
             out["other_modes_elements_per_s"] = other

@@ -107,6 +107,12 @@ class Context:
         self._check(self._lib.fb200_pattern_download(self._h, nat.ptr(ro), nat.ptr(ci)))
         return ro, ci[: self.nnz]
 
+    def row_offsets_download(self) -> np.ndarray:
+        """Only the row offsets of the CSR pattern (the column indices of C3 - C5 are 4 - 9 GB as u64)."""
+        ro = np.zeros(self.nrows + 1, dtype=np.uint64)
+        self._check(self._lib.fb200_pattern_download(self._h, nat.ptr(ro), None))
+        return ro
+
     def pattern_adopt(self, solution_dim: int, row_offsets: np.ndarray, col_indices: np.ndarray):
         ro, ci = nat.as_u64(row_offsets), nat.as_u64(col_indices)
         if ci.size == 0:
