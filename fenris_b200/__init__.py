@@ -12,5 +12,5 @@ from .api import (CompactQuadratureTable, CsrAssembler, CsrMatrix, CsrParAssembl
                   LinearElasticMaterial, MaterialEllipticOperator, Mesh, NeoHookeanMaterial, StVKMaterial, SparsityPattern, UniformQuadratureTable, VectorAssembler, VectorParAssembler, YoungPoisson,
                   apply_homogeneous_dirichlet_bc_csr, apply_homogeneous_dirichlet_bc_rhs, assemble_scalar, canonical_stiffness_quadrature, color_nodes, create_rectangular_uniform_hex_mesh,
                   create_rectangular_uniform_tet_mesh, create_unit_box_uniform_hex_mesh_3d, create_unit_box_uniform_tet_mesh_3d,
-                  create_unit_square_uniform_quad_mesh_2d, hex20_mesh_from, hex27_mesh_from)
+                  create_unit_square_uniform_quad_mesh_2d, hex20_mesh_from, hex27_mesh_from, tet10_mesh_from)
 from .context import Context  # noqa: F401

@@ -97,6 +97,7 @@ def lib():
         "fb200_values_download": (i32, [vp, vp]),
         "fb200_values_upload": (i32, [vp, vp]),
         "fb200_element_matrices": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), u64, u64, vp]),
+        "fb200_element_matrices_u": (i32, [vp, C.POINTER(Operator), C.POINTER(Quadrature), vp, u64, u64, vp]),
         "fb200_assemble_mass_into_csr_device": (i32, [vp, C.POINTER(Quadrature), i32, i32]),
         "fb200_assemble_mass_into_csr": (i32, [vp, C.POINTER(Quadrature), i32, i32, vp]),
         "fb200_assemble_vector": (i32, [vp, C.POINTER(Quadrature), i32, vp, i32, i32, i32, vp]),
@@ -119,6 +120,7 @@ def lib():
         "fb200_gen_quad_mesh": (i32, [u64, u64, dbl, pu64, pu64, vp, vp]),
         "fb200_hex27_from_hex8": (i32, [u64, vp, u64, vp, pu64, vp, vp]),
         "fb200_hex20_from_hex8": (i32, [u64, vp, u64, vp, pu64, vp, vp]),
+        "fb200_tet10_from_tet4": (i32, [u64, vp, u64, vp, pu64, vp, vp]),
         "fb200_canonical_quadrature": (i32, [i32, pi32, vp, vp]),
         "fb200_lame_from_young_poisson": (None, [dbl, dbl, pdbl, pdbl]),
         "fb200_tile_lists_selftest": (i32, [u64, vp, u64, vp, u64, pu64, pi32]),

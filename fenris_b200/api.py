@@ -152,6 +152,23 @@ def hex20_mesh_from(hex8_mesh: Mesh) -> Mesh:
     return Mesh(v20, c20, nat.HEX20)
 
 
+def tet10_mesh_from(tet4_mesh: Mesh) -> Mesh:
+    """Tet10Mesh::from(&tet4_mesh), src/mesh_convert.rs:42-83,444-452"""
+    assert tet4_mesh.element_type == nat.TET4
+    L = nat.lib()
+    v, c = tet4_mesh.vertices_, tet4_mesh.connectivity_
+    n10 = C.c_uint64(0)
+    st = L.fb200_tet10_from_tet4(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n10), None, None)
+    if st != nat.OK:
+        raise Fb200Error(st, "tet10 conversion failed")
+    v10 = np.zeros((n10.value, 3))
+    c10 = np.zeros((len(c), 10), dtype=np.uint64)
+    st = L.fb200_tet10_from_tet4(len(v), nat.ptr(v), len(c), nat.ptr(c), C.byref(n10), nat.ptr(v10), nat.ptr(c10))
+    if st != nat.OK:
+        raise Fb200Error(st, "tet10 conversion failed")
+    return Mesh(v10, c10, nat.TET10)
+
+
 # ----------------------------------------------------------------------------- quadrature tables / operators
 def canonical_stiffness_quadrature(element_type: int):
     """(weights, points) of the element's CanonicalStiffnessQuadrature, src/quadrature/canonical.rs:95-112"""
@@ -364,7 +381,8 @@ class ElementEllipticAssembler:
         try:
             ctx.space_upload(self.space.element_type, self.space.vertices_, self.space.connectivity_)
             dofs = self.solution_dim() * _NODES[self.space.element_type]
-            return ctx.element_matrices(self.op.kind, self.qtable.weights, self.qtable.points, self._data(), element_index, 1, dofs)[0]
+            return ctx.element_matrices(self.op.kind, self.qtable.weights, self.qtable.points, self._data(), element_index, 1, dofs,
+                                        u=getattr(self, "u", None))[0]
         finally:
             if own:
                 ctx.close()

@@ -316,10 +316,12 @@ class Context:
         self._check(self._lib.fb200_values_device(self._h, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
-    def element_matrices(self, op_kind: int, weights, points, data, first: int, count: int, dofs: int) -> np.ndarray:
+    def element_matrices(self, op_kind: int, weights, points, data, first: int, count: int, dofs: int, u=None) -> np.ndarray:
+        """Dense K_e of elements [first, first + count); u = the state for StVK / NeoHookean (None = zeros), ignored by linear operators."""
         op, q = self._structs(op_kind, weights, points, data)
         out = np.zeros((max(count, 1), dofs, dofs))
-        self._check(self._lib.fb200_element_matrices(self._h, C.byref(op), C.byref(q), first, count, nat.ptr(out)))
+        uv = None if u is None else nat.as_f64(u)
+        self._check(self._lib.fb200_element_matrices_u(self._h, C.byref(op), C.byref(q), None if uv is None else nat.ptr(uv), first, count, nat.ptr(out)))
         # column-major per element -> numpy [e][row][col]
         return np.transpose(out[:count], (0, 2, 1)).copy()
 

@@ -74,10 +74,7 @@ struct AssembleParams {
     // chunk-local scatter lists (chunks.cpp); num_chunks above
     const int64_t* slot_off;
     const uint16_t* contrib;
-    const int32_t* slot_node;
-    const uint16_t* slot_k;
-    const uint16_t* slot_cbeg;
-    const uint8_t* slot_flags;
+    const uint64_t* slot_rec;    // 4 words per slot (HostChunks::slot_rec)
     // tile lists of the Hex8 tile kernel (tiles.cpp)
     uint32_t num_tiles;
     const uint32_t* tile_hdr;
@@ -704,10 +701,7 @@ static fb200_status launch_hex8_mma(fb200_ctx* ctx, AssembleParams& p) {
 static void free_chunks(ChunkLists& cl) {
     dev_free(cl.d_slot_off);
     dev_free(cl.d_contrib);
-    dev_free(cl.d_slot_node);
-    dev_free(cl.d_slot_k);
-    dev_free(cl.d_slot_cbeg);
-    dev_free(cl.d_slot_flags);
+    dev_free(cl.d_slot_rec);
     dev_free(cl.d_conn_pos);
     cl.valid = false;
     cl.count = 0;
@@ -723,7 +717,7 @@ static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T>& h) {
 
 static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t count, int chunk_elems) {
     ChunkLists& cl = ctx->chunks;
-    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems) return FB200_OK;
+    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems && cl.sdim == ctx->sdim) return FB200_OK;
     free_chunks(cl);
     const int n = ctx->ei.n;
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -735,15 +729,13 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
     FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     HostChunks hc;
-    build_chunk_lists(n, count, chunk_elems, ids.data(), conn.data(), ctx->N, blk_off.data(), map.data(), hc);
+    build_chunk_lists(n, ctx->sdim, count, chunk_elems, ids.data(), conn.data(), ctx->N, blk_off.data(), map.data(), hc);
     cl.num_chunks = (uint32_t)(hc.slot_off.size() - 1);
-    cl.total_slots = hc.slot_node.size();
+    cl.total_slots = hc.slot_rec.size() / 4;
+    cl.sdim = ctx->sdim;
     FB200_TRY(upload_vec(ctx, &cl.d_slot_off, hc.slot_off));
     FB200_TRY(upload_vec(ctx, &cl.d_contrib, hc.contrib));
-    FB200_TRY(upload_vec(ctx, &cl.d_slot_node, hc.slot_node));
-    FB200_TRY(upload_vec(ctx, &cl.d_slot_k, hc.slot_k));
-    FB200_TRY(upload_vec(ctx, &cl.d_slot_cbeg, hc.slot_cbeg));
-    FB200_TRY(upload_vec(ctx, &cl.d_slot_flags, hc.slot_flags));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_rec, hc.slot_rec));
     FB200_TRY(dev_alloc(ctx, &cl.d_conn_pos, count * n));
     if (count) {
         const int blocks = (int)std::min<uint64_t>(div_up(count * n, 256), (uint64_t)ctx->sm_count * 16);
@@ -769,10 +761,7 @@ static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
     p.num_chunks = cl.num_chunks;
     p.slot_off = cl.d_slot_off;
     p.contrib = cl.d_contrib;
-    p.slot_node = cl.d_slot_node;
-    p.slot_k = cl.d_slot_k;
-    p.slot_cbeg = cl.d_slot_cbeg;
-    p.slot_flags = cl.d_slot_flags;
+    p.slot_rec = cl.d_slot_rec;
     const size_t smem = sizeof(double) * 12 * C;
     auto kernel = assemble_tet4_chunk_kernel<OP, T, C>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1348,29 +1337,45 @@ fb200_status fb200_values_upload(fb200_ctx* ctx, const double* values) {
 
 fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, uint64_t first, uint64_t count,
                                     double* out) {
-    FB200_TRY(validate(ctx, op, q));
+    return fb200_element_matrices_u(ctx, op, q, nullptr, first, count, out);
+}
+
+fb200_status fb200_element_matrices_u(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, uint64_t first,
+                                      uint64_t count, double* out) {
+    const bool nonlinear = ctx && op && (op->kind == FB200_STVK || op->kind == FB200_NEO_HOOKEAN);
+    if (!nonlinear) FB200_TRY(validate(ctx, op, q));
+    if (!ctx) return FB200_ERR_STATE;
+    if (nonlinear && (!ctx->has_space || ctx->ragged)) return fail(ctx, FB200_ERR_STATE, "element matrices need a space (fb200_space_upload)");
     if (first + count > ctx->E) return fail(ctx, FB200_ERR_SHAPE, "element range out of bounds");
     if (count == 0) return FB200_OK;
     if (!out) return fail(ctx, FB200_ERR_SHAPE, "null output");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
-    FB200_TRY(upload_tables(ctx, op, q));
     const int s = op->kind == FB200_LAPLACE ? 1 : ctx->ei.d;
     const uint64_t per = (uint64_t)(s * ctx->ei.n) * (uint64_t)(s * ctx->ei.n);
     double* d_out = nullptr;
     int32_t* d_list = nullptr;
     FB200_TRY(dev_alloc(ctx, &d_out, per * count));
-    fb200_status st = dev_alloc(ctx, &d_list, count);
-    if (st == FB200_OK) {
-        std::vector<int32_t> list(count);
-        for (uint64_t k = 0; k < count; ++k) list[k] = (int32_t)(first + k);
-        h2d_copy(ctx, d_list, list.data(), count * sizeof(int32_t));
-        AssembleParams p;
-        fill_params(ctx, p);
-        p.elem_list = d_list;
-        p.count = count;
-        p.dump = d_out;
-        p.dump_first = first;
-        st = dispatch(ctx, p, op->kind, MODE_DUMP);
+    fb200_status st = FB200_OK;
+    if (nonlinear) {
+        // K_e depends on the state: the tangent of StVK / NeoHookean at u (materials.rs:232-469), dense from the pair kernel of mass_source.cu
+        cudaError_t e = cudaMemsetAsync(d_out, 0, per * count * sizeof(double), ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "memset element matrices");
+        if (st == FB200_OK) st = element_matrices_state_dependent(ctx, op, q, u, first, count, d_out);
+    } else {
+        st = upload_tables(ctx, op, q);
+        if (st == FB200_OK) st = dev_alloc(ctx, &d_list, count);
+        if (st == FB200_OK) {
+            std::vector<int32_t> list(count);
+            for (uint64_t k = 0; k < count; ++k) list[k] = (int32_t)(first + k);
+            h2d_copy(ctx, d_list, list.data(), count * sizeof(int32_t));
+            AssembleParams p;
+            fill_params(ctx, p);
+            p.elem_list = d_list;
+            p.count = count;
+            p.dump = d_out;
+            p.dump_first = first;
+            st = dispatch(ctx, p, op->kind, MODE_DUMP);
+        }
     }
     if (st == FB200_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_out, per * count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

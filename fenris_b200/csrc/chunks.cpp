@@ -9,9 +9,10 @@
 //
 // Per chunk c (positions [c C, min((c+1) C, count))):
 //   contrib[c C n^2 + t], t < ne n^2 : contributor tags  e_local n^2 + a n + b, grouped by slot, elements ascending inside a slot
-//   slots slot_off[c] .. slot_off[c+1]: node (row node I), k (position of the column node in I's block row), cbeg (first contributor,
-//   relative to the chunk), flags (bit 0: row node complete in this chunk); slots are ordered by contributor count, largest first,
-//   so that the threads of a warp (one slot each) run loops of equal length.
+//   slots slot_off[c] .. slot_off[c+1]: one 32-byte record each (HostChunks::slot_rec): where the block's values start and how long the rows
+//   are, the first contributor (relative to the chunk) and the contributor count, whether the row node is complete in this chunk, and the
+//   first 8 contributor tags themselves (most slots have fewer: the kernel's slot loop then touches no other list).  Slots are ordered by
+//   contributor count, largest first, so that the threads of a warp (one slot each) run loops of equal length.
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -20,7 +21,7 @@
 
 namespace fb200 {
 
-void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
+void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
                        const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out) {
     const int n2 = n * n;
     const uint64_t num_chunks = (count + chunk_elems - 1) / chunk_elems;
@@ -31,9 +32,7 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
         for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
     }
     struct Slot {
-        int32_t node;
-        uint16_t k, cbeg;
-        uint8_t flags;
+        uint64_t w[4];
     };
     std::vector<std::vector<Slot>> chunk_slots(num_chunks);
     out.contrib.assign(count * (uint64_t)n2, 0);
@@ -97,8 +96,18 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
             std::vector<Slot>& slots = chunk_slots[c];
             slots.reserve(raw.size());
             for (const Raw& r : raw) {
-                slots.push_back({r.node, (uint16_t)(r.key - (uint64_t)blk_off[r.node]), (uint16_t)tags.size(), (uint8_t)(complete(r.node) ? 1 : 0)});
-                for (uint32_t t = 0; t < r.cnt; ++t) tags.push_back((uint16_t)(pairs[r.begin + t] & 0xffffu));
+                const uint64_t k = r.key - (uint64_t)blk_off[r.node];
+                const uint64_t rl = (uint64_t)(blk_off[r.node + 1] - blk_off[r.node]) * (uint64_t)sdim;
+                Slot sl;
+                sl.w[0] = ((uint64_t)(sdim * sdim) * (uint64_t)blk_off[r.node] + (uint64_t)sdim * k) | (complete(r.node) ? 1ull << 62 : 0ull);
+                sl.w[1] = rl | ((uint64_t)tags.size() << 32) | ((uint64_t)r.cnt << 48);
+                sl.w[2] = sl.w[3] = ~0ull;
+                for (uint32_t t = 0; t < r.cnt; ++t) {
+                    const uint16_t tag = (uint16_t)(pairs[r.begin + t] & 0xffffu);
+                    if (t < 8) sl.w[2 + t / 4] = (sl.w[2 + t / 4] & ~(0xffffull << (16 * (t & 3)))) | ((uint64_t)tag << (16 * (t & 3)));
+                    tags.push_back(tag);
+                }
+                slots.push_back(sl);
             }
             std::copy(tags.begin(), tags.end(), out.contrib.begin() + p0 * (uint64_t)n2);
         }
@@ -113,17 +122,11 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
     out.slot_off.assign(num_chunks + 1, 0);
     for (uint64_t c = 0; c < num_chunks; ++c) out.slot_off[c + 1] = out.slot_off[c] + (int64_t)chunk_slots[c].size();
     const uint64_t total = (uint64_t)out.slot_off[num_chunks];
-    out.slot_node.resize(total);
-    out.slot_k.resize(total);
-    out.slot_cbeg.resize(total);
-    out.slot_flags.resize(total);
+    out.slot_rec.resize(total * 4);
     for (uint64_t c = 0; c < num_chunks; ++c) {
         uint64_t o = (uint64_t)out.slot_off[c];
-        for (const Slot& s : chunk_slots[c]) {
-            out.slot_node[o] = s.node;
-            out.slot_k[o] = s.k;
-            out.slot_cbeg[o] = s.cbeg;
-            out.slot_flags[o] = s.flags;
+        for (const Slot& sl : chunk_slots[c]) {
+            std::copy(sl.w, sl.w + 4, out.slot_rec.begin() + 4 * o);
             ++o;
         }
     }

@@ -51,18 +51,20 @@ struct OrderedCopy {
 struct HostChunks {
     std::vector<int64_t> slot_off;     // num_chunks + 1
     std::vector<uint16_t> contrib;     // count * n^2, chunk c starts at c * chunk_elems * n^2
-    std::vector<int32_t> slot_node;
-    std::vector<uint16_t> slot_k, slot_cbeg;
-    std::vector<uint8_t> slot_flags;
+    // per slot 4 words: [0] index of the block's first value (s^2 blk_off[node] + s k) | complete-row flag << 62,
+    // [1] row length in doubles | first contributor (relative to the chunk) << 32 | contributor count << 48, [2..3] the first 8 contributor tags
+    // (0xffff = none): one 32-byte record per slot - no dependent loads in the kernel's slot loop
+    std::vector<uint64_t> slot_rec;
 };
-void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
+void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
                        const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
 constexpr uint32_t kTileZeroPos = 0x7ffu;  // accumulator position of a flush word that writes 0.0 (owner rows, see below)
 // header of a tile: 0 first schedule position, 1 rounds, 2 n_nodes, 3 n_slots (P), 4 node_begin, 5 flush_begin, 6 n_flush, 7 n_elems,
-// 8 n_store (leading flush entries that are plain stores when the call overwrites), 9 wait_begin, 10 n_wait, 11 flags, 12-15 reserved
+// 8 n_store (leading flush entries that are plain stores when the call overwrites), 9 wait_begin, 10 n_wait, 11 flags,
+// 12 n_publish (leading STORE entries = the shared rows this tile owns; its flag is published after them), 13-15 reserved
 constexpr int kTileHdrWords = 16;
 struct TileShape {
     int tile_bits;    // low Morton bits dropped to name a tile (5: 4 x 4 x 2 elements, 6: 4 x 4 x 4)
@@ -125,10 +127,8 @@ struct ChunkLists {
     uint64_t total_slots = 0;
     int64_t* d_slot_off = nullptr;
     uint16_t* d_contrib = nullptr;
-    int32_t* d_slot_node = nullptr;
-    uint16_t* d_slot_k = nullptr;
-    uint16_t* d_slot_cbeg = nullptr;
-    uint8_t* d_slot_flags = nullptr;
+    uint64_t* d_slot_rec = nullptr;
+    int sdim = 0;
     int32_t* d_conn_pos = nullptr;  // connectivity rows in processing order
 };
 
@@ -320,6 +320,8 @@ fb200_status group_elements_by_rule(fb200_ctx* ctx, uint32_t num_rules, const ui
 // mass_source.cu: CSR assembly of a state-dependent operator (FB200_STVK) at the host vector u (NULL = zeros)
 fb200_status assemble_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, int scatter_mode,
                                       int accumulate);
+fb200_status element_matrices_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u, uint64_t first,
+                                              uint64_t count, double* d_out);
 fb200_status assemble_state_dependent_list(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
                                            const int32_t* d_list, uint64_t count, int plain);
 

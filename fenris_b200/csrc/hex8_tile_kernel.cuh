@@ -294,44 +294,59 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                         eb = en;
                     }
                 };
-                if (!overwrite) {
-                    flush_range(0u, items, std::false_type{});
-                } else {
-                    flush_range(0u, store_items, std::true_type{});
-                    if (epoch) {
-                        // publish this tile's stores, then wait for the owners of the rows the REDUCE segment adds to
-                        // (measurement knobs, results wrong: 8 no publish / no wait, 16 no wait, 32 publish without the barrier)
+                // STORE segment (nothing of it when the call accumulates): with ownership first the shared rows this tile owns; publish
+                // them (barrier: every helper has issued its stores; release store: they are visible before the flag); then the complete
+                // rows - while the owners this tile depends on publish theirs - and only then the reductions into other tiles' rows
+                // (measurement knobs, results wrong: 8 no publish / no wait, 16 no wait, 32 publish without the barrier)
+                const uint32_t n_store = overwrite ? store_items : 0u, n_pub = epoch ? ph[12] : 0u;
+                const uint32_t nwait = (!epoch || (dbg & 24)) ? 0u : ph[10];
+                const uint32_t* wl = p.tile_wait + ph[9];
+                const uint32_t* fp = nullptr;
+                uint32_t seen = epoch;
+#pragma unroll 1
+                for (int part = 0; part < 2; ++part) {
+                    flush_range(part ? n_pub : 0u, part ? n_store : n_pub, std::true_type{});
+                    if (part == 0 && epoch) {
                         if (!(dbg & 32)) named_barrier(BAR_HELPER, TH);
                         if (ht == 0 && !(dbg & 8)) st_release_u32(p.tile_flag + s_tick[(it - 1) & 7u], epoch);
-                        const uint32_t nwait = (dbg & 24) ? 0u : ph[10];
-                        if (nwait) {
-                            const uint32_t* wl = p.tile_wait + ph[9];
-                            for (uint32_t w = (uint32_t)ht; w < nwait; w += (uint32_t)TH) {
-                                const uint32_t* fp = p.tile_flag + wl[w];
-                                unsigned int spins = 0;
-                                while (ld_acquire_u32(fp) != epoch) {
-                                    __nanosleep(64);
-                                    if (++spins > (1u << 24)) {  // > 1 s: never on a healthy launch; report instead of hanging
-                                        flag_error(p.errword, (uint64_t)s_tick[(it - 1) & 7u], FB200_ERR_CUDA);
-                                        break;
-                                    }
-                                }
-                                if ((dbg & 64) && spins) {  // diagnostics: blocked waits, their spins, how far back the owner tile is
-                                    unsigned long long* dc = reinterpret_cast<unsigned long long*>(p.ticket32) + 2;
-                                    const unsigned long long dist = s_tick[(it - 1) & 7u] - wl[w];
-                                    atomicAdd(dc + 0, 1ull);
-                                    atomicAdd(dc + 1, (unsigned long long)spins);
-                                    atomicMax(dc + 2, (unsigned long long)spins);
-                                    atomicAdd(dc + 3, dist);
-                                    atomicMax(dc + 4, dist);
-                                    atomicAdd(dc + (dist < 8 ? 5 : dist < 64 ? 6 : dist < 512 ? 7 : 8), 1ull);
-                                    atomicAdd(dc + (dist < 8 ? 9 : dist < 64 ? 10 : dist < 512 ? 11 : 12), (unsigned long long)spins);
-                                }
-                            }
-                            named_barrier(BAR_HELPER, TH);
+                        // first poll before the complete rows (its latency hides behind them); lanes beyond the list poll nothing
+                        if ((uint32_t)ht < nwait) {
+                            fp = p.tile_flag + __ldg(wl + ht);
+                            seen = ld_acquire_u32(fp);
                         }
                     }
-                    flush_range(store_items, items, std::false_type{});
+                }
+                {
+                    if (nwait) {
+                        for (uint32_t w = (uint32_t)ht; w < nwait; w += (uint32_t)TH) {
+                            if (w != (uint32_t)ht) {
+                                fp = p.tile_flag + wl[w];
+                                seen = ld_acquire_u32(fp);
+                            }
+                            unsigned int spins = 0;
+                            while (seen != epoch) {
+                                __nanosleep(32);
+                                seen = ld_acquire_u32(fp);
+                                if (++spins > (1u << 24)) {  // > 1 s: never on a healthy launch; report instead of hanging
+                                    flag_error(p.errword, (uint64_t)s_tick[(it - 1) & 7u], FB200_ERR_CUDA);
+                                    break;
+                                }
+                            }
+                            if ((dbg & 64) && spins) {  // diagnostics: blocked waits, their spins, how far back the owner tile is
+                                unsigned long long* dc = reinterpret_cast<unsigned long long*>(p.ticket32) + 2;
+                                const unsigned long long dist = s_tick[(it - 1) & 7u] - wl[w];
+                                atomicAdd(dc + 0, 1ull);
+                                atomicAdd(dc + 1, (unsigned long long)spins);
+                                atomicMax(dc + 2, (unsigned long long)spins);
+                                atomicAdd(dc + 3, dist);
+                                atomicMax(dc + 4, dist);
+                                atomicAdd(dc + (dist < 8 ? 5 : dist < 64 ? 6 : dist < 512 ? 7 : 8), 1ull);
+                                atomicAdd(dc + (dist < 8 ? 9 : dist < 64 ? 10 : dist < 512 ? 11 : 12), (unsigned long long)spins);
+                            }
+                        }
+                        named_barrier(BAR_HELPER, TH);
+                    }
+                    flush_range(n_store, items, std::false_type{});
                 }
             }
             tables_done();  // the stages have landed, and every helper has read its accumulators

@@ -502,6 +502,50 @@ static fb200_status hex_refine(int nodes_out, uint64_t nv, const double* v, uint
     return FB200_OK;
 }
 
+// ---------------------------------------------------------------- Tet4 -> Tet10 (src/mesh_convert.rs:42-83, 227-330, 444-452)
+// The 4 vertices, then the midpoints of the edges (0,1) (1,2) (0,2) (0,3) (2,3) (1,3); global labels in first-seen order keyed by the
+// sorted parent set, midpoints = lerp(a, b, 0.5) = 0.5 b + 0.5 a exactly as nalgebra evaluates it.
+fb200_status fb200_tet10_from_tet4(uint64_t nv, const double* v, uint64_t ne, const uint64_t* tet4, uint64_t* nv10, double* v10,
+                                   uint64_t* tet10) {
+    static const int edges[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {2, 3}, {1, 3}};
+    if (!v || !tet4) return FB200_ERR_SHAPE;
+    std::map<std::pair<uint64_t, uint64_t>, uint64_t> label;  // (min parent, max parent | ~0 for a vertex) -> new id
+    const bool write = v10 != nullptr && tet10 != nullptr;
+    for (uint64_t e = 0; e < ne; ++e) {
+        const uint64_t* g = tet4 + 4 * e;
+        for (int a = 0; a < 4; ++a)
+            if (g[a] >= nv) return FB200_ERR_INDEX_OOB;
+        for (int l = 0; l < 10; ++l) {
+            std::pair<uint64_t, uint64_t> key;
+            double pos[3];
+            if (l < 4) {
+                key = {g[l], ~0ull};
+                for (int i = 0; i < 3; ++i) pos[i] = v[3 * g[l] + i];
+            } else {
+                const uint64_t a = g[edges[l - 4][0]], b = g[edges[l - 4][1]];
+                key = {std::min(a, b), std::max(a, b)};
+                for (int i = 0; i < 3; ++i) pos[i] = 0.5 * v[3 * b + i] + 0.5 * v[3 * a + i];
+            }
+            auto it = label.find(key);
+            uint64_t id;
+            if (it == label.end()) {
+                id = label.size();
+                label.emplace(key, id);
+                if (write) {
+                    v10[3 * id] = pos[0];
+                    v10[3 * id + 1] = pos[1];
+                    v10[3 * id + 2] = pos[2];
+                }
+            } else {
+                id = it->second;
+            }
+            if (write) tet10[10 * e + l] = id;
+        }
+    }
+    if (nv10) *nv10 = label.size();
+    return FB200_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------- greedy colouring (fenris-paradis/src/coloring.rs:6-70)

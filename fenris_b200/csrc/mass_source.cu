@@ -45,6 +45,10 @@ struct MsParams {
     const int32_t* forced_list;
     uint64_t forced_count;
     int forced;
+    // WHAT 5 only: dense element matrices instead of the CSR scatter (fb200_element_matrices_u): element first_elem + k -> dump + k (s n)^2,
+    // column-major per element; no pattern needed
+    double* dump;
+    uint64_t first_elem;
 };
 
 template <int d>
@@ -135,11 +139,11 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
     double* w_A = w_u + n * s;
     __syncthreads();
     for (uint64_t k = (uint64_t)blockIdx.x * warps + warp; k < p.count; k += (uint64_t)gridDim.x * warps) {
-        const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[k] : k;
+        const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[k] : k + p.first_elem;
         for (int a = lane; a < n; a += 32) {
             const int id = p.conn[e * n + a];
             w_ids[a] = id;
-            if (WHAT == 0 || WHAT == 5) {
+            if ((WHAT == 0 || WHAT == 5) && !p.dump) {
                 const long long o0 = p.blk_off[id], o1 = p.blk_off[id + 1];
                 w_base[a] = (long long)(s * s) * o0;
                 w_len[a] = (int)(o1 - o0) * s;
@@ -437,6 +441,17 @@ __global__ void __launch_bounds__(128) mass_source_kernel(const MsParams p) {
                         for (int i = 0; i < d; ++i)
 #pragma unroll
                             for (int j = 0; j < i; ++j) C[i * d + j] = C[j * d + i];
+                    }
+                    if (p.dump) {  // dense K_e, column-major: entry (d a + i, d b + j) and its mirror image
+                        double* out = p.dump + k * (uint64_t)(n * d) * (uint64_t)(n * d);
+#pragma unroll
+                        for (int i = 0; i < d; ++i)
+#pragma unroll
+                            for (int j = 0; j < d; ++j) {
+                                out[(uint64_t)(d * b + j) * (n * d) + (d * a + i)] = C[i * d + j];
+                                if (a != b) out[(uint64_t)(d * a + i) * (n * d) + (d * b + j)] = C[i * d + j];
+                            }
+                        continue;
                     }
                     const int kab = p.blockmap[e * (uint64_t)(n * n) + a * n + b], kba = p.blockmap[e * (uint64_t)(n * n) + b * n + a];
                     double* rab = p.values + (w_base[a] + (long long)(d * kab));
@@ -812,6 +827,33 @@ fb200_status fb200::assemble_state_dependent(fb200_ctx* ctx, const fb200_operato
     p.values = ctx->d_values;
     p.errword = ctx->d_errword;
     return ms_launch<5>(ctx, p, scatter_mode);
+}
+
+// The ElementMatrixAssembler::assemble_element_matrix view (local.rs:78-80) of a state-dependent operator: dense K_e(u) of the elements
+// [first, first + count), column-major per element, on the device buffer d_out.  u = NULL: the tangent at the undeformed state.
+fb200_status fb200::element_matrices_state_dependent(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* q, const double* u,
+                                                     uint64_t first, uint64_t count, double* d_out) {
+    std::vector<double> zeros;
+    if (!u) {
+        zeros.assign((size_t)ctx->ei.d * ctx->N + 1, 0.0);
+        u = zeros.data();
+    }
+    int s = 0;
+    FB200_TRY(elliptic_common(ctx, op, q, u, &s));
+    if (!zeros.empty()) FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.nq = q->num_points;
+    p.s = s;
+    p.op = op->kind;
+    p.u = ctx->d_source;
+    p.errword = ctx->d_errword;
+    p.dump = d_out;
+    p.first_elem = first;
+    p.forced = 1;
+    p.forced_list = nullptr;
+    p.forced_count = count;
+    return ms_launch<5>(ctx, p, FB200_SCATTER_ATOMIC);
 }
 
 // One (colour, rule) group of fb200_assemble_into_csr_table_device for a state-dependent operator: u = NULL keeps the state uploaded by

@@ -65,28 +65,44 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
         }
         __syncthreads();
 
-        // ---- phase 2: one thread per slot
+        // ---- phase 2: one thread per slot.  A slot is one 32-byte record (chunks.cpp) holding everything but the tags beyond the eighth,
+        // and the record of the thread's NEXT slot is in flight while the current one is summed: no dependent global load in the loop
         const long long so = p.slot_off[chunk];
         const int U = (int)(p.slot_off[chunk + 1] - so);
-        const int npairs = ne * (N * N);
         const uint16_t* contrib = p.contrib + p0 * (uint64_t)(N * N);
+        const ulonglong2* recs = reinterpret_cast<const ulonglong2*>(p.slot_rec) + 2 * so;
+        ulonglong2 ra = make_ulonglong2(0, 0), rb = make_ulonglong2(~0ull, ~0ull);
+        if (tid < U) {
+            ra = __ldg(recs + 2 * tid);
+            rb = __ldg(recs + 2 * tid + 1);
+        }
         for (int u = tid; u < U; u += T) {
-            const int cb = p.slot_cbeg[so + u];
-            const int ce = u + 1 < U ? (int)p.slot_cbeg[so + u + 1] : npairs;
-            // slot metadata first: its latency overlaps the contributor loop
-            const int node = p.slot_node[so + u];
-            const int kpos = p.slot_k[so + u];
-            const bool st = overwrite && (p.slot_flags[so + u] & 1);
-            const long long o0 = p.blk_off[node], o1 = p.blk_off[node + 1];
+            const ulonglong2 ca = ra, cb2 = rb;
+            if (u + T < U) {
+                ra = __ldg(recs + 2 * (u + T));
+                rb = __ldg(recs + 2 * (u + T) + 1);
+            }
+            const long long dsti = (long long)(ca.x & ((1ull << 62) - 1ull));
+            const bool st = overwrite && (ca.x >> 62) != 0ull;
+            const int rl = (int)(unsigned int)ca.y;
+            const int cb = (int)((ca.y >> 32) & 0xffffull), cnt = (int)(ca.y >> 48);
             double M[D][D];
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
                 for (int j = 0; j < D; ++j) M[i][j] = 0.0;
-            unsigned tag_next = __ldg(contrib + cb);  // every slot has at least one contributor
-            for (int t = cb; t < ce; ++t) {
-                const unsigned tag = tag_next;
-                if (t + 1 < ce) tag_next = __ldg(contrib + t + 1);
+            unsigned long long tw = cb2.x;  // tags 0-3; then 4-7 (cb2.y); beyond the eighth from the chunk's tag list
+            unsigned tag_far = cnt > 8 ? (unsigned)__ldg(contrib + cb + 8) : 0u;
+            for (int t = 0; t < cnt; ++t) {
+                unsigned tag;
+                if (t < 8) {
+                    if (t == 4) tw = cb2.y;
+                    tag = (unsigned)(tw & 0xffffull);
+                    tw >>= 16;
+                } else {
+                    tag = tag_far;
+                    if (t + 1 < cnt) tag_far = __ldg(contrib + cb + t + 1);
+                }
                 const int el = tag >> 4, a = (tag >> 2) & 3, b = tag & 3;
                 const double* ga = s_g + (a * D) * C + el;
                 const double* gb = s_g + (b * D) * C + el;
@@ -100,8 +116,7 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
                         for (int j = 0; j < D; ++j) M[i][j] = fma(va[i], vb[j], M[i][j]);
                 }
             }
-            const int rl = (int)(o1 - o0) * S;
-            double* dst = p.values + ((long long)(S * S) * o0 + (long long)S * kpos);
+            double* dst = p.values + dsti;
             if constexpr (S == 1) {
                 if (st) dst[0] = M[0][0];
                 else atomicAdd(dst, M[0][0]);

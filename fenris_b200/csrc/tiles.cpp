@@ -54,7 +54,7 @@ struct TileOut {
     std::vector<int32_t> nodes;
     std::vector<uint32_t> flush;   // pass 1: CSR order; pass 2 (finish_flush): STORE segment, then REDUCE segment
     std::vector<uint32_t> wait;    // pass 2
-    uint32_t n_store = 0, flags = 0, zero_entries = 0;
+    uint32_t n_store = 0, n_publish = 0, flags = 0, zero_entries = 0;
     std::vector<uint8_t> lnodes;   // rounds * warps * 8
     std::vector<uint16_t> emap;    // rounds * warps * 64
     std::vector<int32_t> elem;     // rounds * warps
@@ -311,8 +311,11 @@ static void finish_flush(TileOut& t, uint32_t tile, bool owner, const uint32_t* 
     }
     std::sort(t.wait.begin(), t.wait.end());
     t.wait.erase(std::unique(t.wait.begin(), t.wait.end()), t.wait.end());
-    std::vector<uint32_t> store, reduce;
+    // STORE segment: first the shared rows this tile owns (the tile publishes its flag right after them, so that the tiles waiting for
+    // it are released as early as possible), then the complete rows
+    std::vector<uint32_t> store, complete_rows, reduce;
     store.reserve(t.flush.size() + 256);
+    complete_rows.reserve(t.flush.size());
     reduce.reserve(t.flush.size());
     t.zero_entries = 0;
     size_t f = 0;
@@ -324,7 +327,7 @@ static void finish_flush(TileOut& t, uint32_t tile, bool owner, const uint32_t* 
         if (cls[u] == 0) {
             reduce.insert(reduce.end(), t.flush.begin() + f, t.flush.begin() + g);
         } else if (cls[u] == 1) {
-            store.insert(store.end(), t.flush.begin() + f, t.flush.begin() + g);
+            complete_rows.insert(complete_rows.end(), t.flush.begin() + f, t.flush.begin() + g);
         } else {
             const int32_t id = t.nodes[u] & 0x7fffffff;
             const uint32_t cnt = (uint32_t)(blk_off[id + 1] - blk_off[id]);
@@ -340,6 +343,8 @@ static void finish_flush(TileOut& t, uint32_t tile, bool owner, const uint32_t* 
         }
         f = g;
     }
+    t.n_publish = (uint32_t)store.size();
+    store.insert(store.end(), complete_rows.begin(), complete_rows.end());
     t.n_store = (uint32_t)store.size();
     store.insert(store.end(), reduce.begin(), reduce.end());
     t.flush.swap(store);
@@ -469,7 +474,7 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         const TileOut& t = *tp;
         const uint32_t hdr[kTileHdrWords] = {(uint32_t)out.elem.size(),  t.rounds, (uint32_t)t.nodes.size(), t.P, (uint32_t)out.nodes.size(),
                                              (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), (uint32_t)t.ne, t.n_store,
-                                             (uint32_t)out.wait.size(),  (uint32_t)t.wait.size(), t.flags, 0u, 0u, 0u, 0u};
+                                             (uint32_t)out.wait.size(),  (uint32_t)t.wait.size(), t.flags, t.n_publish, 0u, 0u, 0u};
         out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
         out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
         out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
@@ -627,8 +632,8 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
         }
         // flush list: every coupled ordered pair (u, v) exactly once with the position of v in u's block row; two segments (STORE, then
         // REDUCE), each in CSR order of its rows; zero words only in the STORE segment of a shared node's owner, completing its rows
-        const uint32_t nstore = h[8], wb = h[9], nw = h[10];
-        if (nstore > nf || (uint64_t)wb + nw > ht.wait.size()) return fail_check(2);
+        const uint32_t nstore = h[8], wb = h[9], nw = h[10], npub = h[12];
+        if (nstore > nf || npub > nstore || (uint64_t)wb + nw > ht.wait.size()) return fail_check(2);
         store_entries += nstore;
         const size_t diag = [&] { size_t d = 0; for (auto& pr : pairs) d += (pr.first >> 8) == (pr.first & 0xffu); return d; }();
         uint32_t last_u = 0, last_k = 0, zeros = 0;
@@ -639,11 +644,13 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
             const uint32_t ps = w & 0x7ffu, tr = (w >> 11) & 1u, u = (w >> 12) & 0x7fu, k = w >> 19;
             const uint32_t seg = f < nstore ? 1u : 2u;
             if (u >= nn) return fail_check(13);
-            if (f && f != nstore && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
+            if (f && f != nstore && f != npub && (u < last_u || (u == last_u && k <= last_k))) return fail_check(14);
             last_u = u;
             last_k = k;
             if (row_seg[u] && row_seg[u] != seg) return fail_check(23);  // a row lives in one segment only
             row_seg[u] = (uint8_t)seg;
+            // the leading part of the STORE segment (before the publish) holds exactly the shared rows this tile owns
+            if (seg == 1 && (f < npub) != (ht.nodes[nb + u] >= 0)) return fail_check(33);
             ++row_entries[u];
             const auto& r = rows[ht.nodes[nb + u] & 0x7fffffff];
             if (k >= r.size()) return fail_check(15);

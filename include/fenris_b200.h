@@ -176,6 +176,11 @@ fb200_status fb200_values_upload(fb200_ctx* ctx, const double* values);
  * [first, first+count), each (s n)^2 doubles column-major like nalgebra's DMatrix. Test/debug surface. */
 fb200_status fb200_element_matrices(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature,
                                     uint64_t first, uint64_t count, double* out);
+/* The same view with the state the assembler was built with (ElementEllipticAssemblerBuilder::with_u, elliptic.rs:241-297): for the
+ * state-dependent operators (FB200_STVK, FB200_NEO_HOOKEAN; fenris-solid/src/materials.rs:232-469) K_e is the tangent stiffness at u
+ * (num_nodes * d doubles, NULL = zeros; fb200_element_matrices is this call with u = NULL); linear operators ignore u. */
+fb200_status fb200_element_matrices_u(fb200_ctx* ctx, const fb200_operator* op, const fb200_quadrature* quadrature, const double* u,
+                                      uint64_t first, uint64_t count, double* out);
 
 /* ---- mass matrix, source vector, global vector assembly (the rest of "assemble a linear system", examples/poisson2d.rs:33-86) --- */
 /* ElementMassAssembler through CsrAssembler / CsrParAssembler (src/assembly/local/mass.rs:127-159, 218-286): M_IJ = I_s * sum_q w_q |det J_q|
@@ -271,6 +276,10 @@ fb200_status fb200_hex27_from_hex8(uint64_t num_vertices, const double* vertices
 /* Hex20Mesh::from(&hex8_mesh) (src/mesh_convert.rs:168-217, 481-488): same calling convention as fb200_hex27_from_hex8. */
 fb200_status fb200_hex20_from_hex8(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* hex8,
                                    uint64_t* num_vertices_out, double* vertices_out, uint64_t* hex20);
+/* Tet10Mesh::from(&tet4_mesh) (src/mesh_convert.rs:42-83, 227-330, 444-452): the 4 vertices, then the midpoints of the edges (0,1) (1,2)
+ * (0,2) (0,3) (2,3) (1,3), labelled in first-seen order.  Same calling convention as fb200_hex27_from_hex8. */
+fb200_status fb200_tet10_from_tet4(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* tet4,
+                                   uint64_t* num_vertices_out, double* vertices_out, uint64_t* tet10);
 fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_points, double* weights, double* points);
 /* LameParameters::from(YoungPoisson) (fenris-solid/src/materials.rs:31-43). */
 void fb200_lame_from_young_poisson(double young, double poisson, double* mu, double* lambda);

@@ -68,6 +68,10 @@ def test_generators_restate_reference_exactly(kats, n):
     m = fb.create_unit_box_uniform_tet_mesh_3d(n)
     v, c = fo.create_unit_box_uniform_tet_mesh_3d(n)
     assert np.array_equal(m.vertices(), v) and np.array_equal(m.connectivity().astype(np.int64), c)
+    # Tet10Mesh::from(&tet4) (mesh_convert.rs:42-83): library converter against the literal restatement - same labels, same midpoints
+    m10 = fb.tet10_mesh_from(m)
+    v10, c10 = fo.tet10_mesh_from_tet4(v, c)
+    assert np.array_equal(m10.connectivity().astype(np.int64), c10) and np.array_equal(m10.vertices(), v10)
     if n <= 2:  # the reference's insta snapshots
         snap = kats[f"bcc_tet_mesh_{n}"]
         assert m.vertices().tolist() == snap["vertices"] and m.connectivity().tolist() == snap["connectivity"]

@@ -154,3 +154,28 @@ def test_materials_through_the_reference_api_mirror(material, mat):
     ref = fo.assemble_elliptic_vector_serial(prob, u)
     assert np.abs(f - ref).max() < TOL * np.abs(ref).max()
     assert abs(fb.assemble_scalar(ea) - fo.assemble_elliptic_scalar(prob, u)) < TOL * abs(fo.assemble_elliptic_scalar(prob, u))
+
+
+@pytest.mark.parametrize("mat", MATERIALS)
+@pytest.mark.parametrize("kind,n", [("quad4", 3), ("tet4", 2), ("hex8", 2), ("tet10", 1), ("hex20", 1), ("hex27", 1)])
+def test_material_element_matrices_equal_oracle(ctx, kind, n, mat):
+    # ElementMatrixAssembler::assemble_element_matrix (local.rs:78-80) for the state-dependent operators: dense K_e(u), no pattern needed
+    et, v, c = _case(kind, n)
+    prob = fo.Problem(et, v, c.astype(np.int64), mat, params=(MU, LAM))
+    s = prob.sdim
+    nn = c.shape[1]
+    u = 0.05 * np.random.default_rng(5).normal(size=s * len(v))
+    ctx.space_upload(et, v, c.astype(np.uint64))
+    first, count = 1 if len(c) > 2 else 0, min(len(c), 7)
+    count = min(count, len(c) - first)
+    K = ctx.element_matrices(mat, prob.weights, prob.points, (MU, LAM), first, count, s * nn, u=u)
+    for k in range(count):
+        nodes = c[first + k].astype(np.int64)
+        ue = u.reshape(-1, s)[nodes].ravel()
+        ref = fo.element_matrix_u(et, v[nodes], mat, ue, prob.weights, prob.points, prob.params_per_point)
+        assert fo.rel_frobenius(K[k], ref) < TOL, (kind, k)
+        assert np.array_equal(K[k], K[k].T)  # upper triangle mirrored (clone_upper_to_lower, util.rs:38-50)
+    # without a state: the linear-elastic element matrix (F = I)
+    K0 = ctx.element_matrices(mat, prob.weights, prob.points, (MU, LAM), first, count, s * nn)
+    Kl = ctx.element_matrices(fo.LINEAR_ELASTIC, prob.weights, prob.points, (MU, LAM), first, count, s * nn)
+    assert fo.rel_frobenius(K0, Kl) < TOL

@@ -100,7 +100,7 @@ def test_slab_partition_nccl_equals_global(scatter_mode, exchange):
 @pytest.mark.skipif(_num_gpus() < 4, reason="needs at least four GPUs")
 @pytest.mark.parametrize("exchange", ["p2p", "peers"])
 def test_slab_partition_four_ranks(exchange):
-    _run(4, _worker, (9, 10, 16, 0, exchange))  # inner ranks have two neighbours
+    _run(4, _worker, (10, 10, 16, 0, exchange))  # inner ranks have two neighbours (the reference generator wants cx == cy)
 
 
 def _range_worker(rank, world, uid, kind, q):
