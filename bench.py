@@ -11,7 +11,8 @@ Contract (see the task statement):  python bench.py --gpus N --steps K --warmup 
       --exchange peers          packed rows, ncclSend / ncclRecv per neighbour, added on arrival
       --exchange allreduce      one world ncclAllReduce over a packed buffer of all interface rows
   * --workload c5 (BASELINE.json config C5): Tet4 linear elasticity, create_unit_box_uniform_tet_mesh_3d(161) = 50 079 372 elements,
-    STRONG scaling: the mesh is cut into N z-slabs of element ranges (fenris_b200/partition.py), neighbour exchange of the packed rows.
+    STRONG scaling: the mesh is cut into N z-slabs of element ranges (fenris_b200/partition.py); the same three exchanges (the fused one
+    lives in the Tet4 chunk kernel's slot scatter).
   * a "step" = one assemble()-equivalent (values = all element contributions, interface exchange included), mesh / pattern / scatter
     lists resident in HBM and built outside the timed region, exactly like benches/assembly.rs:131-141 of the reference keeps the
     pattern outside the timed closure.
@@ -367,8 +368,8 @@ def main():
             ctx.interface_set_peers(peers)
             if exchange == "allreduce":
                 exchange = "peers"
-            if exchange == "p2p" and (c5 or mode != MODE_NAMES["atomic"] or not ctx.interface_enable_p2p()):
-                exchange = "peers"  # the fused exchange lives in the Hex8 tile kernel; everything else uses the packed neighbour exchange
+            if exchange == "p2p" and (mode != MODE_NAMES["atomic"] or not ctx.interface_enable_p2p()):
+                exchange = "peers"  # the fused exchange lives in the Hex8 tile kernel and the Tet4 chunk kernel (ATOMIC scatter)
     # the first assembly builds the scatter lists of the kernel (tile / chunk lists): part of the set-up, like the pattern
     ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode, accumulate=False)
     if world > 1:
@@ -496,6 +497,37 @@ def main():
                "ms_per_step": ms, "steps": e2e_steps}
     del vals_host
 
+    # ---- the pipeline in which the matrix never leaves the device (N = 1, C3): assemble -> homogeneous Dirichlet rows on the resident CSR
+    # (global.rs:379-451) -> Jacobi-PCG on the device (fenris-sparse/src/cg.rs:364-480) -> only the solution crosses PCIe.  Informational:
+    # the PCIe-bound `e2e` above ships 3.9 GB of values per step; a solver that runs where the matrix is assembled ships 49 MB.
+    e2e_solve = None
+    if world == 1 and not c5 and not args.no_e2e and mode == MODE_NAMES["atomic"]:
+        try:
+            vx = cells + 1
+            fixed = np.arange(vx * vx, dtype=np.uint64)          # the node plane z = 0 is clamped
+            b = np.zeros(3 * verts.shape[0])
+            b[2::3] = -1.0 / verts.shape[0]                       # a uniform downward nodal load
+            b[: 3 * len(fixed)] = 0.0
+            iters = 60
+            t0 = time.perf_counter()
+            ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, data, scatter_mode=mode, accumulate=False)
+            ctx.apply_homogeneous_dirichlet_bc_csr(fixed)
+            ctx.synchronize()
+            t1 = time.perf_counter()
+            res = None
+            try:
+                _, its, res = ctx.cg_solve(b, rel_tol=1e-30, max_iter=iters)  # a fixed number of iterations: time per iteration, not convergence
+            except fb.Fb200Error as exc:
+                if exc.status != fb.ERR_NOT_CONVERGED:
+                    raise
+                its = iters
+            t2 = time.perf_counter()
+            e2e_solve = {"assemble_dirichlet_ms": (t1 - t0) * 1e3, "pcg_iterations": int(its), "pcg_ms": (t2 - t1) * 1e3,
+                         "pcg_ms_per_iteration": (t2 - t1) * 1e3 / max(int(its), 1), "h2d_bytes": int(b.nbytes), "d2h_bytes": int(b.nbytes),
+                         "note": "wall clock incl. the H2D of b and the D2H of x; the 3.9 GB of CSR values stay in HBM"}
+        except Exception as exc:  # informational only: never break the bench line
+            e2e_solve = {"error": str(exc)[:200]}
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -514,7 +546,7 @@ def main():
                "sample": f"{'Tet4' if c5 else 'Hex8'} elasticity {n}^3 cells ({len(sc)} elements) x {reps} reps, coloured OpenMP C restatement of CsrParAssembler"}
 
     if rank == 0:
-        exch = {"p2p": "fused into the tile kernel's flush over NVLink peer memory (red.global.add.f64 on the neighbour's rows) + neighbour barrier",
+        exch = {"p2p": "fused into the assembly kernel's scatter over NVLink peer memory (red.global.add.f64 on the neighbour's rows) + neighbour barrier",
                 "peers": "neighbour ncclSend/ncclRecv of the packed rows, summed on arrival", "allreduce": "world ncclAllReduce"}[exchange]
         out = {
             "metric": f"elements/sec into global CSR ({'Tet4' if c5 else 'Hex8'} 3D linear elasticity, fp64)", "value": value, "unit": "elements/s",
@@ -527,6 +559,8 @@ def main():
                        "l2": "inputs+outputs >> L2 (values 3.9 - 9 GB per GPU); no L2 flush needed", "setup_s": setup_s, "mesh_s": t_mesh},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         }
+        if e2e_solve:
+            out["e2e_solve"] = e2e_solve
         if other:
             out["other_modes_elements_per_s"] = other
         print(json.dumps(out), flush=True)

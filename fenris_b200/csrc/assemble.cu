@@ -74,7 +74,10 @@ struct AssembleParams {
     // chunk-local scatter lists (chunks.cpp); num_chunks above
     const int64_t* slot_off;
     const uint16_t* contrib;
-    const uint64_t* slot_rec;    // 4 words per slot (HostChunks::slot_rec)
+    const int32_t* slot_node;
+    const uint16_t* slot_k;
+    const uint16_t* slot_cbeg;
+    const uint8_t* slot_flags;
     // tile lists of the Hex8 tile kernel (tiles.cpp)
     uint32_t num_tiles;
     const uint32_t* tile_hdr;
@@ -83,6 +86,7 @@ struct AssembleParams {
     const uint8_t* tile_lnodes;
     const uint16_t* tile_emap;
     const int32_t* tile_elem;
+    const uint32_t* tile_list;   // launch over a subset of the tiles (one tile colour): ticket t -> tile tile_list[t]; NULL = all tiles
     const uint32_t* tile_wait;   // owner stores: tiles whose published stores a tile's reductions wait for
     uint32_t* tile_flag;         // ... per tile: epoch of the last launch whose stores of the tile are published
     uint32_t tile_epoch;         // ... this launch's epoch; 0 = no ownership (the values were zero-filled, complete rows are stored)
@@ -701,7 +705,10 @@ static fb200_status launch_hex8_mma(fb200_ctx* ctx, AssembleParams& p) {
 static void free_chunks(ChunkLists& cl) {
     dev_free(cl.d_slot_off);
     dev_free(cl.d_contrib);
-    dev_free(cl.d_slot_rec);
+    dev_free(cl.d_slot_node);
+    dev_free(cl.d_slot_k);
+    dev_free(cl.d_slot_cbeg);
+    dev_free(cl.d_slot_flags);
     dev_free(cl.d_conn_pos);
     cl.valid = false;
     cl.count = 0;
@@ -717,7 +724,7 @@ static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T>& h) {
 
 static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t count, int chunk_elems) {
     ChunkLists& cl = ctx->chunks;
-    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems && cl.sdim == ctx->sdim) return FB200_OK;
+    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems) return FB200_OK;
     free_chunks(cl);
     const int n = ctx->ei.n;
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -729,13 +736,15 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
     FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     HostChunks hc;
-    build_chunk_lists(n, ctx->sdim, count, chunk_elems, ids.data(), conn.data(), ctx->N, blk_off.data(), map.data(), hc);
+    build_chunk_lists(n, count, chunk_elems, ids.data(), conn.data(), ctx->E, ctx->N, blk_off.data(), map.data(), hc);
     cl.num_chunks = (uint32_t)(hc.slot_off.size() - 1);
-    cl.total_slots = hc.slot_rec.size() / 4;
-    cl.sdim = ctx->sdim;
+    cl.total_slots = hc.slot_node.size();
     FB200_TRY(upload_vec(ctx, &cl.d_slot_off, hc.slot_off));
     FB200_TRY(upload_vec(ctx, &cl.d_contrib, hc.contrib));
-    FB200_TRY(upload_vec(ctx, &cl.d_slot_rec, hc.slot_rec));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_node, hc.slot_node));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_k, hc.slot_k));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_cbeg, hc.slot_cbeg));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_flags, hc.slot_flags));
     FB200_TRY(dev_alloc(ctx, &cl.d_conn_pos, count * n));
     if (count) {
         const int blocks = (int)std::min<uint64_t>(div_up(count * n, 256), (uint64_t)ctx->sm_count * 16);
@@ -761,9 +770,22 @@ static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
     p.num_chunks = cl.num_chunks;
     p.slot_off = cl.d_slot_off;
     p.contrib = cl.d_contrib;
-    p.slot_rec = cl.d_slot_rec;
+    p.slot_node = cl.d_slot_node;
+    p.slot_k = cl.d_slot_k;
+    p.slot_cbeg = cl.d_slot_cbeg;
+    p.slot_flags = cl.d_slot_flags;
+    // fused interface exchange (comm.cu): interface slots are also reduced into the neighbouring rank's rows; the values were just
+    // cleared when the call overwrites, so no neighbour may add to them before that (neighbour barrier)
+    const bool peer = ctx->p2p.enabled && ctx->p2p.num_peers > 0;
+    if (peer) {
+        p.peer_row = ctx->p2p.d_peer_row;
+        p.peer_values[0] = ctx->p2p.values[0];
+        p.peer_values[1] = ctx->p2p.values[1];
+        if (!p.accumulate) FB200_TRY(p2p_neighbour_barrier(ctx));
+        ctx->p2p.pending = true;
+    }
     const size_t smem = sizeof(double) * 12 * C;
-    auto kernel = assemble_tet4_chunk_kernel<OP, T, C>;
+    auto kernel = peer ? assemble_tet4_chunk_kernel<OP, T, C, true> : assemble_tet4_chunk_kernel<OP, T, C, false>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
@@ -791,6 +813,8 @@ static void free_tiles(TileLists& tl) {
     dev_free(tl.d_nodes);
     dev_free(tl.d_flush);
     dev_free(tl.d_wait);
+    dev_free(tl.d_colour_tiles);
+    tl.colour_off.clear();
     dev_free(tl.d_flag);
     dev_free(tl.d_zero_nodes);
     dev_free(tl.d_lnodes);
@@ -839,6 +863,8 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     FB200_TRY(upload_vec(ctx, &tl.d_nodes, ht.nodes));
     FB200_TRY(upload_vec(ctx, &tl.d_flush, ht.flush));
     FB200_TRY(upload_vec(ctx, &tl.d_wait, ht.wait));
+    FB200_TRY(upload_vec(ctx, &tl.d_colour_tiles, ht.colour_tiles));
+    tl.colour_off = ht.colour_off;
     FB200_TRY(upload_vec(ctx, &tl.d_zero_nodes, ht.zero_nodes));
     FB200_TRY(upload_vec(ctx, &tl.d_lnodes, ht.lnodes));
     FB200_TRY(upload_vec(ctx, &tl.d_emap, ht.emap));
@@ -954,6 +980,47 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
         cudaMemset(ctx->d_ticket, 0, sizeof(dc));
     }
     return check_launch(ctx, "assemble_hex8_tile_kernel");
+}
+
+// Deterministic coloured scatter of a Hex8 space (FB200_SCATTER_COLORED; the reference's CsrParAssembler, global.rs:314-376, at tile
+// granularity): one launch of the tile kernel per TILE colour.  Tiles of a colour share no node, so a launch adds at most once to every
+// CSR value; sums inside a tile are formed in a fixed order and the launches run in colour order: the result is bitwise reproducible.
+template <int OP, int MAXN, int MAXP>
+static fb200_status launch_hex8_tile_colored_t(fb200_ctx* ctx, AssembleParams& p, const TileShape& shape, bool* used) {
+    *used = false;
+    FB200_TRY(ensure_tiles(ctx, shape));
+    const TileLists& tl = ctx->tiles;
+    if (!tl.valid || tl.colour_off.size() < 2) return FB200_OK;
+    *used = true;
+    FB200_TRY(clear_values_if_pending(ctx));
+    AssembleParams q = p;
+    q.tile_epoch = 0;
+    q.tile_static = 0;
+    q.accumulate = 1;  // every flush entry is a reduction onto the cleared (or the caller's) values
+    q.tile_hdr = tl.d_hdr;
+    q.tile_nodes = tl.d_nodes;
+    q.tile_flush = tl.d_flush;
+    q.tile_lnodes = tl.d_lnodes;
+    q.tile_emap = tl.d_emap;
+    q.tile_elem = tl.d_elem;
+    q.tile_wait = tl.d_wait;
+    q.tile_flag = tl.d_flag;
+    q.ticket32 = reinterpret_cast<unsigned int*>(ctx->d_ticket);
+    const size_t smem = Hex8TileSmem<OP, MAXN, MAXP>::bytes;
+    auto kernel = assemble_hex8_tile_kernel<OP, MAXN, MAXP, false>;
+    FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int THREADS = (2 * kTileGroupWarps + kTileHelperWarps) * 32;
+    for (size_t c = 0; c + 1 < tl.colour_off.size(); ++c) {
+        const uint64_t n = tl.colour_off[c + 1] - tl.colour_off[c];
+        if (n == 0) continue;
+        q.tile_list = tl.d_colour_tiles + tl.colour_off[c];
+        q.num_tiles = (uint32_t)n;
+        const int blocks = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
+        FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
+        kernel<<<blocks, THREADS, smem, ctx->stream>>>(q);
+        FB200_TRY(check_launch(ctx, "assemble_hex8_tile_kernel<colour>"));
+    }
+    return FB200_OK;
 }
 
 // tile shape: 4 x 4 x 4 elements, one CTA of 16 compute + 8 helper warps per SM (double-buffered accumulators: 2 x 85.5 KB);
@@ -1099,6 +1166,19 @@ static fb200_status dispatch_mode(fb200_ctx* ctx, AssembleParams& p, int mode) {
         case MODE_DUMP: return launch_element_parallel<N, NG, D, OP, MODE_DUMP>(ctx, p);
         case MODE_COLORED_LIST: return launch_element_parallel<N, NG, D, OP, MODE_COLORED>(ctx, p);
         case FB200_SCATTER_COLORED: {
+            if constexpr (N == 8 && NG == 8 && D == 3) {
+                // Hex8, uniform operator data: colours of tiles instead of colours of elements (deterministic, ~5x faster)
+                static const int env_ct = std::getenv("FB200_HEX8_COLORED_TILES") ? std::atoi(std::getenv("FB200_HEX8_COLORED_TILES")) : 1;
+                const bool want = ctx->tune_colored_tiles >= 0 ? ctx->tune_colored_tiles != 0 : env_ct != 0;
+                if (want && !p.generic_only && p.uniform && p.nq <= 8 && hex8_tile_setting(ctx) == 64 && ctx->d_order && ctx->order_count == p.count &&
+                    std::getenv("FB200_HEX8_V1") == nullptr) {
+                    bool used = false;
+                    TileShape shape = kHex8TileShape;
+                    shape.owner_stores = hex8_owner_setting(ctx);
+                    FB200_TRY((launch_hex8_tile_colored_t<OP, 128, 1216>(ctx, p, shape, &used)));
+                    if (used) return FB200_OK;
+                }
+            }
             const uint64_t ncol = ctx->h_color_off.size() - 1;
             for (uint64_t c = 0; c < ncol; ++c) {
                 AssembleParams pc = p;

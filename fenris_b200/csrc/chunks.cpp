@@ -9,10 +9,9 @@
 //
 // Per chunk c (positions [c C, min((c+1) C, count))):
 //   contrib[c C n^2 + t], t < ne n^2 : contributor tags  e_local n^2 + a n + b, grouped by slot, elements ascending inside a slot
-//   slots slot_off[c] .. slot_off[c+1]: one 32-byte record each (HostChunks::slot_rec): where the block's values start and how long the rows
-//   are, the first contributor (relative to the chunk) and the contributor count, whether the row node is complete in this chunk, and the
-//   first 8 contributor tags themselves (most slots have fewer: the kernel's slot loop then touches no other list).  Slots are ordered by
-//   contributor count, largest first, so that the threads of a warp (one slot each) run loops of equal length.
+//   slots slot_off[c] .. slot_off[c+1]: node (row node I), k (position of the column node in I's block row), cbeg (first contributor,
+//   relative to the chunk), flags (bit 0: row node complete in this chunk, bit 1: partition-interface row); slots are ordered by contributor count, largest first,
+//   so that the threads of a warp (one slot each) run loops of equal length.
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -21,18 +20,24 @@
 
 namespace fb200 {
 
-void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
-                       const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out) {
+void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
+                       uint64_t num_nodes, const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out) {
     const int n2 = n * n;
     const uint64_t num_chunks = (count + chunk_elems - 1) / chunk_elems;
-    // incidences of every node among the processed elements
-    std::vector<int32_t> degree(num_nodes, 0);
+    // incidences of every node over ALL elements of the space - also the ghost elements of a partition, which are in the pattern but are
+    // not assembled here: a row is complete in a chunk (plain stores) only if every element of its node is processed inside that chunk.
+    // Rows that ghost elements touch are never complete: another rank adds to them too (packed exchange or peer-memory reductions).
+    std::vector<int32_t> degree(num_nodes, 0), degree_owned(num_nodes, 0);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
     for (uint64_t pos = 0; pos < count; ++pos) {
         const uint64_t e = order ? (uint64_t)order[pos] : pos;
-        for (int a = 0; a < n; ++a) ++degree[conn[e * n + a]];
+        for (int a = 0; a < n; ++a) ++degree_owned[conn[e * n + a]];
     }
     struct Slot {
-        uint64_t w[4];
+        int32_t node;
+        uint16_t k, cbeg;
+        uint8_t flags;
     };
     std::vector<std::vector<Slot>> chunk_slots(num_chunks);
     out.contrib.assign(count * (uint64_t)n2, 0);
@@ -96,18 +101,9 @@ void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const i
             std::vector<Slot>& slots = chunk_slots[c];
             slots.reserve(raw.size());
             for (const Raw& r : raw) {
-                const uint64_t k = r.key - (uint64_t)blk_off[r.node];
-                const uint64_t rl = (uint64_t)(blk_off[r.node + 1] - blk_off[r.node]) * (uint64_t)sdim;
-                Slot sl;
-                sl.w[0] = ((uint64_t)(sdim * sdim) * (uint64_t)blk_off[r.node] + (uint64_t)sdim * k) | (complete(r.node) ? 1ull << 62 : 0ull);
-                sl.w[1] = rl | ((uint64_t)tags.size() << 32) | ((uint64_t)r.cnt << 48);
-                sl.w[2] = sl.w[3] = ~0ull;
-                for (uint32_t t = 0; t < r.cnt; ++t) {
-                    const uint16_t tag = (uint16_t)(pairs[r.begin + t] & 0xffffu);
-                    if (t < 8) sl.w[2 + t / 4] = (sl.w[2 + t / 4] & ~(0xffffull << (16 * (t & 3)))) | ((uint64_t)tag << (16 * (t & 3)));
-                    tags.push_back(tag);
-                }
-                slots.push_back(sl);
+                slots.push_back({r.node, (uint16_t)(r.key - (uint64_t)blk_off[r.node]), (uint16_t)tags.size(),
+                                 (uint8_t)((complete(r.node) ? 1 : 0) | (degree[r.node] != degree_owned[r.node] ? 2 : 0))});
+                for (uint32_t t = 0; t < r.cnt; ++t) tags.push_back((uint16_t)(pairs[r.begin + t] & 0xffffu));
             }
             std::copy(tags.begin(), tags.end(), out.contrib.begin() + p0 * (uint64_t)n2);
         }
@@ -122,11 +118,17 @@ void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const i
     out.slot_off.assign(num_chunks + 1, 0);
     for (uint64_t c = 0; c < num_chunks; ++c) out.slot_off[c + 1] = out.slot_off[c] + (int64_t)chunk_slots[c].size();
     const uint64_t total = (uint64_t)out.slot_off[num_chunks];
-    out.slot_rec.resize(total * 4);
+    out.slot_node.resize(total);
+    out.slot_k.resize(total);
+    out.slot_cbeg.resize(total);
+    out.slot_flags.resize(total);
     for (uint64_t c = 0; c < num_chunks; ++c) {
         uint64_t o = (uint64_t)out.slot_off[c];
-        for (const Slot& sl : chunk_slots[c]) {
-            std::copy(sl.w, sl.w + 4, out.slot_rec.begin() + 4 * o);
+        for (const Slot& s : chunk_slots[c]) {
+            out.slot_node[o] = s.node;
+            out.slot_k[o] = s.k;
+            out.slot_cbeg[o] = s.cbeg;
+            out.slot_flags[o] = s.flags;
             ++o;
         }
     }

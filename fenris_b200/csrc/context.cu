@@ -315,6 +315,11 @@ fb200_status fb200_set_tuning(fb200_ctx* ctx, const char* name, int32_t value) {
         ctx->tune_hex8_tile = value;
         return FB200_OK;
     }
+    if (name && std::strcmp(name, "hex8_colored_tiles") == 0) {
+        if (value != 0 && value != 1) return fail(ctx, FB200_ERR_SHAPE, "hex8_colored_tiles must be 0 or 1");
+        ctx->tune_colored_tiles = value;
+        return FB200_OK;
+    }
     if (name && std::strcmp(name, "hex8_owner_stores") == 0) {
         if (value != 0 && value != 1) return fail(ctx, FB200_ERR_SHAPE, "hex8_owner_stores must be 0 or 1");
         ctx->tune_owner = value;

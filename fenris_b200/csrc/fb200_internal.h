@@ -51,13 +51,12 @@ struct OrderedCopy {
 struct HostChunks {
     std::vector<int64_t> slot_off;     // num_chunks + 1
     std::vector<uint16_t> contrib;     // count * n^2, chunk c starts at c * chunk_elems * n^2
-    // per slot 4 words: [0] index of the block's first value (s^2 blk_off[node] + s k) | complete-row flag << 62,
-    // [1] row length in doubles | first contributor (relative to the chunk) << 32 | contributor count << 48, [2..3] the first 8 contributor tags
-    // (0xffff = none): one 32-byte record per slot - no dependent loads in the kernel's slot loop
-    std::vector<uint64_t> slot_rec;
+    std::vector<int32_t> slot_node;
+    std::vector<uint16_t> slot_k, slot_cbeg;
+    std::vector<uint8_t> slot_flags;   // bit 0: row node complete in the chunk (plain stores), bit 1: partition-interface row
 };
-void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_nodes,
-                       const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
+void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
+                       uint64_t num_nodes, const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
@@ -83,6 +82,8 @@ struct HostTiles {
     std::vector<uint32_t> flush;      // per tile: first the STORE segment, then the REDUCE segment, each per (row node u, coupled node v) in CSR
                                       // order: position | transposed << 11 | u << 12 | k << 19; position kTileZeroPos = the entry is 0.0
     std::vector<uint32_t> wait;       // per tile: the (lower-numbered) tiles whose stores its reductions must wait for
+    std::vector<uint64_t> colour_off;   // tile colours (empty: none): colour c = colour_tiles[colour_off[c] .. colour_off[c + 1])
+    std::vector<uint32_t> colour_tiles; // tiles grouped by colour, ascending inside a colour; tiles of one colour share no node
     std::vector<int32_t> zero_nodes;  // owner_stores: nodes whose rows no tile stores (touched by ghost elements, or by no owned element at
                                       // all): the only rows an overwriting call has to clear beforehand
     std::vector<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
@@ -110,6 +111,8 @@ struct TileLists {
     int32_t* d_nodes = nullptr;
     uint32_t* d_flush = nullptr;
     uint32_t* d_wait = nullptr;
+    uint32_t* d_colour_tiles = nullptr;  // tiles grouped by colour (HostTiles::colour_tiles); offsets on the host
+    std::vector<uint64_t> colour_off;
     uint32_t* d_flag = nullptr;        // per tile: epoch of the launch whose stores of this tile are published
     int32_t* d_zero_nodes = nullptr;   // rows to clear before an overwriting launch (owner lists)
     uint64_t zero_node_count = 0;
@@ -127,8 +130,10 @@ struct ChunkLists {
     uint64_t total_slots = 0;
     int64_t* d_slot_off = nullptr;
     uint16_t* d_contrib = nullptr;
-    uint64_t* d_slot_rec = nullptr;
-    int sdim = 0;
+    int32_t* d_slot_node = nullptr;
+    uint16_t* d_slot_k = nullptr;
+    uint16_t* d_slot_cbeg = nullptr;
+    uint8_t* d_slot_flags = nullptr;
     int32_t* d_conn_pos = nullptr;  // connectivity rows in processing order
 };
 
@@ -166,6 +171,7 @@ struct fb200_ctx {
     fb200::ChunkLists chunks;
     fb200::TileLists tiles;
     int tune_hex8_tile = -1;  // fb200_set_tuning("hex8_tile"); -1 = FB200_HEX8_TILE from the environment, else 64
+    int tune_colored_tiles = -1;  // fb200_set_tuning("hex8_colored_tiles"): COLORED scatter of Hex8 by tile colours (deterministic); -1 = on
     int tune_owner = -1;      // fb200_set_tuning("hex8_owner_stores"): first-writer stores instead of zero-fill + reductions (TileShape::owner_stores);
                               // -1 = FB200_HEX8_OWNER from the environment, else on
     uint32_t tile_epoch = 0;  // launch counter of the owner-store flags (TileLists::d_flag)

@@ -141,7 +141,10 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         // previous one left in shared memory; consecutive stages of a tile run in consecutive iterations (tables_done() between).
         auto stage0 = [&](int sl) {
             const uint32_t tn = s_tick[sl];
-            if (tn < p.num_tiles && ht < kTileHdrWords / 4) cp_async_16(small_hdr(sl) + 4 * ht, p.tile_hdr + (size_t)tn * kTileHdrWords + 4 * ht);
+            if (tn < p.num_tiles && ht < kTileHdrWords / 4) {
+                const uint32_t tile = p.tile_list ? __ldg(p.tile_list + tn) : tn;  // (a launch over the tiles of one colour)
+                cp_async_16(small_hdr(sl) + 4 * ht, p.tile_hdr + (size_t)tile * kTileHdrWords + 4 * ht);
+            }
         };
         auto stage1 = [&](int sl) {
             if (s_tick[sl] < p.num_tiles) {

@@ -14,9 +14,13 @@
 //            overwrites).  Contributors are visited in ascending element order for both (I, J) and (J, I): the result stays
 //            exactly symmetric.
 // Slots are ordered by contributor count, so the lanes of a warp run loops of equal length.
+// Multi-GPU (PEER): the slots of partition-interface rows (slot_flags bit 1) are additionally reduced into the neighbouring rank's values
+// through a peer-mapped pointer - the interface exchange of the Tet4 path (config C5) is part of the scatter, as in hex8_tile_kernel.cuh.
+// (A variant with one 32-byte record per slot - destination, row length, contributor range and the first eight tags, prefetched one
+//  slot ahead - was measured on the C5 share: 1.29 - 1.33 ms against 1.20 ms for these separate arrays; profiles/r02/README.md.)
 #pragma once
 
-template <int OP, int T, int C>
+template <int OP, int T, int C, bool PEER = false>
 __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assemble_tet4_chunk_kernel(const AssembleParams p) {
     constexpr int N = 4, D = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
@@ -65,44 +69,29 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
         }
         __syncthreads();
 
-        // ---- phase 2: one thread per slot.  A slot is one 32-byte record (chunks.cpp) holding everything but the tags beyond the eighth,
-        // and the record of the thread's NEXT slot is in flight while the current one is summed: no dependent global load in the loop
+        // ---- phase 2: one thread per slot
         const long long so = p.slot_off[chunk];
         const int U = (int)(p.slot_off[chunk + 1] - so);
+        const int npairs = ne * (N * N);
         const uint16_t* contrib = p.contrib + p0 * (uint64_t)(N * N);
-        const ulonglong2* recs = reinterpret_cast<const ulonglong2*>(p.slot_rec) + 2 * so;
-        ulonglong2 ra = make_ulonglong2(0, 0), rb = make_ulonglong2(~0ull, ~0ull);
-        if (tid < U) {
-            ra = __ldg(recs + 2 * tid);
-            rb = __ldg(recs + 2 * tid + 1);
-        }
         for (int u = tid; u < U; u += T) {
-            const ulonglong2 ca = ra, cb2 = rb;
-            if (u + T < U) {
-                ra = __ldg(recs + 2 * (u + T));
-                rb = __ldg(recs + 2 * (u + T) + 1);
-            }
-            const long long dsti = (long long)(ca.x & ((1ull << 62) - 1ull));
-            const bool st = overwrite && (ca.x >> 62) != 0ull;
-            const int rl = (int)(unsigned int)ca.y;
-            const int cb = (int)((ca.y >> 32) & 0xffffull), cnt = (int)(ca.y >> 48);
+            const int cb = p.slot_cbeg[so + u];
+            const int ce = u + 1 < U ? (int)p.slot_cbeg[so + u + 1] : npairs;
+            // slot metadata first: its latency overlaps the contributor loop
+            const int node = p.slot_node[so + u];
+            const int kpos = p.slot_k[so + u];
+            const unsigned sflags = p.slot_flags[so + u];
+            const bool st = overwrite && (sflags & 1u);
+            const long long o0 = p.blk_off[node], o1 = p.blk_off[node + 1];
             double M[D][D];
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
                 for (int j = 0; j < D; ++j) M[i][j] = 0.0;
-            unsigned long long tw = cb2.x;  // tags 0-3; then 4-7 (cb2.y); beyond the eighth from the chunk's tag list
-            unsigned tag_far = cnt > 8 ? (unsigned)__ldg(contrib + cb + 8) : 0u;
-            for (int t = 0; t < cnt; ++t) {
-                unsigned tag;
-                if (t < 8) {
-                    if (t == 4) tw = cb2.y;
-                    tag = (unsigned)(tw & 0xffffull);
-                    tw >>= 16;
-                } else {
-                    tag = tag_far;
-                    if (t + 1 < cnt) tag_far = __ldg(contrib + cb + t + 1);
-                }
+            unsigned tag_next = __ldg(contrib + cb);  // every slot has at least one contributor
+            for (int t = cb; t < ce; ++t) {
+                const unsigned tag = tag_next;
+                if (t + 1 < ce) tag_next = __ldg(contrib + t + 1);
                 const int el = tag >> 4, a = (tag >> 2) & 3, b = tag & 3;
                 const double* ga = s_g + (a * D) * C + el;
                 const double* gb = s_g + (b * D) * C + el;
@@ -116,10 +105,19 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
                         for (int j = 0; j < D; ++j) M[i][j] = fma(va[i], vb[j], M[i][j]);
                 }
             }
-            double* dst = p.values + dsti;
+            const int rl = (int)(o1 - o0) * S;
+            double* dst = p.values + ((long long)(S * S) * o0 + (long long)S * kpos);
+            double* pdst = nullptr;  // the same block in the neighbouring rank's copy of the row (identical row layout, other offset)
+            if constexpr (PEER) {
+                if (sflags & 2u) {
+                    const uint32_t pw = __ldg(p.peer_row + node);
+                    if (pw) pdst = p.peer_values[pw >> 31] + ((long long)(S * S) * (long long)((pw & 0x7fffffffu) - 1u) + (long long)S * kpos);
+                }
+            }
             if constexpr (S == 1) {
                 if (st) dst[0] = M[0][0];
                 else atomicAdd(dst, M[0][0]);
+                if (PEER && pdst) red_add_f64_sys(pdst, M[0][0]);
             } else {
                 const double tr = M[0][0] + M[1][1] + M[2][2];
 #pragma unroll
@@ -129,6 +127,7 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
                         const double v = mu * ((i == j ? tr : 0.0) + M[j][i]) + lam * M[i][j];
                         if (st) dst[i * rl + j] = v;
                         else atomicAdd(dst + i * rl + j, v);
+                        if (PEER && pdst) red_add_f64_sys(pdst + i * rl + j, v);
                     }
             }
         }

@@ -455,6 +455,40 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         }
     };
     run_pool(tiles.size(), finisher);
+    // ---- tile colours for the deterministic coloured scatter (CsrParAssembler's idea, global.rs:322-373, at tile granularity): greedy,
+    // in tile order; two tiles of a colour share no node, so a launch over one colour adds at most once to every CSR value and the
+    // launches, in colour order, fix the order of all additions.  More than 64 colours: no tile colouring (per-element colours are used)
+    {
+        std::vector<uint64_t> node_mask(num_nodes, 0);
+        std::vector<uint8_t> colour(tiles.size(), 0);
+        std::vector<uint64_t> per_colour(64, 0);
+        bool ok = true;
+        for (size_t ti = 0; ti < tiles.size() && ok; ++ti) {
+            uint64_t used = 0;
+            for (int32_t nd : tiles[ti]->nodes) used |= node_mask[nd & 0x7fffffff];
+            int c = 0;
+            while (c < 64 && ((used >> c) & 1)) ++c;
+            if (c == 64) {
+                ok = false;
+                break;
+            }
+            colour[ti] = (uint8_t)c;
+            ++per_colour[c];
+            for (int32_t nd : tiles[ti]->nodes) node_mask[nd & 0x7fffffff] |= 1ull << c;
+        }
+        out.colour_off.clear();
+        out.colour_tiles.clear();
+        if (ok && !tiles.empty()) {
+            int ncol = 0;
+            for (int c = 0; c < 64; ++c)
+                if (per_colour[c]) ncol = c + 1;
+            out.colour_off.assign(ncol + 1, 0);
+            for (int c = 0; c < ncol; ++c) out.colour_off[c + 1] = out.colour_off[c] + per_colour[c];
+            out.colour_tiles.resize(tiles.size());
+            std::vector<uint64_t> cursor(out.colour_off.begin(), out.colour_off.end() - 1);
+            for (size_t ti = 0; ti < tiles.size(); ++ti) out.colour_tiles[cursor[colour[ti]]++] = (uint32_t)ti;
+        }
+    }
     // ---- concatenate
     uint64_t tot_nodes = 0, tot_flush = 0, tot_wait = 0, tot_pos = 0;
     for (const TileOut* t : tiles) {
@@ -712,6 +746,23 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
         if (zero_entries != ht.zero_entries) return fail_check(32);
     } else if (!ht.zero_nodes.empty()) {
         return fail_check(31);
+    }
+    // tile colours: every tile exactly once, tiles of a colour node-disjoint
+    if (!ht.colour_off.empty()) {
+        if (ht.colour_tiles.size() != ntiles || ht.colour_off.back() != ntiles) return fail_check(34);
+        std::vector<uint8_t> tseen(ntiles, 0);
+        std::vector<uint32_t> stamp(num_nodes, 0xffffffffu);
+        for (size_t c = 0; c + 1 < ht.colour_off.size(); ++c)
+            for (uint64_t k = ht.colour_off[c]; k < ht.colour_off[c + 1]; ++k) {
+                const uint32_t t = ht.colour_tiles[k];
+                if (t >= ntiles || tseen[t]++) return fail_check(34);
+                const uint32_t* h = &ht.hdr[t * kTileHdrWords];
+                for (uint32_t u = 0; u < h[2]; ++u) {
+                    uint32_t& st = stamp[ht.nodes[h[4] + u] & 0x7fffffff];
+                    if (st == (uint32_t)c) return fail_check(35);
+                    st = (uint32_t)c;
+                }
+            }
     }
     stats[0] = ntiles;
     stats[1] = max_nodes;

@@ -220,3 +220,36 @@ def test_tile_owner_stores_with_ghost_elements(ctx):
         out[tile] = ctx.values_download().copy()
     _tune(ctx, "own")
     assert np.isfinite(out["own"]).all() and fo.rel_frobenius(out["own"], out["zero"]) < 1e-15
+
+
+@pytest.mark.parametrize("n,op,scramble", [(9, fo.LINEAR_ELASTIC, False), (10, fo.LAPLACE, False), (7, fo.LINEAR_ELASTIC, True), (20, fo.LINEAR_ELASTIC, False)])
+def test_colored_scatter_by_tile_colours_is_bitwise_reproducible(ctx, n, op, scramble):
+    # FB200_SCATTER_COLORED on a Hex8 space: one launch of the tile kernel per TILE colour (CsrParAssembler's colouring idea,
+    # global.rs:322-373, at tile granularity).  Fixed order inside a tile, fixed colour order: identical bits on every run.
+    m = _hex(n, 0.15, scramble)
+    ctx.space_upload(m.element_type, m.vertices(), m.connectivity())
+    ctx.assemble_pattern(1 if op == fo.LAPLACE else 3)
+    ctx.color_nodes()
+    prob = fo.Problem(fo.HEX8, m.vertices(), m.connectivity().astype(np.int64), op, params=() if op == fo.LAPLACE else (MU, LAM))
+    data = None if op == fo.LAPLACE else (MU, LAM)
+    _tune(ctx, "own")
+    runs = []
+    for fill in (1e300, 0.0, -3.0):
+        ctx.values_upload(np.full(ctx.nnz, fill))
+        ctx.assemble_into_csr_device(op, prob.weights, prob.points, data, scatter_mode=fb.SCATTER_COLORED, accumulate=False)
+        ctx.synchronize()
+        runs.append(ctx.values_download().copy())
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    assert fo.rel_frobenius(runs[0], fo.assemble_fast(prob)[2]) < TOL
+    # the per-element colours (one launch of the element kernel per colour) give the same sums in another order
+    ctx.set_tuning("hex8_colored_tiles", 0)
+    try:
+        ctx.assemble_into_csr_device(op, prob.weights, prob.points, data, scatter_mode=fb.SCATTER_COLORED, accumulate=False)
+        ctx.synchronize()
+        assert fo.rel_frobenius(ctx.values_download(), runs[0]) < 1e-14
+    finally:
+        ctx.set_tuning("hex8_colored_tiles", 1)
+    # accumulate semantics (global.rs:534)
+    ctx.assemble_into_csr_device(op, prob.weights, prob.points, data, scatter_mode=fb.SCATTER_COLORED, accumulate=True)
+    ctx.synchronize()
+    assert fo.rel_frobenius(ctx.values_download(), 2.0 * runs[0]) < TOL

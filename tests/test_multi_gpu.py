@@ -103,7 +103,7 @@ def test_slab_partition_four_ranks(exchange):
     _run(4, _worker, (10, 10, 16, 0, exchange))  # inner ranks have two neighbours (the reference generator wants cx == cy)
 
 
-def _range_worker(rank, world, uid, kind, q):
+def _range_worker(rank, world, uid, kind, exchange, q):
     """Tet4 (config C5's kernel: the chunk kernel behind a partition with ghost elements) and Hex27 (the DMMA kernel) slabs from
     partition.element_range_partition, neighbour exchange of the packed interface rows."""
     try:
@@ -133,8 +133,10 @@ def _range_worker(rank, world, uid, kind, q):
         ctx.assemble_pattern(3)
         ctx.comm_init(uid, rank, world)
         ctx.interface_set_peers(part["peers"])
+        if exchange == "p2p":
+            assert ctx.interface_enable_p2p(), "fused p2p exchange refused on a slab partition"
         ctx.values_upload(np.full(ctx.nnz, 1e300))
-        for _ in range(2):
+        for _ in range(3):
             ctx.assemble_into_csr_device(fb.LINEAR_ELASTIC, w, p, (mu, lam), scatter_mode=fb.SCATTER_ATOMIC, accumulate=False)
             ctx.interface_allreduce()
         ctx.synchronize()
@@ -163,6 +165,7 @@ def _range_worker(rank, world, uid, kind, q):
 
 
 @pytest.mark.skipif(_num_gpus() < 2, reason="needs at least two GPUs")
-@pytest.mark.parametrize("kind", ["tet4", "hex27"])
-def test_element_range_partition_equals_global(kind):
-    _run(2, _range_worker, (kind,))
+@pytest.mark.parametrize("kind,exchange", [("tet4", "p2p"), ("tet4", "peers"), ("hex27", "peers"), ("hex27", "p2p")])
+def test_element_range_partition_equals_global(kind, exchange):
+    # ("hex27", "p2p"): the Hex27 kernel has no fused exchange - with p2p enabled the packed neighbour exchange must still be used
+    _run(2, _range_worker, (kind, exchange))
