@@ -715,8 +715,8 @@ static void free_chunks(ChunkLists& cl) {
     cl.ids = nullptr;
 }
 
-template <class T>
-static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T>& h) {
+template <class T, class A>
+static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T, A>& h) {
     FB200_TRY(dev_alloc(ctx, d, h.size()));
     if (!h.empty()) FB200_CUDA(ctx, h2d_copy(ctx, *d, h.data(), h.size() * sizeof(T)));
     return FB200_OK;
@@ -845,15 +845,18 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
         return FB200_OK;
     }
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<int32_t> conn(ctx->E * 8), ids(count);
-    std::vector<uint16_t> map(ctx->E * (uint64_t)64);
-    std::vector<int64_t> blk_off(ctx->N + 1);
-    FB200_CUDA(ctx, cudaMemcpy(conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(ids.data(), d_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    SetupTimer tm;
+    BigVec<int32_t> conn(ctx->E * 8), ids(count);
+    BigVec<uint16_t> map(ctx->E * (uint64_t)64);
+    BigVec<int64_t> blk_off(ctx->N + 1);
+    FB200_CUDA(ctx, d2h_staged(ctx, conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t)));
+    FB200_CUDA(ctx, d2h_staged(ctx, ids.data(), d_ids, ids.size() * sizeof(int32_t)));
+    FB200_CUDA(ctx, d2h_staged(ctx, map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t)));
+    FB200_CUDA(ctx, d2h_staged(ctx, blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t)));
+    tm.lap("tiles: download conn / map / offsets");
     HostTiles ht;
     build_tile_lists(shape, count, ids.data(), ctx->h_order_codes.data(), conn.data(), ctx->E, ctx->E_owned, ctx->N, map.data(), blk_off.data(), ht);
+    tm.lap("tiles: build_tile_lists");
     if (ht.bank_conflict_share < 0.0 || ht.flush.size() >= (1ull << 32) || ht.nodes.size() >= (1ull << 32)) {
         tl.unusable = true;  // degenerate elements (repeated nodes) or lists beyond 32-bit offsets: keep the per-element kernel
         return FB200_OK;
@@ -871,6 +874,7 @@ static fb200_status ensure_tiles(fb200_ctx* ctx, const TileShape& shape) {
     FB200_TRY(upload_vec(ctx, &tl.d_elem, ht.elem));
     FB200_TRY(dev_alloc(ctx, &tl.d_flag, tl.num_tiles));
     FB200_CUDA(ctx, cudaMemsetAsync(tl.d_flag, 0, std::max<size_t>(tl.num_tiles, 1) * sizeof(uint32_t), ctx->stream));
+    tm.lap("tiles: upload lists");
     tl.zero_node_count = ht.zero_nodes.size();
     tl.owner = ht.owner_stores;
     tl.valid = true;

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "fb200_internal.h"
 
@@ -69,25 +70,51 @@ void morton_order(int d, int n, uint64_t N, const double* v, uint64_t E, const u
         }
     const double h = dims ? std::pow(vol / (double)E, 1.0 / dims) : 1.0;
     const double inv = h > 0.0 ? 1.0 / h : 0.0;
-    std::vector<std::pair<uint64_t, uint64_t>> keys(E);
-    for (uint64_t e = 0; e < E; ++e) {
-        uint64_t q[3] = {0, 0, 0};
-        for (int k = 0; k < d; ++k) {
-            double c = 0.0;
-            for (int a = 0; a < n; ++a) c += v[conn[e * n + a] * d + k];
-            c = (c / n - lo[k]) * inv;
-            q[k] = (uint64_t)std::min(std::max(c, 0.0), qmax);
+    // codes in parallel (the centroid gather is the expensive part), then a stable LSD radix sort of (code, element) - ties keep the
+    // element order, exactly like sorting the pairs (code, e)
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, E / 65536));
+    auto code_range = [&](uint64_t e0, uint64_t e1) {
+        for (uint64_t e = e0; e < e1; ++e) {
+            uint64_t q[3] = {0, 0, 0};
+            for (int k = 0; k < d; ++k) {
+                double c = 0.0;
+                for (int a = 0; a < n; ++a) c += v[conn[e * n + a] * d + k];
+                c = (c / n - lo[k]) * inv;
+                q[k] = (uint64_t)std::min(std::max(c, 0.0), qmax);
+            }
+            uint64_t code = 0;
+            for (int b = bits - 1; b >= 0; --b)
+                for (int k = d - 1; k >= 0; --k) code = (code << 1) | ((q[k] >> b) & 1u);
+            codes[e] = code;
         }
-        uint64_t code = 0;
-        for (int b = bits - 1; b >= 0; --b)
-            for (int k = d - 1; k >= 0; --k) code = (code << 1) | ((q[k] >> b) & 1u);
-        keys[e] = {code, e};
+    };
+    {
+        std::vector<std::thread> pool;
+        const uint64_t per = (E + nthreads - 1) / nthreads;
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(code_range, std::min<uint64_t>(E, t * per), std::min<uint64_t>(E, (t + 1) * per));
+        code_range(0, std::min<uint64_t>(E, per));
+        for (auto& th : pool) th.join();
     }
-    std::sort(keys.begin(), keys.end());
-    for (uint64_t e = 0; e < E; ++e) {
-        order[e] = (int32_t)keys[e].second;
-        codes[e] = keys[e].first;
+    uint64_t all_or = 0;
+    for (uint64_t e = 0; e < E; ++e) all_or |= codes[e];
+    std::vector<uint64_t> ka(codes), kb(E);
+    std::vector<int32_t> ia(E), ib(E);
+    for (uint64_t e = 0; e < E; ++e) ia[e] = (int32_t)e;
+    for (int shift = 0; shift < 64 && (all_or >> shift) != 0; shift += 11) {
+        uint64_t count[2049] = {0};
+        for (uint64_t e = 0; e < E; ++e) ++count[((ka[e] >> shift) & 2047u) + 1];
+        for (int b = 0; b < 2048; ++b) count[b + 1] += count[b];
+        for (uint64_t e = 0; e < E; ++e) {
+            const uint64_t pos = count[(ka[e] >> shift) & 2047u]++;
+            kb[pos] = ka[e];
+            ib[pos] = ia[e];
+        }
+        ka.swap(kb);
+        ia.swap(ib);
     }
+    order.swap(ia);
+    codes.swap(ka);
 }
 
 static fb200_status upload_order(fb200_ctx* ctx) {
@@ -152,6 +179,46 @@ __global__ void narrow_indices_kernel(const uint64_t* __restrict__ in, int32_t* 
 __global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, int64_t* __restrict__ out, uint64_t count) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = (int64_t)in[i];
+}
+
+cudaError_t d2h_staged(fb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    constexpr size_t kChunk = 16u << 20;
+    if (bytes < 4 * kChunk) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (!ctx->h_stage[b]) {
+            cudaError_t e = cudaMallocHost(&ctx->h_stage[b], kChunk);
+            if (e == cudaSuccess && !ctx->ev_stage[b]) e = cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+    auto issue = [&](size_t k) -> cudaError_t {
+        const size_t off = k * kChunk, len = std::min(kChunk, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_stage[k & 1], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, ctx->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(ctx->ev_stage[k & 1], ctx->stream);
+    };
+    cudaError_t e = issue(0);
+    for (size_t k = 0; k < nchunks && e == cudaSuccess; ++k) {
+        if (k + 1 < nchunks) e = issue(k + 1);  // (buffer (k + 1) & 1 was drained in iteration k - 1)
+        if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev_stage[k & 1]);
+        if (e == cudaSuccess) {
+            // the destination is usually fresh memory: its first touch (page faults) is the slow part, so several threads copy
+            const size_t off = k * kChunk, len = std::min(kChunk, bytes - off);
+            constexpr int kCopyThreads = 4;
+            const size_t part = (len / kCopyThreads + 4095) & ~(size_t)4095;
+            std::thread th[kCopyThreads - 1];
+            for (int t = 1; t < kCopyThreads; ++t) {
+                const size_t b0 = std::min(len, t * part), b1 = std::min(len, (t + 1) * part);
+                th[t - 1] = std::thread([=]() { std::memcpy(static_cast<char*>(dst) + off + b0, static_cast<const char*>(ctx->h_stage[k & 1]) + b0, b1 - b0); });
+            }
+            std::memcpy(static_cast<char*>(dst) + off, ctx->h_stage[k & 1], std::min(len, part));
+            for (auto& t : th) t.join();
+        }
+    }
+    return e;
 }
 
 fb200_status read_errword(fb200_ctx* ctx) {
@@ -244,6 +311,10 @@ void fb200_destroy(fb200_ctx* ctx) {
     fb200_comm_destroy_internal(ctx);
     free_space(ctx);
     dev_free(ctx->tab.d_data);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
+    }
     dev_free(ctx->d_errword);
     dev_free(ctx->d_ticket);
     dev_free(ctx->d_iface_nodes);
@@ -357,6 +428,7 @@ fb200_status fb200_space_upload(fb200_ctx* ctx, int32_t element_type, uint64_t n
     if (num_nodes >= (1ull << 31) || num_elements >= (1ull << 31) / (uint64_t)(ei.n))
         return fail(ctx, FB200_ERR_UNSUPPORTED, "mesh too large for 32-bit device indices");
     free_space(ctx);
+    SetupTimer tm;
     ctx->elem_type = element_type;
     ctx->ei = ei;
     ctx->N = num_nodes;
@@ -372,8 +444,12 @@ fb200_status fb200_space_upload(fb200_ctx* ctx, int32_t element_type, uint64_t n
     }
     ctx->has_space = ctx->has_connectivity = true;
     ctx->ragged = false;
+    tm.lap("space_upload: H2D vertices + connectivity");
     morton_order(ei.d, ei.n, num_nodes, vertices, num_elements, connectivity, ctx->h_order, ctx->h_order_codes_all);  // indices were validated above
-    return upload_order(ctx);
+    tm.lap("space_upload: Morton order (host)");
+    const fb200_status so = upload_order(ctx);
+    tm.lap("space_upload: upload order");
+    return so;
 }
 
 fb200_status fb200_space_update_vertices(fb200_ctx* ctx, const double* vertices) {

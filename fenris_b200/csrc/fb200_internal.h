@@ -2,9 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/fenris_b200.h"
@@ -58,6 +63,27 @@ struct HostChunks {
 void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
                        uint64_t num_nodes, const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
 
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big list arrays are written completely by a pool
+// of threads right after being sized, so value-initialising (and page-faulting) hundreds of MB on one thread first only costs time
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = DefaultInitAllocator<U>;
+    };
+    using std::allocator<T>::allocator;
+    template <class U>
+    void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+    }
+};
+template <class T>
+using BigVec = std::vector<T, DefaultInitAllocator<T>>;
+
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
 constexpr uint32_t kTileZeroPos = 0x7ffu;  // accumulator position of a flush word that writes 0.0 (owner rows, see below)
@@ -77,18 +103,18 @@ struct TileShape {
                            // other row is reduced into (the caller zero-fills all values first).
 };
 struct HostTiles {
-    std::vector<uint32_t> hdr;        // num_tiles * kTileHdrWords
-    std::vector<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
-    std::vector<uint32_t> flush;      // per tile: first the STORE segment, then the REDUCE segment, each per (row node u, coupled node v) in CSR
+    BigVec<uint32_t> hdr;        // num_tiles * kTileHdrWords
+    BigVec<int32_t> nodes;       // global node id | 0x80000000 when all incident elements of the node lie in the tile
+    BigVec<uint32_t> flush;      // per tile: first the STORE segment, then the REDUCE segment, each per (row node u, coupled node v) in CSR
                                       // order: position | transposed << 11 | u << 12 | k << 19; position kTileZeroPos = the entry is 0.0
-    std::vector<uint32_t> wait;       // per tile: the (lower-numbered) tiles whose stores its reductions must wait for
+    BigVec<uint32_t> wait;       // per tile: the (lower-numbered) tiles whose stores its reductions must wait for
     std::vector<uint64_t> colour_off;   // tile colours (empty: none): colour c = colour_tiles[colour_off[c] .. colour_off[c + 1])
     std::vector<uint32_t> colour_tiles; // tiles grouped by colour, ascending inside a colour; tiles of one colour share no node
     std::vector<int32_t> zero_nodes;  // owner_stores: nodes whose rows no tile stores (touched by ghost elements, or by no owned element at
                                       // all): the only rows an overwriting call has to clear beforehand
-    std::vector<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
-    std::vector<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
-    std::vector<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
+    BigVec<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
+    BigVec<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
+    BigVec<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
     bool owner_stores = false;        // the lists were built with TileShape::owner_stores
     uint64_t zero_entries = 0;        // flush words with position kTileZeroPos
     double bank_conflict_share = 0;   // diagnostic: share of accumulate accesses that collide in a shared-memory bank
@@ -221,6 +247,10 @@ struct fb200_ctx {
     double* d_source = nullptr;
     uint64_t source_capacity = 0;
 
+    // ---- pinned staging for large D2H copies of the host preprocessing (d2h_staged)
+    void* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+
     // ---- tables + deferred error word
     fb200::DeviceTables tab;
     unsigned long long* d_ticket = nullptr;   // dynamic work counter of the element kernels
@@ -299,6 +329,10 @@ inline cudaError_t h2d_copy(fb200_ctx* ctx, void* dst, const void* src, size_t b
     return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
 }
 
+// D2H copy of a large device array into pageable host memory through two pinned staging buffers (a pageable cudaMemcpy runs at a few
+// GB/s; this one at the speed of the host memcpy): chunk k + 1 crosses PCIe while chunk k is copied out of the staging buffer
+cudaError_t d2h_staged(fb200_ctx* ctx, void* dst, const void* src, size_t bytes);
+
 // after a kernel launch
 fb200_status check_launch(fb200_ctx* ctx, const char* name);
 
@@ -332,6 +366,18 @@ fb200_status assemble_state_dependent_list(fb200_ctx* ctx, const fb200_operator*
                                            const int32_t* d_list, uint64_t count, int plain);
 
 inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
+
+// FB200_DEBUG_SETUP=1: wall-clock of the host-side preprocessing steps on stderr (where does setup time go?)
+struct SetupTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool on = std::getenv("FB200_DEBUG_SETUP") != nullptr;
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fb200 setup] %-40s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // offsets[0 .. count] of a caller's CSR-like structure: starts at 0, never decreases (checked on the host before any kernel indexes with it)
 inline bool offsets_well_formed(const uint64_t* offsets, uint64_t count) {

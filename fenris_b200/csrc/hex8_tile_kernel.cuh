@@ -212,16 +212,16 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             const uint32_t* hdr = small_hdr(sl);
             const int nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
             if (valid) {
-                // row table of this tile's flush (used in the next iteration): address of the first value of node u's rows; row length, and for a
-                // partition-interface node (PEER) its block-row offset on the neighbouring rank + 1 | neighbour slot << 31 in the high word
+                // row table of this tile's flush (used in the next iteration): first value of node u's rows and the row length; for a
+                // partition-interface node (PEER) also its block-row offset on the neighbouring rank + 1 | neighbour slot << 31
                 if (ht < nn) {
                     const long long* off = big_off((int)(it % 3u));
                     const long long o0 = off[2 * ht], o1 = off[2 * ht + 1];
-                    long long* fr = buf_frow(b);
-                    fr[2 * ht] = (long long)(p.values + (long long)BS * o0);
-                    unsigned long long w1 = (unsigned long long)(unsigned int)((int)(o1 - o0) * S);
-                    if constexpr (PEER) w1 |= (unsigned long long)p.peer_row[small_ids(sl)[ht] & 0x7fffffff] << 32;
-                    fr[2 * ht + 1] = (long long)w1;
+                    // one 64-bit word per node (a 64-bit shared load costs a quarter of the wavefronts of a 128-bit one): index of the first
+                    // value (48 bits) | row length in doubles << 48 (block rows are < 8192 nodes: tiles.cpp); PEER: a second table of words
+                    unsigned long long* fr = reinterpret_cast<unsigned long long*>(buf_frow(b));
+                    fr[ht] = (unsigned long long)((long long)BS * o0) | ((unsigned long long)(unsigned int)((int)(o1 - o0) * S) << 48);
+                    if constexpr (PEER) reinterpret_cast<uint32_t*>(fr + MAXN)[ht] = p.peer_row[small_ids(sl)[ht] & 0x7fffffff];
                 }
                 // pull this tile's flush list into L2 (it is read in the next iteration)
                 const char* f0 = reinterpret_cast<const char*>(p.tile_flush + hdr[5]);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                 const uint32_t* fl = p.tile_flush + ph[5];
                 const uint32_t items = ph[6], store_items = ph[8];  // (entries)
                 const double* pacc = smem + nb * L::ACC;
-                const longlong2* prow = reinterpret_cast<const longlong2*>(buf_frow(nb));
+                const unsigned long long* prow = reinterpret_cast<const unsigned long long*>(buf_frow(nb));
                 // entries [e0, e1) of the list.  A warp takes blocks of 32 entries = SUB * 32 items; in sub-iteration m lane l handles
                 // item 32 m + l of the block = entry fe[m], column fj[m] (per-lane constants: no division in the loop), so that an
                 // instruction covers 32 consecutive doubles of a run of neighbouring node blocks.  STORE: plain stores; else reductions
@@ -262,15 +262,16 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                             const uint32_t a = w[m];
                             if (a == 0xffffffffu) continue;  // past the end of the range (no list word is all ones: u <= 124)
                             const int j = fj[m];
-                            const longlong2 rt = prow[(a >> 12) & 0x7fu];
-                            const int rl = (int)(unsigned int)(unsigned long long)rt.y;
+                            const uint32_t un = (a >> 12) & 0x7fu;
+                            const unsigned long long rt = prow[un];
+                            const int rl = (int)(rt >> 48);
                             const bool tr = (a & 0x800u) != 0u;
                             const uint32_t apos = a & 0x7ffu;
                             const bool zero = apos == kTileZeroPos;  // an owner writes 0.0 where it has no contribution
                             const double* src = pacc + (int)(zero ? 0u : apos) * BS + (tr ? j * S : j);
                             const int sstride = tr ? 1 : S;
                             const int col = S * (int)(a >> 19) + j;
-                            double* dst = reinterpret_cast<double*>(rt.x) + col;
+                            double* dst = p.values + ((long long)(rt & 0xffffffffffffull) + (long long)col);
                             double v[S];
 #pragma unroll
                             for (int i = 0; i < S; ++i) v[i] = zero ? 0.0 : src[i * sstride];
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
 #pragma unroll
                                 for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
                                 if constexpr (PEER) {
-                                    const uint32_t pw = (uint32_t)((unsigned long long)rt.y >> 32);
+                                    const uint32_t pw = reinterpret_cast<const uint32_t*>(prow + MAXN)[un];
                                     if (pw) {
                                         double* pd = p.peer_values[pw >> 31] + ((long long)BS * (long long)((pw & 0x7fffffffu) - 1u) + (long long)col);
 #pragma unroll

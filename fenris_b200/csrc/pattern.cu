@@ -461,6 +461,14 @@ fb200_status fb200_assemble_pattern(fb200_ctx* ctx, int32_t sdim, uint64_t* num_
     if (sdim < 1 || sdim > 3) return fail(ctx, FB200_ERR_SHAPE, "solution_dim must be 1, 2 or 3");
     FB200_CUDA(ctx, cudaSetDevice(ctx->device));
     free_pattern(ctx);
+    struct PatternLap {
+        SetupTimer tm;
+        cudaStream_t s;
+        ~PatternLap() {
+            if (tm.on) cudaStreamSynchronize(s);
+            tm.lap("assemble_pattern (device)");
+        }
+    } pattern_lap{SetupTimer(), ctx->stream};
     FB200_TRY(build_adjacency(ctx));
     const uint64_t N = ctx->N;
     const ConnView cv = conn_view(ctx);

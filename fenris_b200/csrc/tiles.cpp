@@ -69,6 +69,7 @@ struct Builder {
     HostTiles& out;
     uint64_t conflicts = 0, accesses = 0;
     bool degenerate = false;
+    double sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // FB200_DEBUG_SETUP: seconds per section of build_one
 
     struct RowEntry {
         uint16_t k;
@@ -109,6 +110,12 @@ struct Builder {
 
     bool build_one(uint64_t p0, int ne, TileOut& t) {
         constexpr int n = 8, n2 = 64;
+        auto tp = std::chrono::steady_clock::now();
+        auto lap = [&](int k) {
+            const auto t1 = std::chrono::steady_clock::now();
+            sec[k] += std::chrono::duration<double>(t1 - tp).count();
+            tp = t1;
+        };
         // ---- nodes
         nodes.clear();
         for (int el = 0; el < ne; ++el) {
@@ -131,7 +138,8 @@ struct Builder {
         const int nn = (int)nodes.size();
         if (nn > shape.max_nodes) return false;
         ln.assign((size_t)ne * n, 0);
-        node_elems.assign(nn, {});
+        if ((int)node_elems.size() < nn) node_elems.resize(nn);  // (inner vectors keep their capacity from tile to tile)
+        for (int u = 0; u < nn; ++u) node_elems[u].clear();
         for (int el = 0; el < ne; ++el) {
             const uint64_t e = elem_at(p0 + el);
             for (int a = 0; a < n; ++a) {
@@ -142,8 +150,10 @@ struct Builder {
             }
         }
         if (degenerate) return true;
+        lap(0);
         // ---- rows: coupled nodes of every tile node, ordered by their position k in the global block row
-        rows.assign(nn, {});
+        if ((int)rows.size() < nn) rows.resize(nn);
+        for (int u = 0; u < nn; ++u) rows[u].clear();
         for (int el = 0; el < ne; ++el) {
             const uint64_t e = elem_at(p0 + el);
             for (int a = 0; a < n; ++a)
@@ -158,6 +168,7 @@ struct Builder {
             for (const RowEntry& x : r) nslots += x.v >= u;
         }
         if (nslots > shape.max_slots) return false;
+        lap(1);
         // ---- bank-aware accumulator positions
         static const int kFaces[2][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}};
         static const int kStripes[2][4] = {{0, 2, 4, 6}, {1, 3, 5, 7}};
@@ -197,6 +208,7 @@ struct Builder {
             const auto& r = rows[u];
             return *std::lower_bound(r.begin(), r.end(), k, [](const RowEntry& x, uint16_t kk) { return x.k < kk; });
         };
+        lap(2);
         // ---- flush list + node list
         t.p0 = p0;
         t.ne = ne;
@@ -221,6 +233,7 @@ struct Builder {
                 if (x.k >= (1u << kTileKBits)) degenerate = true;
                 t.flush.push_back(pos | (tr << 11) | ((uint32_t)u << 12) | ((uint32_t)x.k << 19));
             }
+        lap(3);
         // ---- schedule: greedy node-disjoint colouring inside the tile; every colour class is cut into rounds of at most
         // `warps` elements; rounds are padded to `warps` schedule positions (padding: node byte 0 = 0xff, no accumulators)
         std::vector<uint64_t> node_mask(nn, 0);
@@ -277,6 +290,7 @@ struct Builder {
                 }
         }
         pad_round();
+        lap(4);
         t.rounds = (uint32_t)(t.elem.size() / gw);
         if (t.rounds > 255) return false;  // bound asserted by the self test (cannot happen with <= 64 elements per tile)
         return true;
@@ -354,6 +368,7 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
                       uint64_t num_elements, uint64_t num_owned, uint64_t num_nodes, const uint16_t* blockmap, const int64_t* blk_off,
                       HostTiles& out) {
     constexpr int n = 8;
+    SetupTimer tm;
     // incidences of every node over ALL elements of the space - also the ghost elements of a partition, which are in the pattern
     // but are not assembled here: a node is complete only if every element it belongs to is processed inside one tile (then
     // the flush writes every entry of its rows)
@@ -415,6 +430,8 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         }
         conflicts += b.conflicts;
         accesses += b.accesses;
+        if (std::getenv("FB200_DEBUG_SETUP"))
+            std::fprintf(stderr, "[fb200 setup]     worker: nodes %.3f rows %.3f positions %.3f flush %.3f schedule %.3f s\n", b.sec[0], b.sec[1], b.sec[2], b.sec[3], b.sec[4]);
     };
     const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     auto run_pool = [&](uint64_t work_items, const std::function<void()>& fn) {
@@ -424,7 +441,9 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         fn();
         for (auto& th : pool) th.join();
     };
+    tm.lap("  tile lists: degrees + candidates");
     run_pool(cand.size(), worker);
+    tm.lap("  tile lists: pass 1 (per tile)");
     if (degenerate.load()) {  // elements with repeated nodes (or huge block rows): the caller keeps the per-element kernel
         out.hdr.clear();
         out.bank_conflict_share = -1.0;
@@ -454,7 +473,9 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
                 finish_flush(*tiles[ti], (uint32_t)ti, out.owner_stores, owner_tile.data(), degree.data(), degree_owned.data(), blk_off);
         }
     };
+    tm.lap("  tile lists: owners");
     run_pool(tiles.size(), finisher);
+    tm.lap("  tile lists: pass 2 (segments)");
     // ---- tile colours for the deterministic coloured scatter (CsrParAssembler's idea, global.rs:322-373, at tile granularity): greedy,
     // in tile order; two tiles of a colour share no node, so a launch over one colour adds at most once to every CSR value and the
     // launches, in colour order, fix the order of all additions.  More than 64 colours: no tile colouring (per-element colours are used)
@@ -489,6 +510,7 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
             for (size_t ti = 0; ti < tiles.size(); ++ti) out.colour_tiles[cursor[colour[ti]]++] = (uint32_t)ti;
         }
     }
+    tm.lap("  tile lists: tile colours");
     // ---- concatenate
     uint64_t tot_nodes = 0, tot_flush = 0, tot_wait = 0, tot_pos = 0;
     for (const TileOut* t : tiles) {
@@ -497,28 +519,47 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         tot_wait += t->wait.size();
         tot_pos += t->elem.size();
     }
-    out.hdr.reserve(tiles.size() * kTileHdrWords);
-    out.nodes.reserve(tot_nodes);
-    out.flush.reserve(tot_flush);
-    out.wait.reserve(tot_wait);
-    out.lnodes.reserve(tot_pos * n);
-    out.emap.reserve(tot_pos * n * n);
-    out.elem.reserve(tot_pos);
-    for (const TileOut* tp : tiles) {
-        const TileOut& t = *tp;
-        const uint32_t hdr[kTileHdrWords] = {(uint32_t)out.elem.size(),  t.rounds, (uint32_t)t.nodes.size(), t.P, (uint32_t)out.nodes.size(),
-                                             (uint32_t)out.flush.size(), (uint32_t)t.flush.size(), (uint32_t)t.ne, t.n_store,
-                                             (uint32_t)out.wait.size(),  (uint32_t)t.wait.size(), t.flags, t.n_publish, 0u, 0u, 0u};
-        out.hdr.insert(out.hdr.end(), hdr, hdr + kTileHdrWords);
-        out.nodes.insert(out.nodes.end(), t.nodes.begin(), t.nodes.end());
-        out.flush.insert(out.flush.end(), t.flush.begin(), t.flush.end());
-        out.wait.insert(out.wait.end(), t.wait.begin(), t.wait.end());
-        out.lnodes.insert(out.lnodes.end(), t.lnodes.begin(), t.lnodes.end());
-        out.emap.insert(out.emap.end(), t.emap.begin(), t.emap.end());
-        out.elem.insert(out.elem.end(), t.elem.begin(), t.elem.end());
-        out.zero_entries += t.zero_entries;
+    // offsets of every tile in the output arrays (prefix sums), then the copies in parallel
+    const size_t T = tiles.size();
+    std::vector<uint64_t> o_nodes(T + 1, 0), o_flush(T + 1, 0), o_wait(T + 1, 0), o_pos(T + 1, 0);
+    for (size_t ti = 0; ti < T; ++ti) {
+        o_nodes[ti + 1] = o_nodes[ti] + tiles[ti]->nodes.size();
+        o_flush[ti + 1] = o_flush[ti] + tiles[ti]->flush.size();
+        o_wait[ti + 1] = o_wait[ti] + tiles[ti]->wait.size();
+        o_pos[ti + 1] = o_pos[ti] + tiles[ti]->elem.size();
+        out.zero_entries += tiles[ti]->zero_entries;
     }
+    (void)tot_nodes, (void)tot_flush, (void)tot_wait, (void)tot_pos;
+    out.hdr.resize(T * kTileHdrWords);
+    out.nodes.resize(o_nodes[T]);
+    out.flush.resize(o_flush[T]);
+    out.wait.resize(o_wait[T]);
+    out.lnodes.resize(o_pos[T] * n);
+    out.emap.resize(o_pos[T] * n * n);
+    out.elem.resize(o_pos[T]);
+    next.store(0);
+    auto copier = [&]() {
+        for (;;) {
+            const uint64_t t0 = next.fetch_add(64);
+            if (t0 >= T) break;
+            for (uint64_t ti = t0; ti < std::min<uint64_t>(T, t0 + 64); ++ti) {
+                const TileOut& t = *tiles[ti];
+                const uint32_t hdr[kTileHdrWords] = {(uint32_t)o_pos[ti],   t.rounds, (uint32_t)t.nodes.size(), t.P, (uint32_t)o_nodes[ti],
+                                                     (uint32_t)o_flush[ti], (uint32_t)t.flush.size(), (uint32_t)t.ne, t.n_store,
+                                                     (uint32_t)o_wait[ti],  (uint32_t)t.wait.size(), t.flags, t.n_publish, 0u, 0u, 0u};
+                std::copy(hdr, hdr + kTileHdrWords, out.hdr.begin() + ti * kTileHdrWords);
+                std::copy(t.nodes.begin(), t.nodes.end(), out.nodes.begin() + o_nodes[ti]);
+                std::copy(t.flush.begin(), t.flush.end(), out.flush.begin() + o_flush[ti]);
+                std::copy(t.wait.begin(), t.wait.end(), out.wait.begin() + o_wait[ti]);
+                std::copy(t.lnodes.begin(), t.lnodes.end(), out.lnodes.begin() + o_pos[ti] * n);
+                std::copy(t.emap.begin(), t.emap.end(), out.emap.begin() + o_pos[ti] * n * n);
+                std::copy(t.elem.begin(), t.elem.end(), out.elem.begin() + o_pos[ti]);
+            }
+        }
+    };
+    run_pool(T, copier);
     out.bank_conflict_share = accesses.load() ? (double)conflicts.load() / (double)accesses.load() : 0.0;
+    tm.lap("  tile lists: concatenate");
 }
 
 }  // namespace fb200
