@@ -974,7 +974,22 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
     static const int env_static = std::getenv("FB200_TILE_STATIC") ? std::atoi(std::getenv("FB200_TILE_STATIC")) : -1;
     p.tile_static = env_static >= 0 ? env_static : (p.tile_epoch != 0 ? 1 : 0);
     FB200_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned long long), ctx->stream));
-    kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+    if (p.tile_static && p.tile_epoch) {
+        // round-robin tiles + waits between tiles: every CTA must be resident (with the ticket a waited-for tile is always held by a
+        // running CTA; here tile c + k CTAs is held by CTA c whether it runs or not).  A cooperative launch guarantees that or fails;
+        // then the ticket schedule is used - slower with waits, but free of that requirement.
+        void* args[] = {(void*)&p};
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)kernel, dim3(blocks), dim3(THREADS), args, smem, ctx->stream);
+        if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorNotSupported || ce == cudaErrorLaunchOutOfResources) {
+            cudaGetLastError();
+            p.tile_static = 0;
+            kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+        } else if (ce != cudaSuccess) {
+            return cuda_fail(ctx, ce, "cudaLaunchCooperativeKernel(assemble_hex8_tile_kernel)");
+        }
+    } else {
+        kernel<<<blocks, THREADS, smem, ctx->stream>>>(p);
+    }
     if (debug & 64) {  // diagnostics of the owner-store waits (hex8_tile_kernel.cuh)
         unsigned long long dc[16];
         cudaStreamSynchronize(ctx->stream);
