@@ -1053,13 +1053,13 @@ static fb200_status launch_hex8_tile(fb200_ctx* ctx, AssembleParams& p, bool* us
     return launch_hex8_tile_t<OP, 128, 1216>(ctx, p, shape, used);
 }
 
-// Hex27: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh)
-template <int OP, int MODE>
+// Hex27 / Hex20 / Tet10: one CTA per element, DMMA node-block contraction (hex27_mma_kernel.cuh, templated on the node counts)
+template <int N, int NG, int OP, int MODE>
 static fb200_status launch_hex27_mma(fb200_ctx* ctx, AssembleParams& p) {
     FB200_TRY(clear_values_if_pending(ctx));
     if (p.count == 0) return FB200_OK;
-    const size_t smem = hex27_smem_bytes<OP>(p.nq);
-    auto kernel = assemble_hex27_mma_kernel<OP, MODE>;
+    const size_t smem = hex27_smem_bytes<OP, N>(p.nq);
+    auto kernel = assemble_hex27_mma_kernel<OP, MODE, N, NG>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     FB200_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kH27Threads, smem));
@@ -1139,9 +1139,18 @@ static fb200_status launch_element_parallel(fb200_ctx* ctx, AssembleParams& p) {
             }
         }
     }
-    if constexpr (N == 27 && NG == 8 && D == 3) {
+    if constexpr ((N == 27 || N == 20) && NG == 8 && D == 3) {
+        // the dense high-order contraction on the FP64 tensor pipe: Hex27 (81 x 81) and Hex20 (60 x 60)
         static const bool force_v1 = std::getenv("FB200_HEX27_V1") != nullptr;
-        if (p.uniform && p.nq <= kH27GQ && !force_v1) return launch_hex27_mma<OP, MODE>(ctx, p);
+        if (p.uniform && p.nq <= kH27GQ && !force_v1) return launch_hex27_mma<N, NG, OP, MODE>(ctx, p);
+    }
+    if constexpr (N == 10 && NG == 4 && D == 3) {
+        // Tet10 (30 x 30 K_e, 4 points = one k-step) also instantiates the tensor-pipe kernel, but a CTA of 10 warps per element is too much
+        // machinery for it: measured 2.86 ms against 1.78 ms for the generic element kernel on 324 000 elements (profiles/r02/README.md),
+        // so the generic kernel stays the default - north_star reserves the tensor path for dense >= 60 x 60 contractions anyway.
+        // FB200_TET10_MMA=1 selects the DMMA instantiation (parity-tested the same way).
+        static const bool use_mma = std::getenv("FB200_TET10_MMA") != nullptr;
+        if (p.uniform && p.nq <= kH27GQ && use_mma) return launch_hex27_mma<N, NG, OP, MODE>(ctx, p);
     }
     return launch_elements<N, NG, D, OP, MODE>(ctx, p);
 }

@@ -1,5 +1,8 @@
-// Hex27 (tri-quadratic, 27 nodes, 81 x 81 K_e) assembly kernel: one CTA of 10 warps per element, node-block contraction on the FP64
-// tensor pipe (included by assemble.cu; north_star: "tensor cores only on the high-order Hex20/Hex27/Tet10 path").
+// High-order element assembly kernel - Hex27 (tri-quadratic, 81 x 81 K_e), Hex20 (serendipity, 60 x 60) and Tet10 (quadratic, 30 x 30):
+// one CTA of 10 warps per element, node-block contraction on the FP64 tensor pipe (included by assemble.cu; north_star: "tensor cores
+// only on the high-order Hex20/Hex27/Tet10 path").  Template parameters N (nodes) and NG (vertices of the embedded linear element that
+// carries the geometry: 8 = Hex8, 4 = Tet4); the description below is written for Hex27, the other two differ in the counts only
+// (Hex20: 3 node tiles = 6 tile pairs, rows of 60; Tet10: 2 tiles = 3 pairs, 4 points = one k-step, rows of 30, constant Jacobian).
 //
 // Reference semantics (InteractiveComputerGraphics/fenris @ 7181b15): assemble_element_elliptic_matrix elliptic.rs:361-439;
 // Hex27 is SUB-parametric - the Jacobian comes from the embedded Hex8 of the first 8 vertices (hexahedron.rs:318-335) - and the
@@ -23,42 +26,49 @@ constexpr int kH27GQ = 28;                 // point stride of G (== 12 mod 16: c
 constexpr int kH27GC = 32 * kH27GQ + 4;    // component stride of G
 constexpr int kH27Threads = 320;
 
-template <int OP>
-__host__ __device__ constexpr int hex27_kstride() { return OP == FB200_LAPLACE ? 29 : 83; }
+template <int OP, int N = 27>
+__host__ __device__ constexpr int hex27_kstride() { return (OP == FB200_LAPLACE ? N : 3 * N) + 2; }  // odd row stride of the staged K_e (Hex27: 29 / 83)
 
-template <int OP>
+template <int N>
+__host__ __device__ constexpr int hex27_mapstride() { return (N * N + 7) & ~7; }  // u16 map of one element, padded (Hex27: 736)
+
+template <int OP, int N = 27>
 __host__ __device__ inline size_t hex27_smem_bytes(int nq) {
     constexpr int S = OP == FB200_LAPLACE ? 1 : 3;
-    size_t doubles = (size_t)nq * 81 + 3 * kH27GC + (size_t)(27 * S) * hex27_kstride<OP>() + 2 * 24 /* X */ + 2 * 28 /* base */;
-    return doubles * 8 + 2 * 28 * 4 /* rowlen */ + 2 * 736 * 2 /* map */ + 16;
+    size_t doubles = (size_t)nq * (N * 3) + 3 * kH27GC + (size_t)(N * S) * hex27_kstride<OP, N>() + 2 * 24 /* X */ + 2 * 28 /* base */;
+    return doubles * 8 + 2 * 28 * 4 /* rowlen */ + 2 * hex27_mapstride<N>() * 2 /* map */ + 16;
 }
 
 // Software pipeline of one CTA over its elements e_0, e_1, ... (dynamic tickets):
 //     | P2(j): DMMA + epilogue, all 10 warps | sync A | warps 0-3: P1(j+1) geometry, then the global loads of P0(j+2)   | sync B | P0(j+2) -> smem |
 //     |                                      |        | warps 4-9: P3(j) scatter (the long, reduction-throughput-bound phase) |        |                 |
 // so the dependent global loads (connectivity -> row offsets / vertices) and the geometry never sit on the critical path.
-template <int OP, int MODE>
+template <int OP, int MODE, int N = 27, int NG = 8>
 __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(const AssembleParams p) {
-    constexpr int N = 27, D = 3, NG = 8;
+    constexpr int D = 3;
     constexpr int S = OP == FB200_LAPLACE ? 1 : D;
     constexpr int SN = S * N;
-    constexpr int KST = hex27_kstride<OP>();
+    constexpr int KST = hex27_kstride<OP, N>();
+    constexpr int NT = (N + 7) / 8, NPAIRS = NT * (NT + 1) / 2;  // node tiles of 8 and tile pairs (ta <= tb): one warp each
+    constexpr int MAPS = hex27_mapstride<N>();
+    constexpr int MAPK = (N * N + 127) / 128;                   // map entries per loader thread
+    static_assert(N <= 28 && NPAIRS <= kH27Threads / 32 && NG * D <= 24 && (NG == 8 || NG == 4), "one warp per tile pair, tables sized for <= 28 nodes");
     constexpr int GEO_THREADS = 128, SCAT_WARPS = kH27Threads / 32 - 4;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const int nq = p.nq;  // <= 28
     const int ksteps = (nq + 3) >> 2;
-    double* s_gref = smem;                       // [nq][27][3]
-    double* s_G = s_gref + nq * 81;              // [3][32][28] (+4 per component)
+    double* s_gref = smem;                       // [nq][N][3]
+    double* s_G = s_gref + nq * (N * 3);         // [3][32][28] (+4 per component)
     double* s_K = s_G + 3 * kH27GC;              // [SN][KST]
     double* s_X = s_K + SN * KST;                // [2][8][3]
     long long* s_base = reinterpret_cast<long long*>(s_X + 48);  // [2][28]
     int* s_rowlen = reinterpret_cast<int*>(s_base + 56);          // [2][28]
-    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_rowlen + 56); // [2][736]
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(s_rowlen + 56); // [2][MAPS]
     __shared__ unsigned int s_tk[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < nq * 81; i += kH27Threads) s_gref[i] = p.tab[3 * nq + nq * NG * D + i];
+    for (int i = tid; i < nq * (N * 3); i += kH27Threads) s_gref[i] = p.tab[3 * nq + nq * NG * D + i];
     for (int i = tid; i < 3 * kH27GC; i += kH27Threads) s_G[i] = 0.0;
 
     // ---- geometry role (warps 0..3)
@@ -79,9 +89,16 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
 
     // ---- block role: warp -> tile pair (ta <= tb)
     int ta = 0, tb = warp;
-    if (warp >= 4) { ta = 1; tb = warp - 3; }
-    if (warp >= 7) { ta = 2; tb = warp - 5; }
-    if (warp >= 9) { ta = 3; tb = 3; }
+    {
+        int rem = NT;
+        while (rem > 0 && tb >= rem) {  // pairs in the order (0,0) .. (0,NT-1), (1,1) .. : warp >= NPAIRS has no pair
+            tb -= rem;
+            ++ta;
+            --rem;
+        }
+        tb += ta;
+    }
+    const bool has_pair = warp < NPAIRS;
     const int fg = lane >> 2, ft = lane & 3;
     const int na = 8 * ta + fg, nb0 = 8 * tb + 2 * ft;  // this lane's blocks: (na, nb0), (na, nb0 + 1)
     const double mu = p.mu, lam = p.lam;
@@ -91,7 +108,7 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
         long long base;
         int rowlen;
         double x;
-        uint16_t m[6];
+        uint16_t m[MAPK];
     };
     auto p0_load = [&](uint64_t pos, P0Regs& r) {
         const uint64_t e = p.elem_list ? (uint64_t)p.elem_list[pos] : pos;
@@ -108,9 +125,9 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
             r.x = p.vertices[(uint64_t)en[a] * D + i];
         }
         if (MODE != MODE_DUMP) {
-            const uint16_t* mp16 = p.blockmap + e * (uint64_t)(N * N);  // 729 u16: element rows are 2-byte aligned only
+            const uint16_t* mp16 = p.blockmap + e * (uint64_t)(N * N);  // N^2 u16: element rows are 2-byte aligned only
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < MAPK; ++k) {
                 const int i = tid + k * GEO_THREADS;
                 r.m[k] = i < N * N ? mp16[i] : (uint16_t)0;
             }
@@ -127,16 +144,16 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
         }
         if (MODE != MODE_DUMP) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < MAPK; ++k) {
                 const int i = tid + k * GEO_THREADS;
-                if (i < N * N) s_map[buf * 736 + i] = r.m[k];
+                if (i < N * N) s_map[buf * MAPS + i] = r.m[k];
             }
         }
     };
     auto geometry = [&](int buf, uint64_t pos) {
         const double* sx = s_X + buf * 24;
         double Jr[D];
-        {
+        if constexpr (NG == 8) {
             double lo[D], hi[D];
             const double x0 = sx[gi], x4 = sx[4 * D + gi];
 #pragma unroll
@@ -155,6 +172,15 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) Jr[j] = lo[j] + hi[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) Jr[j] = sx[gi] * R[0][j];
+#pragma unroll
+            for (int a = 1; a < NG; ++a) {
+                const double xa = sx[a * D + gi];
+#pragma unroll
+                for (int j = 0; j < D; ++j) Jr[j] = fma(xa, R[a][j], Jr[j]);
+            }
         }
         double r1[D], r2[D];
 #pragma unroll
@@ -177,9 +203,9 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
 #pragma unroll
         for (int j = 0; j < D; ++j) c[j] *= r;
         if (gact && s4 < 3) {
-            const double* tr = s_gref + gq * 81;
+            const double* tr = s_gref + gq * (N * 3);
             double* go = s_G + gi * kH27GC + gq;
-#pragma unroll 9
+#pragma unroll (N % 9 == 0 ? 9 : 10)
             for (int a = 0; a < N; ++a) go[a * kH27GQ] = fma(c[2], tr[a * D + 2], fma(c[1], tr[a * D + 1], c[0] * tr[a * D]));
         }
     };
@@ -209,7 +235,7 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
         // here: s_G = G(e_j), buffer cur = P0(e_j), buffer cur^1 = P0(e_{j+1}) when pos_n is valid
         if (tid == 0) s_tk[cur] = atomicAdd(p.ticket32, 1u);  // e_{j+2}; read after sync A
         // ---- P2: S = G G^T for this warp's tile pair, epilogue, stage K_e
-        {
+        if (has_pair) {
             double M0[S == 1 ? 1 : D][S == 1 ? 1 : D], M1[S == 1 ? 1 : D][S == 1 ? 1 : D];
 #pragma unroll
             for (int m = 0; m < (S == 1 ? 1 : D); ++m)
@@ -285,21 +311,23 @@ __global__ void __launch_bounds__(kH27Threads, 2) assemble_hex27_mma_kernel(cons
             } else {
                 // warp w6 takes K_e rows w6, w6 + 6, ...; lane = column within a third of the row (27 columns = 9 node blocks): the
                 // lane's (block, component) split is loop invariant and the row's (node, component) advances without divisions
-                constexpr int SEG = S == 1 ? 1 : 3;          // instructions per row
-                const int lb = lane / S, lj = lane - lb * S;  // lane < 27: block lb (+ 9 per segment), component lj
+                constexpr int SEG = (SN + 31) / 32;          // instructions per row (Hex27: 3 x 27 columns, Hex20: 2 x 30, Tet10: 1 x 30)
+                static_assert(N % SEG == 0 && SN / SEG <= 32, "a K_e row splits into SEG equal segments of whole node blocks");
+                constexpr int LANES = SN / SEG;              // columns per instruction
+                const int lb = lane / S, lj = lane - lb * S;  // lane < LANES: block lb (+ N / SEG per segment), component lj
                 const long long* sb = s_base + cur * 28;
                 const int* sr = s_rowlen + cur * 28;
-                const uint16_t* sm = s_map + cur * 736;
+                const uint16_t* sm = s_map + cur * MAPS;
                 int a = w6 / S, i = w6 - a * S;
                 for (int r = w6; r < SN; r += SCAT_WARPS) {
-                    if (lane < N) {
+                    if (lane < LANES) {
                         double* rowp = p.values + (sb[a] + (long long)i * sr[a] + lj);
                         const uint16_t* mrow = sm + a * N + lb;
                         const double* krow = s_K + r * KST + lane;
 #pragma unroll
                         for (int sg = 0; sg < SEG; ++sg) {
                             double* dst = rowp + S * (int)mrow[sg * (N / SEG)];
-                            const double v = krow[sg * N];
+                            const double v = krow[sg * LANES];
                             if (MODE == MODE_ATOMIC) atomicAdd(dst, v);
                             else *dst += v;
                         }

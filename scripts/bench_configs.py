@@ -104,6 +104,10 @@ def main():
             mesh, op, data, sdim, name = fb.hex27_mesh_from(fb.create_unit_box_uniform_hex_mesh_3d(63)), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C4 Hex27 elasticity 63^3 cells"
         elif cfg == "c5":
             mesh, op, data, sdim, name = fb.create_unit_box_uniform_tet_mesh_3d(80), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C5 share: Tet4 elasticity 80^3 cells (1/8 of 161^3)"
+        elif cfg == "hex20":  # north_star's high-order tensor path: Hex20 (60 x 60 K_e) on the 63^3 cube
+            mesh, op, data, sdim, name = fb.hex20_mesh_from(fb.create_unit_box_uniform_hex_mesh_3d(63)), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "Hex20 elasticity 63^3 cells"
+        elif cfg == "tet10":  # Tet10 (30 x 30 K_e) on the 30^3 BCC box (324 000 tets)
+            mesh, op, data, sdim, name = fb.tet10_mesh_from(fb.create_unit_box_uniform_tet_mesh_3d(30)), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "Tet10 elasticity 30^3 cells"
         elif cfg == "c3":
             mesh, op, data, sdim, name = fb.create_unit_box_uniform_hex_mesh_3d(126), fb.LINEAR_ELASTIC, (lame.mu, lame.lambda_), 3, "C3 Hex8 elasticity 126^3"
         elif cfg == "cg":  # Jacobi-PCG iterations on the device-resident C3 elasticity matrix
