@@ -356,8 +356,12 @@ fb200_status fb200_interface_enable_p2p(fb200_ctx* ctx) {
     constexpr size_t HDR = 17;
     std::vector<int64_t> send(np * HDR + 2 * total, 0), recv(np * HDR + 2 * total, 0);
     cudaIpcMemHandle_t hv, hs;
-    FB200_CUDA(ctx, cudaIpcGetMemHandle(&hv, ctx->d_values));
-    FB200_CUDA(ctx, cudaIpcGetMemHandle(&hs, pp.d_signal));
+    std::memset(&hv, 0, sizeof(hv));
+    std::memset(&hs, 0, sizeof(hs));
+    if (cudaIpcGetMemHandle(&hv, ctx->d_values) != cudaSuccess || cudaIpcGetMemHandle(&hs, pp.d_signal) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;  // (no IPC in this process / container: told to the neighbours as a refusal, decided by the vote below)
+    }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
     std::vector<size_t> seg(np + 1, 0);
     for (size_t pr = 0; pr < np; ++pr) {
@@ -392,35 +396,64 @@ fb200_status fb200_interface_enable_p2p(fb200_ctx* ctx) {
     dev_free(d_send);
     dev_free(d_recv);
     FB200_TRY(st);
+    // From here on nobody returns before the world has agreed: a rank that enabled the fused exchange next to one that did not would
+    // wait for reductions that never come.  local verdict -> ncclAllReduce(min) -> everybody enables or nobody does.
+    std::string why;
     for (size_t pr = 0; pr < np; ++pr) ok = ok && recv[seg[pr]] == 1;
-    if (!ok) return fail(ctx, FB200_ERR_UNSUPPORTED, "fused p2p exchange needs one neighbour per interface node and at most two neighbours per rank");
+    if (np == 0) ok = true;  // a rank without interface has nothing to fuse and no reason to veto
+    else if (!ok) why = "fused p2p exchange needs one neighbour per interface node and at most two neighbours per rank";
     std::vector<uint32_t> row(ctx->N, 0u);
-    for (size_t pr = 0; pr < np; ++pr) {
+    for (size_t pr = 0; pr < np && ok; ++pr) {
         const size_t nn = (size_t)(ctx->h_peer_begin[pr + 1] - ctx->h_peer_begin[pr]);
         const int64_t* m = recv.data() + seg[pr];
         cudaIpcMemHandle_t rv, rs;
         std::memcpy(&rv, m + 1, 64);
         std::memcpy(&rs, m + 9, 64);
-        for (size_t k = 0; k < nn; ++k) {
+        for (size_t k = 0; k < nn && ok; ++k) {
             const int32_t node = ctx->h_peer_nodes[ctx->h_peer_begin[pr] + k];
             if (m[HDR + 2 * k + 1] != off[node + 1] - off[node] || m[HDR + 2 * k] < 0 || m[HDR + 2 * k] >= (int64_t)0x7fffffff) {
-                p2p_disable(ctx);
-                return fail(ctx, FB200_ERR_SHAPE, "interface rows have different layouts on the two ranks (ghost elements missing?)");
+                ok = false;
+                why = "interface rows have different layouts on the two ranks (ghost elements missing?)";
             }
             row[node] = ((uint32_t)m[HDR + 2 * k] + 1u) | ((uint32_t)pr << 31);
         }
+        if (!ok) break;
         void *pv = nullptr, *ps = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&pv, rv, cudaIpcMemLazyEnablePeerAccess);
         if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ps, rs, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             if (pv) cudaIpcCloseMemHandle(pv);
-            p2p_disable(ctx);
             cudaGetLastError();
-            return fail(ctx, FB200_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle failed (no peer access between the ranks?): ") + cudaGetErrorString(e));
+            ok = false;
+            why = std::string("cudaIpcOpenMemHandle failed (no peer access between the ranks?): ") + cudaGetErrorString(e);
+            break;
         }
         pp.values[pr] = static_cast<double*>(pv);
         pp.signal[pr] = static_cast<unsigned long long*>(ps);
         pp.peer_rank[pr] = ctx->peer_ranks[pr];
+    }
+    {
+        int32_t* d_vote = nullptr;
+        int32_t vote = ok ? 1 : 0;
+        FB200_TRY(dev_alloc(ctx, &d_vote, 1));
+        cudaError_t e = h2d_copy(ctx, d_vote, &vote, sizeof(vote));
+        int rc = 0;
+        if (e == cudaSuccess) rc = g_nccl.AllReduce(d_vote, d_vote, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, ctx->nccl_comm, ctx->stream);
+        if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(&vote, d_vote, sizeof(vote), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx->stream);
+        dev_free(d_vote);
+        if (rc != 0) {
+            p2p_disable(ctx);
+            return nccl_fail(ctx, rc, "ncclAllReduce(p2p vote)");
+        }
+        if (e != cudaSuccess) {
+            p2p_disable(ctx);
+            return cuda_fail(ctx, e, "p2p vote");
+        }
+        if (vote != 1) {
+            p2p_disable(ctx);
+            return fail(ctx, FB200_ERR_UNSUPPORTED, why.empty() ? "another rank cannot use the fused p2p exchange" : why);
+        }
     }
     FB200_TRY(dev_alloc(ctx, &pp.d_peer_row, (size_t)ctx->N));
     if (ctx->N) FB200_CUDA(ctx, h2d_copy(ctx, pp.d_peer_row, row.data(), ctx->N * sizeof(uint32_t)));

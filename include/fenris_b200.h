@@ -253,7 +253,8 @@ fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const
 /* Sum the interface rows over the ranks that share them.  Peers set: pack per peer -> ncclSend/ncclRecv (one group) -> add the
  * received blocks; otherwise pack -> ncclAllReduce(sum, f64) -> unpack.  Over NVLink, enqueued on the ctx stream. */
 fb200_status fb200_interface_allreduce(fb200_ctx* ctx);
-/* Optional, after fb200_comm_init + fb200_interface_set_peers (collective over the neighbours): fuse the interface exchange into the
+/* Optional, after fb200_comm_init + fb200_interface_set_peers (COLLECTIVE over all ranks of the communicator: the ranks vote, and either
+ * all of them enable it or none does): fuse the interface exchange into the
  * assembly kernel.  Every rank maps its neighbours' value arrays (CUDA IPC over NVLink) and learns where their copies of the shared rows
  * start; the Hex8 tile kernel's flush then adds this rank's partial sums of an interface row to the neighbour's copy as well
  * (red.global.add.f64 on the peer pointer), and fb200_interface_allreduce shrinks to a neighbour barrier - no pack, no ncclSend/ncclRecv,
