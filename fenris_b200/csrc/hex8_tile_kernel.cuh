@@ -371,8 +371,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     // =============================================================================================== compute warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTileComputeRegs));
     const int grp = warp / GW, gwarp = warp - grp * GW;
-    double* s_X = wbase + warp * L::WARP_DOUBLES;
-    double* s_G = s_X + 24;
+    double* s_G = wbase + warp * L::WARP_DOUBLES + 24;  // (the first 24 doubles of a warp's block are unused since the coordinates are read in place)
     const int nq = p.nq;  // <= 8
     // lane (gq, gi) owns row gi of the Jacobian at point gq (the 4th lane of a point shadows row 0)
     const int gq = lane >> 2, s4 = lane & 3;
@@ -394,23 +393,21 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
     const int src1 = (lane & ~3) | (gi == 2 ? 0 : gi + 1), src2 = (lane & ~3) | (gi == 0 ? 2 : gi - 1);
     const int ba = lane >> 2;
     const int frag = ba * GS + 3 * (lane & 3);
-    const int xl = lane < N * D ? lane : 0;
-    const int x_node = xl / D, x_comp = xl - x_node * D;
     const double mu = p.mu, lam = p.lam;
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint32_t* emap32 = reinterpret_cast<const uint32_t*>(p.tile_emap);
 
     // element data of a schedule position: tile-local node indices (lanes 0-7, one byte each; byte 0 = 0xff: padding position),
     // accumulator positions of the lane's two blocks
-    auto load_elem = [&](uint64_t pos, uint32_t& ln_, uint32_t& em_) {
-        ln_ = 0;
-        if (lane < N) ln_ = p.tile_lnodes[pos * N + lane];
+    auto load_elem = [&](uint64_t pos, uint2& ln_, uint32_t& em_) {
+        ln_ = __ldg(reinterpret_cast<const uint2*>(p.tile_lnodes) + pos);  // the 8 node bytes, the same 8-byte word for every lane (one transaction)
         em_ = ld_u32_hint(emap32 + pos * 32 + lane, pol_stream);
     };
 
     __syncthreads();  // (A)
     bool preloaded = false;
-    uint32_t ln = 0xffu, em = 0xffffffffu;
+    uint2 ln = make_uint2(0xffu, 0u);
+    uint32_t em = 0xffffffffu;
     for (uint32_t it = 0;; ++it) {
         const int sl = (int)(it & 7u), b = (int)(it & 1u);
         if (s_tick[sl] >= p.num_tiles) break;
@@ -425,8 +422,8 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
 
         for (int r = grp; r < R; r += 2) {
             const uint32_t em_c = em;
-            const bool active = (__shfl_sync(FULL, ln, 0) & 0xffu) != 0xffu;
-            const int u_x = (int)(__shfl_sync(FULL, ln, x_node) & 0x7fu);
+            const bool active = (ln.x & 0xffu) != 0xffu;
+            const uint2 ln_c = ln;
             if (r + 2 < R) {
                 load_elem((uint64_t)p0 + (r + 2) * GW + gwarp, ln, em);
             } else {
@@ -439,13 +436,15 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             }
             double K0[S][S], K1[S][S];
             if (active && !(dbg & 1)) {
-                if (lane < N * D) s_X[lane] = tX[u_x * D + x_comp];
-                __syncwarp();
-                // ---- geometry: row gi of J at point gq (element/hexahedron.rs:101-107), cofactors, det (elliptic.rs:399-405)
+                __syncwarp();  // (every lane has read the previous element's gradients in s_G before anybody overwrites them)
+                // ---- geometry: row gi of J at point gq (element/hexahedron.rs:101-107), cofactors, det (elliptic.rs:399-405).  Component
+                // gi of the 8 vertices straight from the tile's coordinate table (three distinct addresses per load: broadcast)
                 double Jr[D];
                 {
-                    const double x0 = s_X[gi], x1 = s_X[D + gi], x2 = s_X[2 * D + gi], x3 = s_X[3 * D + gi];
-                    const double x4 = s_X[4 * D + gi], x5 = s_X[5 * D + gi], x6 = s_X[6 * D + gi], x7 = s_X[7 * D + gi];
+                    const double* tXg = tX + gi;
+                    auto un = [&](int a) { return (int)(((a < 4 ? ln_c.x : ln_c.y) >> (8 * (a & 3))) & 0x7fu) * D; };
+                    const double x0 = tXg[un(0)], x1 = tXg[un(1)], x2 = tXg[un(2)], x3 = tXg[un(3)];
+                    const double x4 = tXg[un(4)], x5 = tXg[un(5)], x6 = tXg[un(6)], x7 = tXg[un(7)];
                     Jr[0] = fma(P0[3], x6 - x7, fma(P0[2], x5 - x4, fma(P0[1], x2 - x3, P0[0] * (x1 - x0))));
                     Jr[1] = fma(P1[3], x6 - x5, fma(P1[2], x7 - x4, fma(P1[1], x2 - x1, P1[0] * (x3 - x0))));
                     Jr[2] = fma(P2[3], x6 - x2, fma(P2[2], x7 - x3, fma(P2[1], x5 - x1, P2[0] * (x4 - x0))));
