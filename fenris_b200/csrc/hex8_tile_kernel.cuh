@@ -221,7 +221,10 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                     // value (48 bits) | row length in doubles << 48 (block rows are < 8192 nodes: tiles.cpp); PEER: a second table of words
                     unsigned long long* fr = reinterpret_cast<unsigned long long*>(buf_frow(b));
                     fr[ht] = (unsigned long long)((long long)BS * o0) | ((unsigned long long)(unsigned int)((int)(o1 - o0) * S) << 48);
-                    if constexpr (PEER) reinterpret_cast<uint32_t*>(fr + MAXN)[ht] = p.peer_row[small_ids(sl)[ht] & 0x7fffffff];
+                    // (only tiles with partition-interface nodes - header flag bit 0 - look the neighbour rows up, here and in the flush)
+                    if constexpr (PEER) {
+                        if (hdr[11] & 1u) reinterpret_cast<uint32_t*>(fr + MAXN)[ht] = p.peer_row[small_ids(sl)[ht] & 0x7fffffff];
+                    }
                 }
                 // pull this tile's flush list into L2 (it is read in the next iteration)
                 const char* f0 = reinterpret_cast<const char*>(p.tile_flush + hdr[5]);
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                 const uint32_t items = ph[6], store_items = ph[8];  // (entries)
                 const double* pacc = smem + nb * L::ACC;
                 const unsigned long long* prow = reinterpret_cast<const unsigned long long*>(buf_frow(nb));
+                const bool tile_iface = PEER && (ph[11] & 1u) != 0u;  // warp-uniform: most tiles have no interface node
                 // entries [e0, e1) of the list.  A warp takes blocks of 32 entries = SUB * 32 items; in sub-iteration m lane l handles
                 // item 32 m + l of the block = entry fe[m], column fj[m] (per-lane constants: no division in the loop), so that an
                 // instruction covers 32 consecutive doubles of a run of neighbouring node blocks.  STORE: plain stores; else reductions
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
 #pragma unroll
                                 for (int i = 0; i < S; ++i) red_add_f64_hint(dst + (long long)i * rl, v[i], pol_keep);
                                 if constexpr (PEER) {
-                                    const uint32_t pw = reinterpret_cast<const uint32_t*>(prow + MAXN)[un];
+                                    const uint32_t pw = tile_iface ? reinterpret_cast<const uint32_t*>(prow + MAXN)[un] : 0u;
                                     if (pw) {
                                         double* pd = p.peer_values[pw >> 31] + ((long long)BS * (long long)((pw & 0x7fffffffu) - 1u) + (long long)col);
 #pragma unroll

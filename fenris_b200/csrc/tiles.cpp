@@ -309,13 +309,14 @@ static void finish_flush(TileOut& t, uint32_t tile, bool owner, const uint32_t* 
     t.flags = 0;
     for (int u = 0; u < nn; ++u) {
         const int32_t id = t.nodes[u] & 0x7fffffff;
+        const bool ghosted = degree[id] != degree_owned[id];
+        if (ghosted) t.flags |= 1u;  // the tile touches a partition-interface node (the fused exchange looks its neighbour rows up)
         if (t.nodes[u] < 0) {
             cls[u] = 1;
         } else if (!owner) {
             cls[u] = 0;
-        } else if (degree[id] != degree_owned[id]) {
+        } else if (ghosted) {
             cls[u] = 0;  // ghost elements touch the node: other ranks add to its rows too; cleared by the caller, never stored
-            t.flags |= 1u;
         } else if (owner_tile[id] == tile) {
             cls[u] = 2;
         } else {
@@ -765,6 +766,14 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
         }
         for (uint32_t k = 0; k < nw; ++k)
             if (ht.wait[wb + k] >= (uint32_t)t || (k && ht.wait[wb + k] <= ht.wait[wb + k - 1])) return fail_check(29);
+        {  // header flag bit 0 <=> the tile touches a node that ghost elements touch too
+            bool any = false;
+            for (uint32_t u = 0; u < nn; ++u) {
+                const int32_t id = ht.nodes[nb + u] & 0x7fffffff;
+                any = any || degree[id] != degree_owned[id];
+            }
+            if (any != ((h[11] & 1u) != 0u)) return fail_check(36);
+        }
         if (!ht.owner_stores && (nw || zeros)) return fail_check(30);
         for (uint32_t u = 0; u < nn; ++u) {
             const bool flag = ht.nodes[nb + u] < 0;

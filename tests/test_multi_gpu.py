@@ -31,10 +31,12 @@ def _worker(rank, world, uid, cx, cy, cz, scatter_mode, exchange, q):
         ctx.assemble_pattern(3)
         ctx.color_nodes()
         ctx.comm_init(uid, rank, world)
-        if exchange in ("peers", "p2p"):
+        if exchange in ("peers", "p2p", "p2p_zero"):
             ctx.interface_set_peers(iface["peers"])
-            if exchange == "p2p":  # the exchange fused into the tile kernel's flush over peer-mapped memory (comm.cu)
+            if exchange != "peers":  # the exchange fused into the tile kernel's flush over peer-mapped memory (comm.cu)
                 assert ctx.interface_enable_p2p(), "fused p2p exchange refused on a slab partition"
+            if exchange == "p2p_zero":  # ... with zero-fill + reductions instead of owner stores (the other list flavour)
+                ctx.set_tuning("hex8_owner_stores", 0)
         else:
             ctx.interface_set(iface["local_nodes"], iface["packed_offsets"], iface["packed_len"])
         ctx.values_upload(np.full(ctx.nnz, 1e300))  # overwrite semantics: nothing of this may survive
@@ -92,7 +94,7 @@ def _run(world, target, args):
 
 
 @pytest.mark.skipif(_num_gpus() < 2, reason="needs at least two GPUs")
-@pytest.mark.parametrize("scatter_mode,exchange", [(0, "p2p"), (0, "peers"), (0, "allreduce"), (2, "peers"), (1, "p2p")])
+@pytest.mark.parametrize("scatter_mode,exchange", [(0, "p2p"), (0, "p2p_zero"), (0, "peers"), (0, "allreduce"), (2, "peers"), (1, "p2p")])
 def test_slab_partition_nccl_equals_global(scatter_mode, exchange):
     _run(2, _worker, (12, 12, 16, scatter_mode, exchange))
 
