@@ -29,8 +29,11 @@
 //                    STORE segment (rows complete in the tile, and all entries - zeros included - of shared rows this tile OWNS,
 //                    being the lowest-numbered tile that touches the node) and a REDUCE segment.  After its stores a tile publishes
 //                    flag[tile] = launch epoch (barrier, fence, release store); before its reductions it waits for the flags of the
-//                    owners of the rows it adds to (tiles.cpp `wait`).  Tickets are handed out in tile order, so every tile waited
-//                    for is already running: no deadlock.
+//                    owners of the rows it adds to (tiles.cpp `wait`).  A tile only waits for lower-numbered tiles.  With waits the
+//                    tiles are dealt round-robin (tile = CTA + k CTAs, cooperative launch: all CTAs resident) - under the atomic
+//                    ticket a waiting CTA lets the six tiles it holds age while others take tiles that depend on them (measured
+//                    5 - 6 ms instead of 2.5; profiles/r02/README.md); the ticket remains for launches without waits.
+//            colours (tile_list) a launch may cover the tiles of one colour only: the deterministic COLORED scatter (assemble.cu).
 //            peers   (PEER, multi-GPU) rows of partition-interface nodes are also reduced straight into the neighbouring rank's copy
 //                    of the row through a peer-mapped pointer (NVLink): the interface exchange is part of the flush (comm.cu).
 // On the structured C3 mesh this is 1.27 CSR updates per value instead of 2.4, 65 % of them plain stores.  Sums differ from the
