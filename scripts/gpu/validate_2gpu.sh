@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, call 24 (2 GPUs): peer lookups only in interface tiles: multi-GPU tests (incl. p2p with zero-fill lists), bench N = 2, N = 1
+# 2 GPUs: multi-GPU tests (incl. p2p with zero-fill lists), bench N = 2, N = 1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_multi_gpu.py -q -x > gpurun_out/r2b_24_multi.log 2>&1; tail -n 2 gpurun_out/r2b_24_multi.log
+timeout 900 python -m pytest tests/test_multi_gpu.py -q -x > gpurun_out/v2_multi.log 2>&1; tail -n 2 gpurun_out/v2_multi.log
 for i in 1 2; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --no-e2e 2>/dev/null | tail -n 1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print('n2', d['ms_per_step'], d['value'], d['config']['exchange'], d['parity']['rel_frobenius'])"; done
