@@ -78,6 +78,8 @@ struct AssembleParams {
     const uint16_t* slot_k;
     const uint16_t* slot_cbeg;
     const uint8_t* slot_flags;
+    const int64_t* slot_dst;     // first value of the slot's block / row length (precomputed: no dependent loads in the slot loop)
+    const int32_t* slot_rl;
     // tile lists of the Hex8 tile kernel (tiles.cpp)
     uint32_t num_tiles;
     const uint32_t* tile_hdr;
@@ -709,6 +711,8 @@ static void free_chunks(ChunkLists& cl) {
     dev_free(cl.d_slot_k);
     dev_free(cl.d_slot_cbeg);
     dev_free(cl.d_slot_flags);
+    dev_free(cl.d_slot_dst);
+    dev_free(cl.d_slot_rl);
     dev_free(cl.d_conn_pos);
     cl.valid = false;
     cl.count = 0;
@@ -724,7 +728,7 @@ static fb200_status upload_vec(fb200_ctx* ctx, T** d, const std::vector<T, A>& h
 
 static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t count, int chunk_elems) {
     ChunkLists& cl = ctx->chunks;
-    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems) return FB200_OK;
+    if (cl.valid && cl.count == count && cl.ids == d_ids && cl.chunk_elems == chunk_elems && cl.sdim == ctx->sdim) return FB200_OK;
     free_chunks(cl);
     const int n = ctx->ei.n;
     FB200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -736,7 +740,8 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
     FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     HostChunks hc;
-    build_chunk_lists(n, count, chunk_elems, ids.data(), conn.data(), ctx->E, ctx->N, blk_off.data(), map.data(), hc);
+    build_chunk_lists(n, ctx->sdim, count, chunk_elems, ids.data(), conn.data(), ctx->E, ctx->N, blk_off.data(), map.data(), hc);
+    cl.sdim = ctx->sdim;
     cl.num_chunks = (uint32_t)(hc.slot_off.size() - 1);
     cl.total_slots = hc.slot_node.size();
     FB200_TRY(upload_vec(ctx, &cl.d_slot_off, hc.slot_off));
@@ -745,6 +750,8 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     FB200_TRY(upload_vec(ctx, &cl.d_slot_k, hc.slot_k));
     FB200_TRY(upload_vec(ctx, &cl.d_slot_cbeg, hc.slot_cbeg));
     FB200_TRY(upload_vec(ctx, &cl.d_slot_flags, hc.slot_flags));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_dst, hc.slot_dst));
+    FB200_TRY(upload_vec(ctx, &cl.d_slot_rl, hc.slot_rl));
     FB200_TRY(dev_alloc(ctx, &cl.d_conn_pos, count * n));
     if (count) {
         const int blocks = (int)std::min<uint64_t>(div_up(count * n, 256), (uint64_t)ctx->sm_count * 16);
@@ -774,6 +781,8 @@ static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
     p.slot_k = cl.d_slot_k;
     p.slot_cbeg = cl.d_slot_cbeg;
     p.slot_flags = cl.d_slot_flags;
+    p.slot_dst = cl.d_slot_dst;
+    p.slot_rl = cl.d_slot_rl;
     // fused interface exchange (comm.cu): interface slots are also reduced into the neighbouring rank's rows; the values were just
     // cleared when the call overwrites, so no neighbour may add to them before that (neighbour barrier)
     const bool peer = ctx->p2p.enabled && ctx->p2p.num_peers > 0;

@@ -20,7 +20,7 @@
 
 namespace fb200 {
 
-void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
+void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
                        uint64_t num_nodes, const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out) {
     const int n2 = n * n;
     const uint64_t num_chunks = (count + chunk_elems - 1) / chunk_elems;
@@ -122,9 +122,15 @@ void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* or
     out.slot_k.resize(total);
     out.slot_cbeg.resize(total);
     out.slot_flags.resize(total);
+    out.slot_dst.resize(total);
+    out.slot_rl.resize(total);
     for (uint64_t c = 0; c < num_chunks; ++c) {
         uint64_t o = (uint64_t)out.slot_off[c];
         for (const Slot& s : chunk_slots[c]) {
+            // where the block's values start and how long the rows are: precomputed, so that the kernel's slot loop has no load that
+            // depends on another one (node -> block-row offsets)
+            out.slot_dst[o] = (int64_t)(sdim * sdim) * blk_off[s.node] + (int64_t)sdim * s.k;
+            out.slot_rl[o] = (int32_t)((blk_off[s.node + 1] - blk_off[s.node]) * sdim);
             out.slot_node[o] = s.node;
             out.slot_k[o] = s.k;
             out.slot_cbeg[o] = s.cbeg;

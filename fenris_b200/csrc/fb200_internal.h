@@ -59,8 +59,10 @@ struct HostChunks {
     std::vector<int32_t> slot_node;
     std::vector<uint16_t> slot_k, slot_cbeg;
     std::vector<uint8_t> slot_flags;   // bit 0: row node complete in the chunk (plain stores), bit 1: partition-interface row
+    std::vector<int64_t> slot_dst;     // index of the block's first value: s^2 blk_off[node] + s k
+    std::vector<int32_t> slot_rl;      // row length in doubles
 };
-void build_chunk_lists(int n, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
+void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const int32_t* order, const int32_t* conn, uint64_t num_elements,
                        uint64_t num_nodes, const int64_t* blk_off, const uint16_t* blockmap, HostChunks& out);
 
 // std::vector whose resize() leaves trivially constructible elements uninitialised: the big list arrays are written completely by a pool
@@ -160,6 +162,9 @@ struct ChunkLists {
     uint16_t* d_slot_k = nullptr;
     uint16_t* d_slot_cbeg = nullptr;
     uint8_t* d_slot_flags = nullptr;
+    int64_t* d_slot_dst = nullptr;
+    int32_t* d_slot_rl = nullptr;
+    int sdim = 0;
     int32_t* d_conn_pos = nullptr;  // connectivity rows in processing order
 };
 

@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
         for (int u = tid; u < U; u += T) {
             const int cb = p.slot_cbeg[so + u];
             const int ce = u + 1 < U ? (int)p.slot_cbeg[so + u + 1] : npairs;
-            // slot metadata first: its latency overlaps the contributor loop
-            const int node = p.slot_node[so + u];
-            const int kpos = p.slot_k[so + u];
+            // slot metadata first (independent loads: the destination and the row length are precomputed, chunks.cpp): their latency
+            // overlaps the contributor loop
+            const long long dsti = p.slot_dst[so + u];
+            const int rl = p.slot_rl[so + u];
             const unsigned sflags = p.slot_flags[so + u];
             const bool st = overwrite && (sflags & 1u);
-            const long long o0 = p.blk_off[node], o1 = p.blk_off[node + 1];
             double M[D][D];
 #pragma unroll
             for (int i = 0; i < D; ++i)
@@ -105,13 +105,13 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : (C <= 512 ? 4 : 2))) assem
                         for (int j = 0; j < D; ++j) M[i][j] = fma(va[i], vb[j], M[i][j]);
                 }
             }
-            const int rl = (int)(o1 - o0) * S;
-            double* dst = p.values + ((long long)(S * S) * o0 + (long long)S * kpos);
+            double* dst = p.values + dsti;
             double* pdst = nullptr;  // the same block in the neighbouring rank's copy of the row (identical row layout, other offset)
             if constexpr (PEER) {
                 if (sflags & 2u) {
+                    const int node = p.slot_node[so + u];
                     const uint32_t pw = __ldg(p.peer_row + node);
-                    if (pw) pdst = p.peer_values[pw >> 31] + ((long long)(S * S) * (long long)((pw & 0x7fffffffu) - 1u) + (long long)S * kpos);
+                    if (pw) pdst = p.peer_values[pw >> 31] + ((long long)(S * S) * (long long)((pw & 0x7fffffffu) - 1u) + (long long)S * (long long)p.slot_k[so + u]);
                 }
             }
             if constexpr (S == 1) {
