@@ -125,6 +125,7 @@ def lib():
         "fb200_lame_from_young_poisson": (None, [dbl, dbl, pdbl, pdbl]),
         "fb200_tile_lists_selftest": (i32, [u64, vp, u64, vp, u64, pu64, pi32]),
         "fb200_tile_lists_selftest_ex": (i32, [u64, vp, u64, vp, u64, i32, pu64, pi32]),
+        "fb200_chunk_lists_selftest": (i32, [u64, vp, u64, vp, u64, i32, i32, pu64, pi32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = header/library mismatch: fail loudly

@@ -141,3 +141,115 @@ void build_chunk_lists(int n, int sdim, uint64_t count, int chunk_elems, const i
 }
 
 }  // namespace fb200
+
+// ---------------------------------------------------------------------------------------------------------------- host self check
+// Builds the node-block rows and the block map the way fb200_assemble_pattern does, the Morton order of the owned elements, the chunk
+// lists, and verifies them (no GPU): every contribution (element, a, b) of every owned element appears exactly once, in the slot of its
+// node block (row node, k); a slot's contributors are in ascending element order; destination and row length match the block offsets;
+// the complete flag is set exactly for rows whose node has ALL its elements - ghost elements included - inside the chunk; the interface
+// flag exactly for rows that ghost elements touch.
+extern "C" fb200_status fb200_chunk_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
+                                                   uint64_t num_owned, int32_t chunk_elems, int32_t sdim, uint64_t stats[4], int32_t* failed_check) {
+    using namespace fb200;
+    constexpr int n = 4, n2 = 16;
+    if (failed_check) *failed_check = 0;
+    if (!vertices || !connectivity || !stats || num_owned > num_elements || chunk_elems < 1 || chunk_elems > 4096 || sdim < 1 || sdim > 3) return FB200_ERR_SHAPE;
+    for (uint64_t i = 0; i < num_elements * n; ++i)
+        if (connectivity[i] >= num_nodes) return FB200_ERR_INDEX_OOB;
+    auto fail_check = [&](int id) {
+        if (failed_check) *failed_check = id;
+        return FB200_ERR_STATE;
+    };
+    std::vector<std::vector<int32_t>> rows(num_nodes);
+    std::vector<int32_t> conn(num_elements * n);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) {
+            conn[e * n + a] = (int32_t)connectivity[e * n + a];
+            for (int b = 0; b < n; ++b) rows[connectivity[e * n + a]].push_back((int32_t)connectivity[e * n + b]);
+        }
+    std::vector<int64_t> blk_off(num_nodes + 1, 0);
+    for (uint64_t i = 0; i < num_nodes; ++i) {
+        auto& r = rows[i];
+        std::sort(r.begin(), r.end());
+        r.erase(std::unique(r.begin(), r.end()), r.end());
+        if (r.size() >= 65536) return FB200_ERR_UNSUPPORTED;
+        blk_off[i + 1] = blk_off[i] + (int64_t)r.size();
+    }
+    std::vector<uint16_t> map(num_elements * (uint64_t)n2);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) {
+            const auto& r = rows[conn[e * n + a]];
+            for (int b = 0; b < n; ++b) map[e * n2 + a * n + b] = (uint16_t)(std::lower_bound(r.begin(), r.end(), conn[e * n + b]) - r.begin());
+        }
+    std::vector<int32_t> order_all, order;
+    std::vector<uint64_t> codes_all;
+    morton_order(3, n, num_nodes, vertices, num_elements, connectivity, order_all, codes_all);
+    for (size_t i = 0; i < order_all.size(); ++i)
+        if ((uint64_t)order_all[i] < num_owned) order.push_back(order_all[i]);
+    HostChunks hc;
+    build_chunk_lists(n, sdim, order.size(), chunk_elems, order.data(), conn.data(), num_elements, num_nodes, blk_off.data(), map.data(), hc);
+    const uint64_t count = order.size(), num_chunks = (count + chunk_elems - 1) / chunk_elems;
+    if (hc.slot_off.size() != num_chunks + 1 || hc.contrib.size() != count * n2) return fail_check(1);
+    std::vector<int32_t> degree(num_nodes, 0), degree_owned(num_nodes, 0);
+    for (uint64_t e = 0; e < num_elements; ++e)
+        for (int a = 0; a < n; ++a) {
+            ++degree[conn[e * n + a]];
+            if (e < num_owned) ++degree_owned[conn[e * n + a]];
+        }
+    uint64_t complete_slots = 0, iface_slots = 0;
+    for (uint64_t c = 0; c < num_chunks; ++c) {
+        const uint64_t p0 = c * (uint64_t)chunk_elems;
+        const int ne = (int)std::min<uint64_t>(chunk_elems, count - p0);
+        const int64_t so = hc.slot_off[c], U = hc.slot_off[c + 1] - so;
+        if (U < 0 || (uint64_t)(so + U) > hc.slot_node.size()) return fail_check(2);
+        std::vector<int32_t> inside(num_nodes > 0 ? 0 : 0);
+        std::vector<std::pair<int32_t, int32_t>> local;  // (node, incidences inside the chunk)
+        {
+            std::vector<int32_t> nodes;
+            for (int el = 0; el < ne; ++el)
+                for (int a = 0; a < n; ++a) nodes.push_back(conn[(uint64_t)order[p0 + el] * n + a]);
+            std::sort(nodes.begin(), nodes.end());
+            for (size_t i = 0; i < nodes.size();) {
+                size_t j = i;
+                while (j < nodes.size() && nodes[j] == nodes[i]) ++j;
+                local.emplace_back(nodes[i], (int32_t)(j - i));
+                i = j;
+            }
+        }
+        std::vector<uint8_t> seen((size_t)ne * n2, 0);
+        for (int64_t u = 0; u < U; ++u) {
+            const int32_t node = hc.slot_node[so + u];
+            const int k = hc.slot_k[so + u], cb = hc.slot_cbeg[so + u];
+            const int ce = u + 1 < U ? (int)hc.slot_cbeg[so + u + 1] : ne * n2;
+            if (node < 0 || (uint64_t)node >= num_nodes || k >= (int)rows[node].size() || cb >= ce) return fail_check(3);
+            if (hc.slot_dst[so + u] != (int64_t)(sdim * sdim) * blk_off[node] + (int64_t)sdim * k ||
+                hc.slot_rl[so + u] != (int32_t)((blk_off[node + 1] - blk_off[node]) * sdim))
+                return fail_check(4);
+            int last_el = -1;
+            for (int t = cb; t < ce; ++t) {
+                const unsigned tag = hc.contrib[p0 * n2 + t];
+                const int el = tag >> 4, a = (tag >> 2) & 3, b = tag & 3;
+                if (el >= ne || el < last_el) return fail_check(5);  // contributors in ascending element order
+                last_el = el;
+                const uint64_t e = (uint64_t)order[p0 + el];
+                if (conn[e * n + a] != node || map[e * n2 + a * n + b] != k) return fail_check(6);
+                if (seen[(size_t)el * n2 + a * n + b]++) return fail_check(7);
+            }
+            const auto it = std::lower_bound(local.begin(), local.end(), std::make_pair(node, (int32_t)0));
+            const bool complete = it != local.end() && it->first == node && it->second == degree[node];
+            const bool iface = degree[node] != degree_owned[node];
+            if (((hc.slot_flags[so + u] & 1) != 0) != complete) return fail_check(8);
+            if (((hc.slot_flags[so + u] & 2) != 0) != iface) return fail_check(9);
+            if (complete && iface) return fail_check(10);  // a row another rank adds to is never stored
+            complete_slots += complete;
+            iface_slots += iface;
+        }
+        for (uint8_t s : seen)
+            if (s != 1) return fail_check(11);  // every contribution exactly once
+    }
+    stats[0] = num_chunks;
+    stats[1] = hc.slot_node.size();
+    stats[2] = complete_slots;
+    stats[3] = iface_slots;
+    return FB200_OK;
+}

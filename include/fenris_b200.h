@@ -303,6 +303,13 @@ fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const double* vert
 fb200_status fb200_tile_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
                                        uint64_t num_owned, uint64_t stats[8], int32_t* failed_check);
 
+/* Host-only self check of the Tet4 chunk lists (csrc/chunks.cpp; no GPU needed): every contribution (element, a, b) of every owned element
+ * exactly once in the slot of its node block, contributors in ascending element order, destinations / row lengths consistent with the block
+ * offsets, the "complete" flag exactly for rows whose node has all its elements - ghost elements of a partition included - inside the chunk,
+ * the "interface" flag exactly for rows ghost elements touch.  stats[0..3] = chunks, slots, complete slots, interface slots. */
+fb200_status fb200_chunk_lists_selftest(uint64_t num_nodes, const double* vertices, uint64_t num_elements, const uint64_t* connectivity,
+                                        uint64_t num_owned, int32_t chunk_elems, int32_t solution_dim, uint64_t stats[4], int32_t* failed_check);
+
 #ifdef __cplusplus
 }
 #endif
