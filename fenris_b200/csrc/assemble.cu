@@ -735,10 +735,10 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
     std::vector<int32_t> conn(ctx->E * n), ids(count);
     std::vector<int64_t> blk_off(ctx->N + 1);
     std::vector<uint16_t> map(ctx->E * (uint64_t)(n * n));
-    FB200_CUDA(ctx, cudaMemcpy(conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(ids.data(), d_ids, ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
-    FB200_CUDA(ctx, cudaMemcpy(map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, d2h_copy(ctx, conn.data(), ctx->d_conn, conn.size() * sizeof(int32_t)));
+    FB200_CUDA(ctx, d2h_copy(ctx, ids.data(), d_ids, ids.size() * sizeof(int32_t)));
+    FB200_CUDA(ctx, d2h_copy(ctx, blk_off.data(), ctx->d_blk_off, blk_off.size() * sizeof(int64_t)));
+    FB200_CUDA(ctx, d2h_copy(ctx, map.data(), ctx->d_blockmap, map.size() * sizeof(uint16_t)));
     HostChunks hc;
     build_chunk_lists(n, ctx->sdim, count, chunk_elems, ids.data(), conn.data(), ctx->E, ctx->N, blk_off.data(), map.data(), hc);
     cl.sdim = ctx->sdim;

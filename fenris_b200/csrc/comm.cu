@@ -218,7 +218,7 @@ fb200_status fb200_interface_set(fb200_ctx* ctx, uint64_t count, const uint64_t*
     ctx->iface_packed_len = 0;
     // validate on the host against the block structure
     std::vector<int64_t> off(ctx->N + 1);
-    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, d2h_copy(ctx, off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t)));
     std::vector<int32_t> nodes(count);
     std::vector<int64_t> offs(count);
     const uint64_t ss = (uint64_t)ctx->sdim * ctx->sdim;
@@ -258,7 +258,7 @@ fb200_status fb200_interface_set_peers(fb200_ctx* ctx, uint64_t num_peers, const
     p2p_disable(ctx);
     if (num_peers == 0) return FB200_OK;
     std::vector<int64_t> off(ctx->N + 1);
-    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, d2h_copy(ctx, off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t)));
     const uint64_t ss = (uint64_t)ctx->sdim * ctx->sdim, total_nodes = peer_begin[num_peers];
     std::vector<int32_t> h_nodes(total_nodes);
     std::vector<int64_t> h_offs(total_nodes);
@@ -346,7 +346,7 @@ fb200_status fb200_interface_enable_p2p(fb200_ctx* ctx) {
     // every rank must reach the exchanges below or none: agree on `ok` with the neighbours first (a refusal is sent as a zero-length layout)
     const uint64_t total = ctx->peer_count;
     std::vector<int64_t> off(ctx->N + 1);
-    FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    FB200_CUDA(ctx, d2h_copy(ctx, off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t)));
     // message to peer pr: [ok, ipc handle of values (64 B), ipc handle of the signal words (64 B)] as 17 int64, then (offset, count) per node
     if (!pp.d_signal) {
         FB200_TRY(dev_alloc(ctx, &pp.d_signal, (size_t)std::max(ctx->nranks, 1)));

@@ -334,6 +334,13 @@ inline cudaError_t h2d_copy(fb200_ctx* ctx, void* dst, const void* src, size_t b
     return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
 }
 
+// D2H copy of an array that kernels on ctx->stream produced: ordered on that stream (a blocking cudaMemcpy on the legacy stream is not
+// ordered after work on a cudaStreamNonBlocking stream) and complete on return
+inline cudaError_t d2h_copy(fb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+}
+
 // D2H copy of a large device array into pageable host memory through two pinned staging buffers (a pageable cudaMemcpy runs at a few
 // GB/s; this one at the speed of the host memcpy): chunk k + 1 crosses PCIe while chunk k is copied out of the staging buffer
 cudaError_t d2h_staged(fb200_ctx* ctx, void* dst, const void* src, size_t bytes);

@@ -548,7 +548,7 @@ fb200_status fb200_pattern_download(fb200_ctx* ctx, uint64_t* row_offsets, uint6
     if (col_indices && ctx->nnz) {
         // stream the expansion through a bounded staging buffer
         std::vector<int64_t> h_off(ctx->N + 1);
-        FB200_CUDA(ctx, cudaMemcpy(h_off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        FB200_CUDA(ctx, d2h_copy(ctx, h_off.data(), ctx->d_blk_off, (ctx->N + 1) * sizeof(int64_t)));
         const uint64_t chunk_entries = 32ull << 20;  // 256 MiB of u64
         uint64_t* d_stage = nullptr;
         uint64_t max_node_entries = 0;
@@ -670,10 +670,10 @@ fb200_status fb200_color_nodes(fb200_ctx* ctx, uint64_t* num_colors) {
     // The reference colours serially on the host (sequential_greedy_coloring); so do we, from the device copy.
     const uint64_t E = ctx->E_owned;
     std::vector<int32_t> nodes(ctx->conn_len);
-    if (ctx->conn_len) FB200_CUDA(ctx, cudaMemcpy(nodes.data(), ctx->d_conn, ctx->conn_len * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (ctx->conn_len) FB200_CUDA(ctx, d2h_copy(ctx, nodes.data(), ctx->d_conn, ctx->conn_len * sizeof(int32_t)));
     std::vector<int64_t> off(ctx->E + 1);
     if (ctx->ragged) {
-        FB200_CUDA(ctx, cudaMemcpy(off.data(), ctx->d_elem_off, (ctx->E + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        FB200_CUDA(ctx, d2h_copy(ctx, off.data(), ctx->d_elem_off, (ctx->E + 1) * sizeof(int64_t)));
     } else {
         for (uint64_t e = 0; e <= ctx->E; ++e) off[e] = (int64_t)(e * (uint64_t)ctx->ei.n);
     }
