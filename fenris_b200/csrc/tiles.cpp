@@ -253,6 +253,9 @@ struct Builder {
         t.lnodes.clear();
         t.emap.clear();
         t.elem.clear();
+        t.lnodes.reserve((size_t)(ne + 8 * gw) * n);  // (one allocation each instead of a dozen reallocations per tile)
+        t.emap.reserve((size_t)(ne + 8 * gw) * n2);
+        t.elem.reserve((size_t)(ne + 8 * gw));
         t.rounds = 0;
         auto pad_round = [&]() {
             while (t.elem.size() % gw) {
