@@ -88,6 +88,7 @@ using BigVec = std::vector<T, DefaultInitAllocator<T>>;
 
 // tiles of the tile-accumulating Hex8 kernel (host build: tiles.cpp::build_tile_lists; consumer: hex8_tile_kernel.cuh)
 constexpr int kTileKBits = 13;     // bits of k (position of the column node in a block row) in a flush word
+constexpr uint32_t kTileFirstTouch = 0x8000u;  // bit 15 of an element-map entry: first contribution to the accumulator position in the tile
 constexpr uint32_t kTileZeroPos = 0x7ffu;  // accumulator position of a flush word that writes 0.0 (owner rows, see below)
 // header of a tile: 0 first schedule position, 1 rounds, 2 n_nodes, 3 n_slots (P), 4 node_begin, 5 flush_begin, 6 n_flush, 7 n_elems,
 // 8 n_store (leading flush entries that are plain stores when the call overwrites), 9 wait_begin, 10 n_wait, 11 flags,
@@ -115,7 +116,7 @@ struct HostTiles {
     std::vector<int32_t> zero_nodes;  // owner_stores: nodes whose rows no tile stores (touched by ghost elements, or by no owned element at
                                       // all): the only rows an overwriting call has to clear beforehand
     BigVec<uint8_t> lnodes;      // positions * 8: tile-local node index of each element node (byte 0 = 0xff: padding position)
-    BigVec<uint16_t> emap;       // positions * 64: accumulator position of block (a, b), 0xffff when u_a > u_b (mirrored at the flush)
+    BigVec<uint16_t> emap;       // positions * 64: accumulator position of block (a, b) (| kTileFirstTouch), 0xffff when u_a > u_b (mirrored at the flush)
     BigVec<int32_t> elem;        // positions: element id of each schedule position (-1: padding)
     bool owner_stores = false;        // the lists were built with TileShape::owner_stores
     uint64_t zero_entries = 0;        // flush words with position kTileZeroPos

@@ -44,11 +44,13 @@
 // quadrature point instead of 24 and applies the signs as operand negations.
 #pragma once
 
+// a += K, or a = K when this is the first contribution to the accumulator in the tile (tiles.cpp marks it in the element map): the
+// accumulators are never cleared between tiles
 template <int S>
-__device__ __forceinline__ void tile_accumulate(double* __restrict__ a, const double (&K)[S][S]) {
+__device__ __forceinline__ void tile_accumulate(double* __restrict__ a, const double (&K)[S][S], bool first) {
     double v[S * S];
 #pragma unroll
-    for (int i = 0; i < S * S; ++i) v[i] = a[i];
+    for (int i = 0; i < S * S; ++i) v[i] = first ? 0.0 : a[i];
 #pragma unroll
     for (int i = 0; i < S; ++i)
 #pragma unroll
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         // owner stores (see the header comment): flags are compared with this launch's epoch; 0 = the lists carry no ownership or the
         // call accumulates (then every entry is a reduction and nothing is published or waited for)
         const uint32_t epoch = overwrite ? p.tile_epoch : 0u;
-        int pf_P = 0;  // previous tile: accumulator positions in use
         // iteration `it`: tables of tiles it + 2 .. it + 4, flush of tile it - 1 (after the compute warps have finished it)
         for (uint32_t it = 0;; ++it) {
             const int sl = (int)(it & 7u), b = (int)(it & 1u), nb = b ^ 1;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             }
             const bool valid = s_tick[sl] < p.num_tiles;
             const uint32_t* hdr = small_hdr(sl);
-            const int nn = valid ? (int)hdr[2] : 0, P = valid ? (int)hdr[3] : 0;
+            const int nn = valid ? (int)hdr[2] : 0;
             if (valid) {
                 // row table of this tile's flush (used in the next iteration): first value of node u's rows and the row length; for a
                 // partition-interface node (PEER) also its block-row offset on the neighbouring rank + 1 | neighbour slot << 31
@@ -360,12 +361,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                     flush_range(n_store, items, std::false_type{});
                 }
             }
-            tables_done();  // the stages have landed, and every helper has read its accumulators
-            {
-                double* old = smem + nb * L::ACC;
-                for (int i = ht; i < pf_P * BS; i += TH) old[i] = 0.0;
-            }
-            pf_P = P;
+            tables_done();  // the stages have landed, and every helper has read its accumulators (no clearing: first contributions store)
             // accumulator buffer nb is clear (again) and the tables of tile it + 2 are there: release tile it + 1
             if (s_tick[(it + 1) & 7u] < p.num_tiles) {
                 __threadfence_block();
@@ -536,8 +532,8 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
             if (r > 0) named_barrier(1 + grp, TC);
             if (active && !(dbg & 4)) {
                 const uint32_t e0 = em_c & 0xffffu, e1 = em_c >> 16;
-                if (e0 != 0xffffu) tile_accumulate<S>(acc + e0 * BS, K0);
-                if (e1 != 0xffffu) tile_accumulate<S>(acc + e1 * BS, K1);
+                if (e0 != 0xffffu) tile_accumulate<S>(acc + (e0 & (kTileFirstTouch - 1u)) * BS, K0, (e0 & kTileFirstTouch) != 0u);
+                if (e1 != 0xffffu) tile_accumulate<S>(acc + (e1 & (kTileFirstTouch - 1u)) * BS, K1, (e1 & kTileFirstTouch) != 0u);
             }
             if (r + 1 < R) {
                 __threadfence_block();

@@ -265,6 +265,9 @@ struct Builder {
                 t.emap.insert(t.emap.end(), n2, (uint16_t)0xffffu);
             }
         };
+        // bit 15 of a map entry: this is the FIRST contribution to the accumulator in the tile's schedule (rounds run in order and are
+        // node-disjoint) - the kernel stores instead of adding, so the accumulators never have to be cleared between tiles
+        std::vector<uint8_t> touched(t.P, 0);
         for (int s = 0; s < ne; ++s) {
             const int el = sched[s];
             if (s > 0 && colour[el] != colour[sched[s - 1]]) pad_round();
@@ -277,7 +280,13 @@ struct Builder {
             for (int a = 0; a < n; ++a)
                 for (int b = 0; b < n; ++b) {
                     const int u = ln[el * n + a], v = ln[el * n + b];
-                    em[a * n + b] = u <= v ? find_pos(u, blockmap[e * n2 + a * n + b]).pos : (uint16_t)0xffffu;
+                    if (u <= v) {
+                        const uint16_t pos = find_pos(u, blockmap[e * n2 + a * n + b]).pos;
+                        em[a * n + b] = (uint16_t)(pos | (touched[pos] ? 0u : (unsigned)kTileFirstTouch));
+                        touched[pos] = 1;
+                    } else {
+                        em[a * n + b] = (uint16_t)0xffffu;
+                    }
                 }
             // diagnostic: bank collisions of the four half-warp access groups
             for (int h = 0; h < 2; ++h)
@@ -663,6 +672,7 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
         // schedule: every position is an element of the tile or padding; rounds are node-disjoint
         std::vector<std::pair<uint32_t, uint32_t>> pairs;  // (u << 8 | v) -> accumulator position, from the element maps
         std::vector<uint32_t> pair_pos;
+        std::vector<uint8_t> first_seen(P, 0);
         uint32_t real = 0;
         for (uint32_t r = 0; r < R; ++r) {
             std::vector<uint8_t> used(nn, 0);
@@ -688,12 +698,16 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
                 }
                 for (int a = 0; a < n; ++a)
                     for (int b = 0; b < n; ++b) {
-                        const uint16_t ps = em[a * n + b];
+                        const uint16_t raw = em[a * n + b];
                         if (ln[a] > ln[b]) {
-                            if (ps != 0xffffu) return fail_check(8);
+                            if (raw != 0xffffu) return fail_check(8);
                             continue;
                         }
+                        const uint16_t ps = raw & (uint16_t)(kTileFirstTouch - 1);
                         if (ps >= P) return fail_check(8);
+                        // the first-touch bit is set exactly on the first schedule position that uses the accumulator
+                        if (((raw & kTileFirstTouch) != 0) != (first_seen[ps] == 0)) return fail_check(37);
+                        first_seen[ps] = 1;
                         pairs.emplace_back(((uint32_t)ln[a] << 8) | ln[b], ps);
                     }
             }
