@@ -769,7 +769,13 @@ static fb200_status ensure_chunks(fb200_ctx* ctx, const int32_t* d_ids, uint64_t
 template <int OP, int C, int T>
 static fb200_status launch_tet4_chunks_t(fb200_ctx* ctx, AssembleParams& p) {
     FB200_TRY(clear_values_if_pending(ctx));
-    if (p.count == 0) return FB200_OK;
+    if (p.count == 0) {  // (a rank without owned elements still takes part in the neighbour barriers of the fused exchange)
+        if (ctx->p2p.enabled && ctx->p2p.num_peers > 0) {
+            if (!p.accumulate) FB200_TRY(p2p_neighbour_barrier(ctx));
+            ctx->p2p.pending = true;
+        }
+        return FB200_OK;
+    }
     FB200_TRY(ensure_chunks(ctx, ctx->d_order, ctx->order_count, C));
     const ChunkLists& cl = ctx->chunks;
     p.conn_pos = cl.d_conn_pos;
@@ -945,7 +951,6 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
             FB200_TRY(clear_values_if_pending(ctx));
         }
     }
-    if (tl.num_tiles == 0) return FB200_OK;
     p.num_tiles = tl.num_tiles;
     p.tile_hdr = tl.d_hdr;
     p.tile_nodes = tl.d_nodes;
@@ -965,6 +970,7 @@ static fb200_status launch_hex8_tile_t(fb200_ctx* ctx, AssembleParams& p, const 
         if (!p.accumulate) FB200_TRY(p2p_neighbour_barrier(ctx));
         ctx->p2p.pending = true;
     }
+    if (tl.num_tiles == 0) return FB200_OK;  // (a rank without owned elements still takes part in the neighbour barriers)
     const size_t smem = Hex8TileSmem<OP, MAXN, MAXP>::bytes;
     auto kernel = peer ? assemble_hex8_tile_kernel<OP, MAXN, MAXP, true> : assemble_hex8_tile_kernel<OP, MAXN, MAXP, false>;
     FB200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
