@@ -81,6 +81,8 @@ struct Builder {
     std::vector<std::vector<RowEntry>> rows;
     std::vector<std::vector<int>> node_elems;
     std::vector<uint8_t> ln;  // ne * 8
+    std::vector<uint16_t> pair_pos = std::vector<uint16_t>(128 * 128, (uint16_t)0xffffu);  // accumulator position of the pair (u, v), u <= v
+    std::vector<uint8_t> pair_seen = std::vector<uint8_t>(128 * 128, (uint8_t)0);           // (u, v) already has a row entry
 
     uint64_t elem_at(uint64_t pos) const { return order ? (uint64_t)order[pos] : pos; }
 
@@ -154,18 +156,30 @@ struct Builder {
         // ---- rows: coupled nodes of every tile node, ordered by their position k in the global block row
         if ((int)rows.size() < nn) rows.resize(nn);
         for (int u = 0; u < nn; ++u) rows[u].clear();
+        // (a pair (u, v) has one position k in the block row of u, whichever element reports it: keep the first report only)
         for (int el = 0; el < ne; ++el) {
             const uint64_t e = elem_at(p0 + el);
-            for (int a = 0; a < n; ++a)
-                for (int b = 0; b < n; ++b) rows[ln[el * n + a]].push_back({blockmap[e * n2 + a * n + b], ln[el * n + b], 0});
+            for (int a = 0; a < n; ++a) {
+                const int u = ln[el * n + a];
+                for (int b = 0; b < n; ++b) {
+                    const int v = ln[el * n + b];
+                    uint8_t& seen = pair_seen[u * 128 + v];
+                    if (!seen) {
+                        seen = 1;
+                        rows[u].push_back({blockmap[e * n2 + a * n + b], (uint8_t)v, 0});
+                    }
+                }
+            }
         }
         int nslots = 0, nflush = 0;
         for (int u = 0; u < nn; ++u) {
             auto& r = rows[u];
             std::sort(r.begin(), r.end(), [](const RowEntry& x, const RowEntry& y) { return x.k < y.k; });
-            r.erase(std::unique(r.begin(), r.end(), [](const RowEntry& x, const RowEntry& y) { return x.k == y.k; }), r.end());
             nflush += (int)r.size();
-            for (const RowEntry& x : r) nslots += x.v >= u;
+            for (const RowEntry& x : r) {
+                nslots += x.v >= u;
+                pair_seen[u * 128 + x.v] = 0;  // (table clean again for the next tile)
+            }
         }
         if (nslots > shape.max_slots) return false;
         lap(1);
@@ -199,15 +213,12 @@ struct Builder {
                         if (fill[q] < fill[r]) r = q;
                 }
                 x.pos = (uint16_t)(r + 16 * fill[r]++);
+                pair_pos[u * 128 + x.v] = x.pos;
             }
         }
         int maxfill = 0;
         for (int q = 0; q < 16; ++q) maxfill = std::max(maxfill, fill[q]);
         t.P = (uint32_t)(16 * maxfill);
-        auto find_pos = [&](int u, uint16_t k) -> const RowEntry& {
-            const auto& r = rows[u];
-            return *std::lower_bound(r.begin(), r.end(), k, [](const RowEntry& x, uint16_t kk) { return x.k < kk; });
-        };
         lap(2);
         // ---- flush list + node list
         t.p0 = p0;
@@ -221,13 +232,8 @@ struct Builder {
                 uint32_t pos, tr = 0;
                 if (x.v >= u) {
                     pos = x.pos;
-                } else {  // mirrored block: find (v, u) in row v
-                    pos = 0xffffu;
-                    for (const RowEntry& y : rows[x.v])
-                        if (y.v == u) {
-                            pos = y.pos;
-                            break;
-                        }
+                } else {  // mirrored block: the accumulator of (v, u)
+                    pos = pair_pos[x.v * 128 + u];
                     tr = 1;
                 }
                 if (x.k >= (1u << kTileKBits)) degenerate = true;
@@ -281,7 +287,7 @@ struct Builder {
                 for (int b = 0; b < n; ++b) {
                     const int u = ln[el * n + a], v = ln[el * n + b];
                     if (u <= v) {
-                        const uint16_t pos = find_pos(u, blockmap[e * n2 + a * n + b]).pos;
+                        const uint16_t pos = pair_pos[u * 128 + v];
                         em[a * n + b] = (uint16_t)(pos | (touched[pos] ? 0u : (unsigned)kTileFirstTouch));
                         touched[pos] = 1;
                     } else {
@@ -573,6 +579,23 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
     run_pool(T, copier);
     out.bank_conflict_share = accesses.load() ? (double)conflicts.load() / (double)accesses.load() : 0.0;
     tm.lap("  tile lists: concatenate");
+    if (tm.on) {  // FB200_DEBUG_SETUP: a checksum of everything that goes to the device (list builds must be reproducible)
+        uint64_t hsh = 1469598103934665603ull;
+        auto mix = [&](const void* ptr, size_t bytes) {
+            const unsigned char* c = static_cast<const unsigned char*>(ptr);
+            for (size_t i = 0; i < bytes; ++i) hsh = (hsh ^ c[i]) * 1099511628211ull;
+        };
+        mix(out.hdr.data(), out.hdr.size() * 4);
+        mix(out.nodes.data(), out.nodes.size() * 4);
+        mix(out.flush.data(), out.flush.size() * 4);
+        mix(out.wait.data(), out.wait.size() * 4);
+        mix(out.lnodes.data(), out.lnodes.size());
+        mix(out.emap.data(), out.emap.size() * 2);
+        mix(out.elem.data(), out.elem.size() * 4);
+        mix(out.colour_tiles.data(), out.colour_tiles.size() * 4);
+        mix(out.zero_nodes.data(), out.zero_nodes.size() * 4);
+        std::fprintf(stderr, "[fb200 setup]   tile lists: checksum %016llx\n", (unsigned long long)hsh);
+    }
 }
 
 }  // namespace fb200
