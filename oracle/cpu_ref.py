@@ -34,15 +34,33 @@ def _host_tag() -> str:
 
 
 def build(force: bool = False) -> str:
+    """Compile cpu_ref.c when the library is missing, older than the source or was built on another host.  Several processes may call this
+    at once (one bench rank per GPU, each checking its rows): the build runs under a file lock, into a private file that is renamed into
+    place, so nobody ever loads a half-written library."""
+    import fcntl
     src = os.path.join(_HERE, "cpu_ref.c")
-    stamp = os.path.join(_HERE, "_build", "host.tag")
+    bdir = os.path.join(_HERE, "_build")
+    stamp = os.path.join(bdir, "host.tag")
     tag = _host_tag()
-    old = open(stamp).read().strip() if os.path.exists(stamp) else ""
-    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src) or old != tag
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
-        with open(stamp, "w") as f:
-            f.write(tag)
+
+    def stale() -> bool:
+        old = open(stamp).read().strip() if os.path.exists(stamp) else ""
+        return (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src) or old != tag
+
+    if force or stale():
+        os.makedirs(bdir, exist_ok=True)
+        with open(os.path.join(bdir, ".lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():  # (another process may have built it while this one waited)
+                    tmp = os.path.join("_build", f"libfenris_cpu_ref.{os.getpid()}.so")
+                    subprocess.check_call(["make", "-C", _HERE, "-s", "-B", f"OUT={tmp}"])
+                    os.replace(os.path.join(_HERE, tmp), _SO)
+                    with open(stamp + f".{os.getpid()}", "w") as f:
+                        f.write(tag)
+                    os.replace(stamp + f".{os.getpid()}", stamp)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
