@@ -203,6 +203,7 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
         // owner stores (see the header comment): flags are compared with this launch's epoch; 0 = the lists carry no ownership or the
         // call accumulates (then every entry is a reduction and nothing is published or waited for)
         const uint32_t epoch = overwrite ? p.tile_epoch : 0u;
+        bool gave_up = false;  // this thread has seen a wait time out (or an error reported by anybody): no more waiting
         // iteration `it`: tables of tiles it + 2 .. it + 4, flush of tile it - 1 (after the compute warps have finished it)
         for (uint32_t it = 0;; ++it) {
             const int sl = (int)(it & 7u), b = (int)(it & 1u), nb = b ^ 1;
@@ -336,12 +337,14 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                                 seen = ld_acquire_u32(fp);
                             }
                             unsigned int spins = 0;
-                            while (seen != epoch) {
+                            // a healthy wait lasts microseconds.  After ~1 s: report and stop waiting - for good, and so does every other
+                            // CTA once the error word is set (the result is invalid anyway; the launch must end, not hang the device)
+                            while (seen != epoch && !gave_up) {
                                 __nanosleep(32);
                                 seen = ld_acquire_u32(fp);
-                                if (++spins > (1u << 24)) {  // > 1 s: never on a healthy launch; report instead of hanging
+                                if (++spins > (1u << 22) || ((spins & 1023u) == 0u && *reinterpret_cast<volatile unsigned long long*>(p.errword) != ~0ull)) {
                                     flag_error(p.errword, (uint64_t)s_tick[(it - 1) & 7u], FB200_ERR_CUDA);
-                                    break;
+                                    gave_up = true;
                                 }
                             }
                             if ((dbg & 64) && spins) {  // diagnostics: blocked waits, their spins, how far back the owner tile is
