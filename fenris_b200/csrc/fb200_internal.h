@@ -104,6 +104,7 @@ struct TileShape {
                            // that touches the node and reduced into by the others once that tile has published its stores - an
                            // overwriting assembly then needs no zero-fill of the values.  0: only tile-complete rows are stored, every
                            // other row is reduced into (the caller zero-fills all values first).
+    int memo = 1;  // 1: tiles with a local connectivity seen before are re-labelled copies (tiles.cpp Builder::Memo); 0: every tile is built
 };
 struct HostTiles {
     BigVec<uint32_t> hdr;        // num_tiles * kTileHdrWords

@@ -75,12 +75,71 @@ struct Builder {
         uint16_t k;
         uint8_t v;
         uint16_t pos;  // accumulator position (v >= u only)
+        uint16_t src;  // el * 64 + a * 8 + b: the block-map entry of the tile that reported k
     };
+    // Everything a tile's lists hold except the global numbers (node ids, element ids, the positions k in the block rows) is a function of
+    // its LOCAL connectivity `ln` alone - `nodes` is sorted, so the local index is monotone in the global id and the CSR order of a row is
+    // the order of the local column indices.  On a structured mesh nearly all tiles share one local connectivity: the lists of a
+    // connectivity seen before are copied and re-labelled instead of being rebuilt (byte-identical result: FB200_DEBUG_SETUP checksum;
+    // FB200_TILE_MEMO=0 switches the table off).
+    struct Memo {
+        uint64_t hash;
+        int ne, nn;
+        std::vector<uint8_t> ln;
+        uint32_t P, rounds;
+        std::vector<uint32_t> flush;      // pos | tr << 11 | u << 12, k = 0
+        std::vector<uint16_t> flush_src;  // where k comes from (RowEntry::src)
+        std::vector<uint8_t> lnodes;
+        std::vector<uint16_t> emap;
+        std::vector<int8_t> elem;  // tile-local element of every schedule position, -1 = padding
+        uint64_t conflicts, accesses;
+    };
+    std::vector<Memo> memo;
+    uint64_t memo_hits = 0;
+    const bool memo_on = [this] {
+        const char* e = std::getenv("FB200_TILE_MEMO");
+        return shape.memo != 0 && !(e && e[0] == '0');
+    }();
+    static constexpr size_t kMemoCap = 64;
+
+    // lists of a known local connectivity; false: not applicable (the caller builds them)
+    bool from_memo(const Memo& m, uint64_t p0, int ne, TileOut& t) {
+        constexpr int n2 = 64;
+        const size_t nf = m.flush.size();
+        t.flush.resize(nf);
+        uint32_t prev_u = 0xffffffffu, prev_k = 0;
+        for (size_t i = 0; i < nf; ++i) {
+            const uint32_t src = m.flush_src[i];
+            const uint32_t k = blockmap[elem_at(p0 + (src >> 6)) * n2 + (src & 63u)];
+            const uint32_t u = (m.flush[i] >> 12) & 0x7fu;
+            if (u == prev_u && k <= prev_k) return false;  // not the CSR order of this row: cannot happen with sorted block rows - rebuild
+            prev_u = u;
+            prev_k = k;
+            if (k >= (1u << kTileKBits)) degenerate = true;
+            t.flush[i] = m.flush[i] | (k << 19);
+        }
+        const int nn = (int)nodes.size();
+        t.p0 = p0;
+        t.ne = ne;
+        t.P = m.P;
+        t.rounds = m.rounds;
+        t.nodes.resize(nn);
+        for (int u = 0; u < nn; ++u) t.nodes[u] = nodes[u] | (inc[u] == degree[nodes[u]] ? (int32_t)0x80000000 : 0);
+        t.lnodes = m.lnodes;
+        t.emap = m.emap;
+        t.elem.resize(m.elem.size());
+        for (size_t i = 0; i < m.elem.size(); ++i) t.elem[i] = m.elem[i] < 0 ? -1 : (int32_t)elem_at(p0 + (uint64_t)m.elem[i]);
+        conflicts += m.conflicts;
+        accesses += m.accesses;
+        ++memo_hits;
+        return true;
+    }
     std::vector<int32_t> nodes;
     std::vector<int> inc;
     std::vector<std::vector<RowEntry>> rows;
     std::vector<std::vector<int>> node_elems;
     std::vector<uint8_t> ln;  // ne * 8
+    std::vector<uint16_t> flush_src;
     std::vector<uint16_t> pair_pos = std::vector<uint16_t>(128 * 128, (uint16_t)0xffffu);  // accumulator position of the pair (u, v), u <= v
     std::vector<uint8_t> pair_seen = std::vector<uint8_t>(128 * 128, (uint8_t)0);           // (u, v) already has a row entry
 
@@ -152,6 +211,17 @@ struct Builder {
             }
         }
         if (degenerate) return true;
+        uint64_t ln_hash = 1469598103934665603ull;
+        if (memo_on) {
+            for (uint8_t x : ln) ln_hash = (ln_hash ^ x) * 1099511628211ull;
+            lap(0);
+            for (const Memo& m : memo)
+                if (m.hash == ln_hash && m.ne == ne && m.nn == nn && m.ln == ln && from_memo(m, p0, ne, t)) {
+                    lap(5);
+                    return true;
+                }
+        }
+        const uint64_t conflicts0 = conflicts, accesses0 = accesses;
         lap(0);
         // ---- rows: coupled nodes of every tile node, ordered by their position k in the global block row
         if ((int)rows.size() < nn) rows.resize(nn);
@@ -166,7 +236,7 @@ struct Builder {
                     uint8_t& seen = pair_seen[u * 128 + v];
                     if (!seen) {
                         seen = 1;
-                        rows[u].push_back({blockmap[e * n2 + a * n + b], (uint8_t)v, 0});
+                        rows[u].push_back({blockmap[e * n2 + a * n + b], (uint8_t)v, 0, (uint16_t)(el * n2 + a * n + b)});
                     }
                 }
             }
@@ -227,8 +297,10 @@ struct Builder {
         for (int u = 0; u < nn; ++u) t.nodes[u] = nodes[u] | (inc[u] == degree[nodes[u]] ? (int32_t)0x80000000 : 0);
         t.flush.clear();
         t.flush.reserve(nflush);
+        flush_src.clear();
         for (int u = 0; u < nn; ++u)
             for (const RowEntry& x : rows[u]) {
+                flush_src.push_back(x.src);
                 uint32_t pos, tr = 0;
                 if (x.v >= u) {
                     pos = x.pos;
@@ -311,6 +383,29 @@ struct Builder {
         lap(4);
         t.rounds = (uint32_t)(t.elem.size() / gw);
         if (t.rounds > 255) return false;  // bound asserted by the self test (cannot happen with <= 64 elements per tile)
+        if (memo_on && !degenerate && memo.size() < kMemoCap) {
+            Memo m;
+            m.hash = ln_hash;
+            m.ne = ne;
+            m.nn = nn;
+            m.ln = ln;
+            m.P = t.P;
+            m.rounds = t.rounds;
+            m.flush = t.flush;
+            for (uint32_t& w : m.flush) w &= (1u << 19) - 1u;
+            m.flush_src = flush_src;
+            m.lnodes = t.lnodes;
+            m.emap = t.emap;
+            m.elem.resize(t.elem.size());
+            {
+                size_t i = 0;
+                int s = 0;
+                for (int32_t e : t.elem) m.elem[i++] = e < 0 ? (int8_t)-1 : (int8_t)sched[s++];
+            }
+            m.conflicts = conflicts - conflicts0;
+            m.accesses = accesses - accesses0;
+            memo.push_back(std::move(m));
+        }
         return true;
     }
 };
@@ -450,7 +545,8 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         conflicts += b.conflicts;
         accesses += b.accesses;
         if (std::getenv("FB200_DEBUG_SETUP"))
-            std::fprintf(stderr, "[fb200 setup]     worker: nodes %.3f rows %.3f positions %.3f flush %.3f schedule %.3f s\n", b.sec[0], b.sec[1], b.sec[2], b.sec[3], b.sec[4]);
+            std::fprintf(stderr, "[fb200 setup]     worker: nodes %.3f rows %.3f positions %.3f flush %.3f schedule %.3f relabel %.3f s\n", b.sec[0], b.sec[1], b.sec[2], b.sec[3], b.sec[4], b.sec[5]),
+                std::fprintf(stderr, "[fb200 setup]     worker: %llu tiles relabelled from %zu known local connectivities\n", (unsigned long long)b.memo_hits, b.memo.size());
     };
     const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     auto run_pool = [&](uint64_t work_items, const std::function<void()>& fn) {
@@ -864,5 +960,17 @@ extern "C" fb200_status fb200_tile_lists_selftest_ex(uint64_t num_nodes, const d
     stats[7] = max_rounds;
     stats[8] = store_entries;
     stats[9] = zero_entries;
+    // ---- the lists do not depend on the memo of local connectivities: built tile by tile they are byte-identical
+    {
+        TileShape plain = shape;
+        plain.memo = 0;
+        HostTiles h2;
+        build_tile_lists(plain, order.size(), order.data(), codes.data(), conn.data(), num_elements, num_owned, num_nodes, map.data(), blk_off.data(), h2);
+        auto same = [](const auto& x, const auto& y) { return x.size() == y.size() && std::equal(x.begin(), x.end(), y.begin()); };
+        if (!same(ht.hdr, h2.hdr) || !same(ht.nodes, h2.nodes) || !same(ht.flush, h2.flush) || !same(ht.wait, h2.wait) || !same(ht.zero_nodes, h2.zero_nodes) ||
+            !same(ht.lnodes, h2.lnodes) || !same(ht.emap, h2.emap) || !same(ht.elem, h2.elem) || !same(ht.colour_off, h2.colour_off) ||
+            !same(ht.colour_tiles, h2.colour_tiles) || ht.bank_conflict_share != h2.bank_conflict_share || ht.zero_entries != h2.zero_entries)
+            return fail_check(38);
+    }
     return FB200_OK;
 }
