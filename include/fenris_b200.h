@@ -275,8 +275,6 @@ fb200_status fb200_gen_quad_mesh(uint64_t cells_x, uint64_t cells_y, double cell
  * (query with vertices27 == NULL). */
 fb200_status fb200_hex27_from_hex8(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* hex8,
                                    uint64_t* num_vertices27, double* vertices27, uint64_t* hex27);
-/* Canonical stiffness quadrature of an element type (src/quadrature/canonical.rs:95,102-104,110-112):
- * query num_points with weights == NULL. points are point-major [num_points * dim]. */
 /* Hex20Mesh::from(&hex8_mesh) (src/mesh_convert.rs:168-217, 481-488): same calling convention as fb200_hex27_from_hex8. */
 fb200_status fb200_hex20_from_hex8(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* hex8,
                                    uint64_t* num_vertices_out, double* vertices_out, uint64_t* hex20);
@@ -284,6 +282,8 @@ fb200_status fb200_hex20_from_hex8(uint64_t num_vertices, const double* vertices
  * (0,2) (0,3) (2,3) (1,3), labelled in first-seen order.  Same calling convention as fb200_hex27_from_hex8. */
 fb200_status fb200_tet10_from_tet4(uint64_t num_vertices, const double* vertices, uint64_t num_elements, const uint64_t* tet4,
                                    uint64_t* num_vertices_out, double* vertices_out, uint64_t* tet10);
+/* Canonical stiffness quadrature of an element type (src/quadrature/canonical.rs:95,102-104,110-112):
+ * query num_points with weights == NULL. points are point-major [num_points * dim]. */
 fb200_status fb200_canonical_quadrature(int32_t element_type, int32_t* num_points, double* weights, double* points);
 /* LameParameters::from(YoungPoisson) (fenris-solid/src/materials.rs:31-43). */
 void fb200_lame_from_young_poisson(double young, double poisson, double* mu, double* lambda);

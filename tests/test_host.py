@@ -53,6 +53,26 @@ def test_no_cpu_fallback_without_gpu():
         fb.color_nodes(mesh)
 
 
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """The boundary is a C ABI: include/fenris_b200.h must compile as C99 (what cgo / bindgen / JNI headers consume), and the plain C
+    program examples/assemble_csr.c must link against the library with nothing but gcc.  Without a device it has to fail loudly at
+    fb200_create (exit code 3) - there is no CPU path behind the ABI."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "assemble_csr")
+    libdir = os.path.join(ROOT, "fenris_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "assemble_csr.c"), "-L", libdir, "-lfenris_b200", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")  # also on a GPU box: this test is about the failure path
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 3, (r.returncode, r.stdout, r.stderr)
+    assert "fb200_create" in r.stderr and "CUDA" in r.stderr
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "fenris_b200")
     for dirpath, _, files in os.walk(pkg):
