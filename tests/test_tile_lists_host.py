@@ -110,3 +110,22 @@ def test_owner_lists_on_unstructured_numbering_and_partitions():
         for owner in (0, 1):
             st, failed, s = _selftest_ex(verts, conn, owner, owned=n_owned)
             assert st == nat.OK, f"rank {rank}: check {failed} failed"
+
+
+@pytest.mark.parametrize("seed,keep", [(0, 0.7), (1, 0.4), (2, 0.9)])
+def test_perforated_meshes_many_local_connectivities(seed, keep):
+    """Cubes with a random subset of the elements removed (unused nodes stay in the space): partial tiles of every shape, i.e. many
+    different tile-local connectivities - some repeated, most not.  Besides the list invariants this exercises the memo of local
+    connectivities both ways (check 38 of the self test rebuilds every tile without it and compares all arrays)."""
+    m = fb.create_unit_box_uniform_hex_mesh_3d(14)
+    rng = np.random.default_rng(seed)
+    c = m.connectivity()[rng.random(m.num_elements()) < keep]
+    for owner in (0, 1):
+        st, failed, s = _selftest_ex(m.vertices(), c, owner)
+        assert st == nat.OK, f"check {failed} failed"
+        assert s[6] >= len(c)
+    # and as a partition: the removed elements' neighbours of the upper half are ghosts
+    half = c[:, 0] < np.median(c[:, 0])
+    cc = np.concatenate([c[half], c[~half]])
+    st, failed, s = _selftest_ex(m.vertices(), cc, 1, owned=int(half.sum()))
+    assert st == nat.OK, f"check {failed} failed"
