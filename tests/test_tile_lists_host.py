@@ -112,7 +112,7 @@ def test_owner_lists_on_unstructured_numbering_and_partitions():
             assert st == nat.OK, f"rank {rank}: check {failed} failed"
 
 
-@pytest.mark.parametrize("seed,keep", [(0, 0.7), (1, 0.4), (2, 0.9)])
+@pytest.mark.parametrize("seed,keep", [(0, 0.7), (1, 0.4), (2, 0.9), (3, 0.995)])
 def test_perforated_meshes_many_local_connectivities(seed, keep):
     """Cubes with a random subset of the elements removed (unused nodes stay in the space): partial tiles of every shape, i.e. many
     different tile-local connectivities - some repeated, most not.  Besides the list invariants this exercises the memo of local
