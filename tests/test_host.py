@@ -53,6 +53,17 @@ def test_no_cpu_fallback_without_gpu():
         fb.color_nodes(mesh)
 
 
+def test_integration_binding_lists_every_entry_point():
+    """INTEGRATION.md's `extern "C"` block (the Rust -sys crate a maintainer would add) names exactly the functions the header declares."""
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = txt[txt.index('extern "C" {'):txt.index("`usize == u64`")]
+    bound = set(re.findall(r"pub fn (fb200_[a-z0-9_]+)", blk))
+    assert bound == set(nat.declared_symbols())
+    hdr = open(os.path.join(ROOT, "include", "fenris_b200.h")).read()
+    for name, value in re.findall(r"\b(FB200_(?:ERR_[A-Z_]+|OK))\s*=\s*(\d+)", hdr):
+        assert re.search(rf"pub const {name}: i32 = {value};", txt), name
+
+
 def test_header_is_plain_c_and_the_c_example_links(tmp_path):
     """The boundary is a C ABI: include/fenris_b200.h must compile as C99 (what cgo / bindgen / JNI headers consume), and the plain C
     program examples/assemble_csr.c must link against the library with nothing but gcc.  Without a device it has to fail loudly at
