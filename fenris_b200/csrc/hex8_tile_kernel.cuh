@@ -342,9 +342,11 @@ __global__ void __launch_bounds__((2 * kTileGroupWarps + kTileHelperWarps) * 32,
                             while (seen != epoch && !gave_up) {
                                 __nanosleep(32);
                                 seen = ld_acquire_u32(fp);
-                                if (++spins > (1u << 22) || ((spins & 1023u) == 0u && *reinterpret_cast<volatile unsigned long long*>(p.errword) != ~0ull)) {
+                                if (++spins > (1u << 22)) {
                                     flag_error(p.errword, (uint64_t)s_tick[(it - 1) & 7u], FB200_ERR_CUDA);
                                     gave_up = true;
+                                } else if ((spins & 1023u) == 0u && *reinterpret_cast<volatile unsigned long long*>(p.errword) != ~0ull) {
+                                    gave_up = true;  // somebody else's error (it keeps its own code and element)
                                 }
                             }
                             if ((dbg & 64) && spins) {  // diagnostics: blocked waits, their spins, how far back the owner tile is
