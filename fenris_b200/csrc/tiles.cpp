@@ -486,8 +486,17 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
     // incidences of every node over ALL elements of the space - also the ghost elements of a partition, which are in the pattern
     // but are not assembled here: a node is complete only if every element it belongs to is processed inside one tile (then
     // the flush writes every entry of its rows)
+    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    std::atomic<uint64_t> next{0};
+    auto run_pool = [&](uint64_t work_items, const std::function<void()>& fn) {
+        const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, work_items / 64));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(fn);
+        fn();
+        for (auto& th : pool) th.join();
+    };
     std::vector<int32_t> degree(num_nodes, 0), degree_owned(num_nodes, 0);
-    for (uint64_t e = 0; e < num_elements; ++e)
+    for (uint64_t e = 0; e < num_elements; ++e)  // (atomic increments from a thread pool: slower than this loop on the 8-core build host)
         for (int a = 0; a < n; ++a) {
             ++degree[conn[e * n + a]];
             if (e < num_owned) ++degree_owned[conn[e * n + a]];
@@ -512,7 +521,6 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
         p0 += ne;
     }
     std::vector<std::vector<TileOut>> results(cand.size());
-    std::atomic<uint64_t> next{0};
     std::atomic<uint64_t> conflicts{0}, accesses{0};
     std::atomic<bool> degenerate{false};
     auto worker = [&]() {
@@ -548,14 +556,6 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
             std::fprintf(stderr, "[fb200 setup]     worker: nodes %.3f rows %.3f positions %.3f flush %.3f schedule %.3f relabel %.3f s\n", b.sec[0], b.sec[1], b.sec[2], b.sec[3], b.sec[4], b.sec[5]),
                 std::fprintf(stderr, "[fb200 setup]     worker: %llu tiles relabelled from %zu known local connectivities\n", (unsigned long long)b.memo_hits, b.memo.size());
     };
-    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-    auto run_pool = [&](uint64_t work_items, const std::function<void()>& fn) {
-        const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, work_items / 64));
-        std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(fn);
-        fn();
-        for (auto& th : pool) th.join();
-    };
     tm.lap("  tile lists: degrees + candidates");
     run_pool(cand.size(), worker);
     tm.lap("  tile lists: pass 1 (per tile)");
@@ -571,11 +571,21 @@ void build_tile_lists(const TileShape& shape, uint64_t count, const int32_t* ord
     std::vector<uint32_t> owner_tile;
     if (out.owner_stores) {
         owner_tile.assign(num_nodes, 0xffffffffu);
-        for (size_t ti = 0; ti < tiles.size(); ++ti)
-            for (int32_t nd : tiles[ti]->nodes) {
-                uint32_t& o = owner_tile[nd & 0x7fffffff];
-                if (o == 0xffffffffu) o = (uint32_t)ti;
+        next.store(0);
+        auto claim = [&]() {  // lowest tile number per node: an atomic minimum gives what the in-order loop gives
+            for (;;) {
+                const uint64_t t0 = next.fetch_add(64);
+                if (t0 >= tiles.size()) break;
+                for (uint64_t ti = t0; ti < std::min<uint64_t>(tiles.size(), t0 + 64); ++ti)
+                    for (int32_t nd : tiles[ti]->nodes) {
+                        uint32_t* o = &owner_tile[nd & 0x7fffffff];
+                        uint32_t cur = __atomic_load_n(o, __ATOMIC_RELAXED);
+                        while ((uint32_t)ti < cur && !__atomic_compare_exchange_n(o, &cur, (uint32_t)ti, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                        }
+                    }
             }
+        };
+        run_pool(tiles.size(), claim);
         for (uint64_t i = 0; i < num_nodes; ++i)
             if (owner_tile[i] == 0xffffffffu || degree[i] != degree_owned[i]) out.zero_nodes.push_back((int32_t)i);
     }
